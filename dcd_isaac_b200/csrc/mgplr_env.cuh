@@ -1,0 +1,423 @@
+// mgplr_env.cuh -- device-side MultiGrid adversarial-maze semantics for sm_100a.
+//
+// State layout in HBM: the maze is a bit-packed uint8 grid -- one wall bit per
+// cell, row y of env e in the 32-bit word wall[y*N + e] (rows are struct-of-arrays across envs so a
+// warp of 32 envs reads 128 contiguous bytes per row) -- plus one 16-byte "hot" record per env with
+// the agent / goal / start coordinates and the episode counters.  Cell codes other than wall are
+// coordinates, not cells: goal (gx,gy), agent (ax,ay,dir), start (sx,sy,sdir).
+//
+// Every function cites the reference file:line whose behaviour it reproduces (paths relative to the
+// reference root); gym-minigrid 1.0.1 / gym 0.15.7 / numpy legacy RandomState pieces are third-party
+// and are implemented from their published algorithms.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mgplr.h"
+
+namespace mgplr {
+
+constexpr int kV = 5;             // agent_view_size of every registered adversarial env (adversarial.py:71)
+constexpr int kNone = 63;         // coordinate sentinel for "None"
+constexpr int kObsFloats = 3 * kV * kV;
+constexpr uint32_t kErrRetries = 1u, kErrNoStart = 2u, kErrBadLoc = 4u;
+
+struct Cfg {
+  int W, max_steps, max_episode_steps, see_through, n_clutter, resample, goal_last, fixed_env, n_editor;
+};
+
+// Device view of one venv (all pointers are HBM).
+struct Dev {
+  int N;
+  Cfg c;
+  uint32_t *wall;    // [W][N] wall bit-plane rows (bit x of row y)
+  uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx6|gy6|sx6|sy6|sdir2  z: elapsed16|eplen16  w: ep_ret bits
+  uint32_t *adv;     // [N] adversary_step_count12 | adversary_max_steps12 | n_clutter_sampled1
+  int4 *metrics;     // [N] n_clutter_placed, distance_to_goal, passable, shortest_path_length
+  uint32_t *mt;      // [624][N] MT19937 state (numpy RandomState of each env)
+  uint32_t *mti;     // [N] index of the next word to generate (incremental twist), 0..623
+  uint32_t *limbs;   // [3][N] seed limbs lo, hi, count (re-seed of fixed_environment)
+  uint32_t *words;   // [N] MT words consumed since seeding
+  uint32_t *err;     // [N] sticky error bits
+};
+
+struct Env {
+  int ax, ay, adir, has_agent, done_flag, step_count;
+  int gx, gy, sx, sy, sdir;
+  int elapsed, ep_len;
+  float ep_ret;
+};
+
+__device__ __forceinline__ Env unpack(const uint4 h) {
+  Env e;
+  e.ax = h.x & 63; e.ay = (h.x >> 6) & 63; e.adir = (h.x >> 12) & 3; e.has_agent = (h.x >> 14) & 1;
+  e.done_flag = (h.x >> 15) & 1; e.step_count = h.x >> 16;
+  e.gx = h.y & 63; e.gy = (h.y >> 6) & 63; e.sx = (h.y >> 12) & 63; e.sy = (h.y >> 18) & 63; e.sdir = (h.y >> 24) & 3;
+  e.elapsed = h.z & 0xffff; e.ep_len = h.z >> 16;
+  e.ep_ret = __uint_as_float(h.w);
+  return e;
+}
+__device__ __forceinline__ uint4 pack(const Env &e) {
+  uint4 h;
+  h.x = (uint32_t)e.ax | ((uint32_t)e.ay << 6) | ((uint32_t)e.adir << 12) | ((uint32_t)e.has_agent << 14) |
+        ((uint32_t)e.done_flag << 15) | ((uint32_t)e.step_count << 16);
+  h.y = (uint32_t)e.gx | ((uint32_t)e.gy << 6) | ((uint32_t)e.sx << 12) | ((uint32_t)e.sy << 18) | ((uint32_t)e.sdir << 24);
+  h.z = ((uint32_t)e.elapsed & 0xffff) | ((uint32_t)e.ep_len << 16);
+  h.w = __float_as_uint(e.ep_ret);
+  return h;
+}
+
+// Wall rows of one env: shared memory (stride = tile size) in the hot kernels, HBM (stride = N) elsewhere.
+struct Rows {
+  uint32_t *p;
+  int stride;
+  __device__ __forceinline__ uint32_t get(int r) const { return p[r * stride]; }
+  __device__ __forceinline__ void set(int r, uint32_t v) const { p[r * stride] = v; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// numpy legacy RandomState == MT19937, generated incrementally: word i of the next generation is
+// x[i+397] ^ twist(x[i], x[i+1]) and only depends on already-updated words when produced in order, so
+// producing one word per draw in place is output-identical to the batch twist and never stalls a
+// lane for 624 dependent iterations.
+struct Rng {
+  uint32_t *mt;
+  int N, e;
+  uint32_t idx, used;
+  bool loaded;
+  const Dev *d;
+  __device__ Rng(const Dev &dev, int env) : mt(dev.mt), N(dev.N), e(env), idx(0), used(0), loaded(false), d(&dev) {}
+  __device__ __forceinline__ void load() {
+    if (!loaded) { idx = d->mti[e]; used = d->words[e]; loaded = true; }
+  }
+  __device__ __forceinline__ void store() {
+    if (loaded) { d->mti[e] = idx; d->words[e] = used; }
+  }
+  __device__ uint32_t next() {
+    load();
+    const uint32_t i = idx;
+    const uint32_t i1 = (i + 1 == 624) ? 0 : i + 1;
+    const uint32_t im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
+    const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    mt[(size_t)i * N + e] = y;
+    idx = i1;
+    used++;
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  // RandomState.randint(lo, hi): masked rejection on 32-bit words, no draw when hi-lo == 1
+  // (gym_minigrid MiniGridEnv._rand_int; call sites multigrid.py:603-606, adversarial.py:205,567).
+  __device__ int randint(int lo, int hi) {
+    const uint32_t rng = (uint32_t)(hi - lo - 1);
+    if (rng == 0) return lo;
+    const uint32_t mask = 0xffffffffu >> __clz(rng);
+    uint32_t v;
+    do { v = next() & mask; } while (v > rng);
+    return lo + (int)v;
+  }
+};
+
+// MT19937 init_by_array for one env (RandomState.seed([lo, hi])), SoA state.
+__device__ __noinline__ void mt_seed(const Dev &d, int e, uint32_t k0, uint32_t k1, int klen) {
+  uint32_t *mt = d.mt;
+  const size_t N = d.N;
+  uint32_t prev = 19650218u;
+  mt[e] = prev;
+  for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; mt[(size_t)i * N + e] = prev; }
+  int i = 1, j = 0;
+  prev = mt[e];
+  for (int k = 624; k; k--) {
+    const uint32_t key = (j == 0) ? k0 : k1;
+    uint32_t v = (mt[(size_t)i * N + e] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key + (uint32_t)j;
+    mt[(size_t)i * N + e] = v; prev = v;
+    i++; j++;
+    if (i >= 624) { mt[e] = prev; i = 1; }
+    if (j >= klen) j = 0;
+  }
+  for (int k = 623; k; k--) {
+    uint32_t v = (mt[(size_t)i * N + e] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
+    mt[(size_t)i * N + e] = v; prev = v;
+    i++;
+    if (i >= 624) { mt[e] = prev; i = 1; }
+  }
+  mt[e] = 0x80000000u;
+  d.mti[e] = 0;  // numpy's mti = 624 ("regenerate everything") == incremental index 0
+  d.words[e] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_wall(const Rows &R, int x, int y) { return (R.get(y) >> x) & 1u; }
+
+// grid.get(x, y) is None: no wall, no goal, no agent object (agent object sits at the agent's cell)
+__device__ __forceinline__ bool is_empty(const Rows &R, const Env &e, int x, int y) {
+  return !is_wall(R, x, y) && !(x == e.gx && y == e.gy) && !(e.has_agent && x == e.ax && y == e.ay);
+}
+
+// AdversarialEnv._gen_grid (adversarial.py:166-172): empty grid + wall_rect border.
+__device__ inline void gen_grid(const Rows &R, int W) {
+  const uint32_t full = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
+  const uint32_t mid = 1u | (1u << (W - 1));
+  R.set(0, full);
+  for (int r = 1; r < W - 1; r++) R.set(r, mid);
+  R.set(W - 1, full);
+}
+
+// place_obj over the whole grid (multigrid.py:565-632): x=_rand_int(0,W), y=_rand_int(0,H); reject
+// non-empty cells; raise after max_tries (max_tries < 0: unbounded).
+__device__ __noinline__ bool place_random(const Rows &R, const Env &e, Rng &rng, int W, int max_tries, int &ox, int &oy) {
+  int tries = 0;
+  for (;;) {
+    if (max_tries >= 0 && tries > max_tries) return false;
+    tries++;
+    const int x = rng.randint(0, W), y = rng.randint(0, W);
+    if (!is_empty(R, e, x, y)) continue;
+    ox = x; oy = y;
+    return true;
+  }
+}
+
+// reset_metrics + compute_metrics (adversarial.py:184-192,407-447): interior wall count, Manhattan
+// distance, and reachability / hop count by a bit-parallel flood fill over the interior rows.
+__device__ __noinline__ int4 compute_metrics(const Rows &R, const Env &e, int W, bool do_reset) {
+  int4 m;
+  const int unreachable = (W - 2) * (W - 2) + 1;
+  const uint32_t interior = ((W >= 32) ? 0xffffffffu : ((1u << W) - 1u)) & ~1u & ~(1u << (W - 1));
+  int n = 0;
+  for (int y = 1; y < W - 1; y++) n += __popc(R.get(y) & interior);
+  m.x = n; m.y = -1; m.z = -1; m.w = unreachable;
+  (void)do_reset;
+  if (e.sx == kNone || e.gx == kNone) return m;
+  m.y = abs(e.gx - e.sx) + abs(e.gy - e.sy);
+  uint32_t reach[32], nxt[32];
+  for (int y = 0; y < W; y++) reach[y] = 0;
+  reach[e.sy] = 1u << e.sx;
+  m.z = 0;
+  if (e.sx == e.gx && e.sy == e.gy) { m.z = 1; m.w = 0; return m; }
+  for (int d = 1; d <= unreachable; d++) {
+    bool grew = false;
+    for (int y = 1; y < W - 1; y++) {
+      const uint32_t r = reach[y];
+      uint32_t v = (r | (r << 1) | (r >> 1) | reach[y - 1] | reach[y + 1]) & ~R.get(y) & interior;
+      nxt[y] = v;
+      grew |= (v != r);
+    }
+    for (int y = 1; y < W - 1; y++) reach[y] = nxt[y];
+    if ((reach[e.gy] >> e.gx) & 1u) { m.z = 1; m.w = d; return m; }
+    if (!grew) break;
+  }
+  return m;
+}
+
+// reset_agent (adversarial.py:238-269) + TimeLimit.reset_agent (time_limit.py:46-48).
+__device__ __forceinline__ bool reset_agent(Env &e) {
+  e.has_agent = 0; e.adir = e.sdir; e.done_flag = 0;  // reset_agent_status (adversarial.py:231-236)
+  if (e.sx == kNone) return false;                     // ValueError at adversarial.py:248-249
+  e.has_agent = 1; e.ax = e.sx; e.ay = e.sy;
+  e.step_count = 0; e.elapsed = 0;
+  return true;
+}
+
+// AdversarialEnv.reset (adversarial.py:194-229).
+__device__ inline void reset_adversary(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Cfg &c) {
+  e.step_count = 0;
+  uint32_t adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
+  if (c.resample) sampled = 0;
+  adv = 0u | (adv_max << 12) | (sampled << 24);
+  e.sdir = rng.randint(0, 4);
+  e.has_agent = 0; e.adir = e.sdir; e.done_flag = 0;
+  e.sx = e.sy = kNone; e.gx = e.gy = kNone;
+  met = make_int4(0, -1, -1, (c.W - 2) * (c.W - 2) + 1);
+  gen_grid(R, c.W);
+}
+
+// step_adversary (adversarial.py:452-539), goal_noise == 0.  Returns done.
+__device__ inline bool step_adversary(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Cfg &c, int loc,
+                                      uint32_t &err) {
+  const int W = c.W, I = W - 2, A = I * I;
+  if (loc < 0 || loc >= A) { err |= kErrBadLoc; return false; }
+  int adv_step = adv & 0xfff, adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
+  if (c.resample && !sampled) {
+    adv_max = (int)(((double)loc / (double)A) * (double)c.n_clutter) + 2;
+    sampled = 1;
+  }
+  if (adv_step < adv_max) {
+    const int x = loc % I + 1, y = loc / I + 1;
+    const bool goal_step = c.goal_last ? (adv_step == adv_max - 2) : (adv_step == 0);
+    const bool agent_step = c.goal_last ? (adv_step == adv_max - 1) : (adv_step == 1);
+    if (goal_step) {  // remove_wall + put_obj(Goal)
+      R.set(y, R.get(y) & ~(1u << x));
+      e.gx = x; e.gy = y;
+    } else if (agent_step) {
+      R.set(y, R.get(y) & ~(1u << x));  // remove_wall
+      if (x == e.gx && y == e.gy) {     // goal already here -> place_one_agent(0, rand_dir=False)
+        int px = 0, py = 0;
+        e.has_agent = 0;
+        place_random(R, e, rng, W, -1, px, py);
+        e.sx = px; e.sy = py;
+      } else { e.sx = x; e.sy = y; }
+      e.has_agent = 1; e.ax = e.sx; e.ay = e.sy;
+    } else if (is_empty(R, e, x, y)) {
+      R.set(y, R.get(y) | (1u << x));
+    }
+  }
+  adv_step++;
+  adv = (uint32_t)adv_step | ((uint32_t)adv_max << 12) | ((uint32_t)sampled << 24);
+  if (adv_step >= c.n_clutter + 2) { met = compute_metrics(R, e, W, true); return true; }
+  return false;
+}
+
+// reset_random (adversarial.py:541-581).  n_walls < 0 -> int(n_clutter/2).
+__device__ __noinline__ void reset_random(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Dev &d, int env,
+                                    int n_walls, uint32_t &err) {
+  const Cfg &c = d.c;
+  const int W = c.W;
+  if (c.fixed_env) {  // self.seed(self.seed_value) (adversarial.py:542-543)
+    mt_seed(d, env, d.limbs[env], d.limbs[(size_t)d.N + env], (int)d.limbs[2 * (size_t)d.N + env]);
+    rng.loaded = false;
+  }
+  e.step_count = 0;
+  uint32_t adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
+  e.has_agent = 0; e.adir = e.sdir; e.done_flag = 0;
+  e.sx = e.sy = kNone; e.gx = e.gy = kNone;
+  gen_grid(R, W);
+  int x = 0, y = 0;
+  if (!place_random(R, e, rng, W, 100, x, y)) err |= kErrRetries;
+  e.gx = x; e.gy = y;
+  e.sdir = rng.randint(0, 4);
+  place_random(R, e, rng, W, -1, x, y);
+  e.sx = x; e.sy = y; e.has_agent = 1; e.ax = x; e.ay = y;
+  if (n_walls < 0) n_walls = c.n_clutter / 2;
+  else { adv_max = (uint32_t)n_walls + 2; sampled = 1; }  // _resample_n_clutter (adversarial.py:151-156)
+  for (int i = 0; i < n_walls; i++) {
+    if (!place_random(R, e, rng, W, 100, x, y)) { err |= kErrRetries; break; }
+    R.set(y, R.get(y) | (1u << x));
+  }
+  adv = 0u | (adv_max << 12) | (sampled << 24);
+  met = compute_metrics(R, e, W, true);
+  if (!reset_agent(e)) err |= kErrNoStart;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Egocentric view (multigrid.py:977-1055 gen_obs_grid/gen_agent_obs, 320-338 slice, 300-318
+// rotate_left, 749-782 get_view_exts; gym_minigrid Grid.process_vis / encode).
+//
+// image[vx][vy] = cell((ax,ay) + f*(V-1-vy) + r*(vx-V/2)), f = DIR_TO_VEC[dir], r = (-f.y, f.x);
+// out of bounds = wall.  Rows of the view are built as 5-bit masks (bit vx) from the wall bit-plane.
+// Returns wall masks w[vy], visibility masks vis[vy] and the goal's view cell (gvx,gvy) or (-1,-1).
+struct View {
+  uint32_t w[kV], vis[kV];
+  int gvx, gvy;
+};
+
+template <bool SEE_THROUGH>
+__device__ __forceinline__ View render_view(const Rows &R, const Env &e, int W) {
+  View v;
+  // 64-bit extended rows: bit (x+8) of E = wall at x, everything outside [0,W) is wall
+  const int d = e.adir;
+  const bool vertical = d & 1;             // facing down/up: view rows are world rows
+  const int sgn = (d == 0 || d == 1) ? 1 : -1;  // forward sign along its axis
+  uint64_t E[kV];
+#pragma unroll
+  for (int k = 0; k < kV; k++) {
+    // vertical: world row for view row vy=k is ay + sgn*(4-k); horizontal: world row for view column vx=k
+    // is ay + ry*(k-2) with r = (-f.y, f.x): dir 0 -> r=(0,1) ; dir 2 -> r=(0,-1)
+    const int wy = vertical ? (e.ay + sgn * (kV - 1 - k)) : (e.ay + sgn * (k - kV / 2));
+    uint64_t row = ~0ull;
+    if (wy >= 0 && wy < W) row = ((uint64_t)R.get(wy) << 8) | 0xffull | (~0ull << (W + 8));
+    E[k] = row;
+  }
+#pragma unroll
+  for (int vy = 0; vy < kV; vy++) {
+    uint32_t m = 0;
+    if (vertical) {
+      // wx for vx: dir 3 (up): ax + (vx-2) ; dir 1 (down): r = (-1,0): ax - (vx-2)
+      const uint32_t five = (uint32_t)(E[vy] >> (e.ax - 2 + 8)) & 31u;
+      m = (d == 3) ? five : (__brev(five) >> 27);
+    } else {
+      const int wx = e.ax + sgn * (kV - 1 - vy);
+#pragma unroll
+      for (int vx = 0; vx < kV; vx++) m |= (uint32_t)((E[vx] >> (wx + 8)) & 1ull) << vx;
+    }
+    v.w[vy] = m;
+  }
+  // goal in view coordinates: fd = (g-a).f, lt = (g-a).r
+  {
+    const int dx = e.gx - e.ax, dy = e.gy - e.ay;
+    int fd, lt;
+    if (d == 0) { fd = dx; lt = dy; } else if (d == 1) { fd = dy; lt = -dx; }
+    else if (d == 2) { fd = -dx; lt = -dy; } else { fd = -dy; lt = dx; }
+    const int gvy = kV - 1 - fd, gvx = lt + kV / 2;
+    const bool in = (e.gx != kNone) && gvx >= 0 && gvx < kV && gvy >= 0 && gvy < kV;
+    v.gvx = in ? gvx : -1; v.gvy = in ? gvy : -1;
+  }
+  if (SEE_THROUGH) {
+#pragma unroll
+    for (int j = 0; j < kV; j++) v.vis[j] = 31u;
+  } else {
+    // gym_minigrid Grid.process_vis(agent_pos=(V/2, V-1)), the two sweeps per row as bit closures
+    uint32_t m = 1u << (kV / 2);
+#pragma unroll
+    for (int j = kV - 1; j >= 0; j--) {
+      const uint32_t open = ~v.w[j] & 31u;
+      uint32_t P = m;
+#pragma unroll
+      for (int it = 0; it < kV - 1; it++) P |= ((P & open) << 1) & 31u;   // left -> right, i = 0..V-2
+      const uint32_t srcL = P & open & 15u;
+      uint32_t nxt = srcL | (srcL << 1);
+      uint32_t Q = P;
+#pragma unroll
+      for (int it = 0; it < kV - 1; it++) Q |= (Q & open) >> 1;           // right -> left, i = V-1..1
+      const uint32_t srcR = Q & open & 30u;
+      nxt |= srcR | (srcR >> 1);
+      v.vis[j] = Q;
+      m = nxt;
+    }
+  }
+  return v;
+}
+
+// cell code of view cell (vx,vy): 0 unseen, 1 empty, 2 wall, 3 goal
+__device__ __forceinline__ int view_code(const View &v, int vx, int vy) {
+  if (!((v.vis[vy] >> vx) & 1u)) return 0;
+  if (vx == kV / 2 && vy == kV - 1) return 1;  // the agent's own cell is blanked (multigrid.py:1009-1013)
+  if ((v.w[vy] >> vx) & 1u) return 2;
+  if (vx == v.gvx && vy == v.gvy) return 3;
+  return 1;
+}
+
+// float32(uint8 / 10.0) for the codes that occur (obs_wrappers.py:104-110): type 0,1,2,8 ; colour 0,0,5,1
+__device__ __forceinline__ float type_f(int code) { return code == 0 ? 0.0f : code == 1 ? 0.1f : code == 2 ? 0.2f : 0.8f; }
+__device__ __forceinline__ float color_f(int code) { return code == 2 ? 0.5f : code == 3 ? 0.1f : 0.0f; }
+
+// write the preprocessed observation [3][5][5] (c, vx, vy) to `o` (shared or global)
+__device__ __forceinline__ void emit_obs_f32(const View &v, float *o) {
+#pragma unroll
+  for (int vx = 0; vx < kV; vx++)
+#pragma unroll
+    for (int vy = 0; vy < kV; vy++) {
+      const int code = view_code(v, vx, vy);
+      o[vx * kV + vy] = type_f(code);
+      o[kV * kV + vx * kV + vy] = color_f(code);
+      o[2 * kV * kV + vx * kV + vy] = 0.0f;
+    }
+}
+// raw gym_minigrid encoding [vx][vy][3]
+__device__ __forceinline__ void emit_obs_u8(const View &v, uint8_t *o) {
+#pragma unroll
+  for (int vx = 0; vx < kV; vx++)
+#pragma unroll
+    for (int vy = 0; vy < kV; vy++) {
+      const int code = view_code(v, vx, vy);
+      uint8_t *p = o + (vx * kV + vy) * 3;
+      p[0] = code == 0 ? 0 : code == 1 ? 1 : code == 2 ? 2 : 8;
+      p[1] = code == 2 ? 5 : code == 3 ? 1 : 0;
+      p[2] = 0;
+    }
+}
+
+}  // namespace mgplr

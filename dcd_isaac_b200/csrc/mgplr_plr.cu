@@ -1,0 +1,369 @@
+// mgplr_plr.cu -- rollout math of the PLR path on sm_100a: GAE (algos/storage.py:233-256), per-episode
+// score reduction (level_replay/level_sampler.py:486-549,307-349), rank/staleness sample weights
+// (level_sampler.py:726-785) and sequential replay sampling (level_sampler.py:664-680,601-604).
+//
+// All rollout tensors are [T or T+1][N] with the actor index fastest (RolloutStorage's [T,N,1]), so one
+// thread per actor walking the time axis reads 128 contiguous bytes per warp per step.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mgplr.h"
+
+extern "C" int mgplr_set_error_(int code, const char *msg);  // mgplr_venv.cu (shared last-error slot)
+static int pfail(int code, const char *msg) { return mgplr_set_error_(code, msg); }
+#define PCK(call)                                                        \
+  do {                                                                   \
+    cudaError_t _e = (call);                                             \
+    if (_e != cudaSuccess) return pfail((int)_e, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ GAE
+// delta = r[t] + gamma*v[t+1]*m[t+1] - v[t];  gae = delta + (gamma*lambda)*m[t+1]*gae;  ret[t] = gae + v[t]
+// evaluated in float32 with one rounding per operation, in the reference's operand order (no FMA
+// contraction), so the result is bit-identical to the torch CPU ops of algos/storage.py:251-256.
+__global__ void k_gae(const float *__restrict__ rewards, const float *__restrict__ values, const float *__restrict__ masks,
+                      float *__restrict__ returns, int T, int N, float gamma, float gl) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  float gae = 0.0f;
+  float v_next = values[(size_t)T * N + e];
+  for (int t = T - 1; t >= 0; t--) {
+    const float r = rewards[(size_t)t * N + e], m = masks[(size_t)(t + 1) * N + e], v = values[(size_t)t * N + e];
+    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, v_next), m)), v);
+    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, m), gae));
+    returns[(size_t)t * N + e] = __fadd_rn(gae, v);
+    v_next = v;
+  }
+}
+
+// gamma / gae_lambda are the Python floats (doubles): `gamma*value_preds` casts gamma to float32, while
+// `gamma * gae_lambda * masks` multiplies the two in double FIRST and casts the product (storage.py:252,255).
+extern "C" int mgplr_gae(const float *rewards, const float *value_preds, const float *masks, float *returns, int32_t T,
+                         int32_t N, double gamma, double gae_lambda, void *stream) {
+  if (!rewards || !value_preds || !masks || !returns || T < 1 || N < 1) return pfail(MGPLR_E_BADARG, "mgplr_gae: bad arguments");
+  k_gae<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, value_preds, masks, returns, T, N, (float)gamma,
+                                                          (float)(gamma * gae_lambda));
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ episode scores
+// done[t] = !(masks[t] > 0) for t in 0..T.  An episode is [start_t, t) for every done step t >= 1
+// (t == 0 is skipped WITHOUT moving start_t, level_sampler.py:504-505).
+__global__ void k_count_episodes(const float *__restrict__ masks, int T, int N, int32_t *__restrict__ counts) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  int c = 0;
+  for (int t = 1; t <= T; t++) c += !(masks[(size_t)t * N + e] > 0.f);
+  counts[e] = c;
+}
+
+// single-CTA exclusive scan over actors (canonical actor-major record order)
+__global__ void k_scan_counts(const int32_t *__restrict__ counts, int N, int32_t *__restrict__ offsets, int32_t *__restrict__ total) {
+  __shared__ int32_t warp_sums[32];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int32_t v = (i < N) ? counts[i] : 0;
+    int32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int32_t w = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      warp_sums[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int32_t warp_prefix = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+    if (i < N) offsets[i] = carry + warp_prefix + x - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += warp_prefix + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_episode_scores(const float *__restrict__ masks, const float *__restrict__ cliff, const float *__restrict__ returns,
+                                 const float *__restrict__ values, const float *__restrict__ rewards,
+                                 const int32_t *__restrict__ seeds, int T, int N, int strategy,
+                                 const int32_t *__restrict__ offsets, mgplr_episode *__restrict__ out, int max_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  int k = offsets[e];
+  int start = 0;
+  double sum = 0.0, vsum = 0.0;
+  float mx = -INFINITY, rsum = 0.f, vmin = INFINITY;
+  for (int t = 0; t < T; t++) {
+    // accumulate step t into the running episode [start, ...)
+    const float ret = returns ? returns[(size_t)t * N + e] : 0.f, v = values[(size_t)t * N + e], r = rewards[(size_t)t * N + e];
+    float a = ret - v;
+    if (strategy == MGPLR_SCORE_POSITIVE_VALUE_LOSS) a = fmaxf(a, 0.f);
+    else if (strategy == MGPLR_SCORE_VALUE_L1) a = fabsf(a);
+    sum += (double)a; mx = fmaxf(mx, a);
+    rsum += r;  // torch sums the f32 rewards of the slice (level_sampler.py:534)
+    vsum += (double)v; vmin = fminf(vmin, v);
+    // done at t+1 closes the episode [start, t+1)
+    if (!(masks[(size_t)(t + 1) * N + e] > 0.f)) {
+      const int t_end = t + 1;
+      if (k < max_out) {
+        mgplr_episode ep;
+        ep.actor = e; ep.t_start = start; ep.t_end = t_end; ep.seed = seeds ? seeds[(size_t)start * N + e] : -1;
+        const int n = t_end - start;
+        ep.mean_score = (float)(sum / (double)n); ep.max_score = mx; ep.reward_sum = rsum;
+        ep.value_sum = (float)vsum; ep.value_min = vmin;
+        ep.cliffhanger = cliff ? !(cliff[(size_t)t_end * N + e] > 0.f) : 0;
+        out[k] = ep;
+      }
+      k++;
+      start = t_end; sum = 0.0; vsum = 0.0; mx = -INFINITY; rsum = 0.f; vmin = INFINITY;
+    }
+  }
+}
+
+static int32_t *g_scratch = nullptr;
+static size_t g_scratch_n = 0;
+static int g_scratch_dev = -1;
+
+extern "C" int mgplr_plr_episode_scores(const float *masks, const float *cliffhanger_masks, const float *returns,
+                                        const float *value_preds, const float *rewards, const int32_t *level_seeds, int32_t T,
+                                        int32_t N, int32_t strategy, mgplr_episode *episodes, int32_t max_episodes,
+                                        int32_t *n_episodes, void *stream) {
+  if (!masks || !value_preds || !rewards || !episodes || !n_episodes || T < 1 || N < 1)
+    return pfail(MGPLR_E_BADARG, "mgplr_plr_episode_scores: bad arguments");
+  if (strategy != MGPLR_SCORE_MAX_MC && !returns) return pfail(MGPLR_E_BADARG, "returns required for this strategy");
+  int dev = 0;
+  PCK(cudaGetDevice(&dev));
+  if (g_scratch_dev != dev || g_scratch_n < 2 * (size_t)N) {
+    if (g_scratch) cudaFree(g_scratch);
+    g_scratch = nullptr;
+    PCK(cudaMalloc((void **)&g_scratch, 2 * (size_t)N * sizeof(int32_t)));
+    g_scratch_n = 2 * (size_t)N; g_scratch_dev = dev;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t *counts = g_scratch, *offsets = g_scratch + N;
+  k_count_episodes<<<(N + 127) / 128, 128, 0, st>>>(masks, T, N, counts);
+  k_scan_counts<<<1, 1024, 0, st>>>(counts, N, offsets, n_episodes);
+  k_episode_scores<<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, returns, value_preds, rewards, level_seeds, T, N,
+                                                    strategy, offsets, episodes, max_episodes);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ sample weights
+// One CTA.  rank transform: rank 1 = highest score; ties broken by index (higher index first), i.e.
+// np.flip(np.argsort(scores, kind='stable')).  weights = 1/rank^(1/T) masked by seen, normalised; staleness:
+// clip(s,0)^(1/Ts) masked, normalised; mix (1-c) w + c s.
+constexpr int kMaxBuf = 8192;
+
+struct Key {
+  double s;
+  int32_t i;
+};
+// "a comes before b" in DESCENDING order with the tie rule above
+__device__ __forceinline__ bool before(const Key &a, const Key &b) { return a.s > b.s || (a.s == b.s && a.i > b.i); }
+
+__device__ void block_sort_desc(Key *keys, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const Key a = keys[i], b = keys[ixj];
+          if (up ? before(b, a) : before(a, b)) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+}
+
+__device__ double block_sum(double v, double *red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double w = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) red[32] = w;
+  }
+  __syncthreads();
+  const double r = red[32];
+  __syncthreads();
+  return r;
+}
+
+// rank weights (before staleness mixing) into w_rank[n] (global); uses dynamic smem for the keys
+__device__ void rank_weights(const double *scores, const double *unseen, int n, double temperature, double *w_rank, Key *keys,
+                             double *red) {
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    Key k;
+    k.s = (i < n) ? scores[i] : -INFINITY; k.i = (i < n) ? i : -1 - i;
+    keys[i] = k;
+  }
+  __syncthreads();
+  block_sort_desc(keys, n2);
+  const double inv_t = 1.0 / temperature;
+  double part = 0.0;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const int i = keys[r].i;
+    const double w = (1.0 / pow((double)(r + 1), inv_t)) * (1.0 - unseen[i]);
+    w_rank[i] = w; part += w;
+  }
+  const double z = block_sum(part, red);
+  double nseen_part = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) nseen_part += (1.0 - unseen[i]);
+  const double nseen = block_sum(nseen_part, red);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (z > 0) w_rank[i] = w_rank[i] / z;
+    else w_rank[i] = ((1.0 / (double)n) * (1.0 - unseen[i])) / (nseen / (double)n);  // uniform over seen (level_sampler.py:733-736)
+  }
+  __syncthreads();
+}
+
+__device__ void mix_staleness(const double *w_rank, const double *staleness, const double *unseen, int n, double coef,
+                              double stale_t, double *weights, double *red) {
+  if (!(coef > 0)) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) weights[i] = w_rank[i];
+    __syncthreads();
+    return;
+  }
+  const double inv_t = 1.0 / stale_t;
+  double part = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double s = pow(fmax(staleness[i], 0.0), inv_t) * (1.0 - unseen[i]);
+    weights[i] = s; part += s;
+  }
+  const double z = block_sum(part, red);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double s = (z > 0) ? weights[i] / z : (1.0 / (double)n) * (1.0 - unseen[i]);
+    weights[i] = (1.0 - coef) * w_rank[i] + coef * s;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_sample_weights(const double *scores, const double *staleness, const double *unseen, int n,
+                                                         double temperature, double coef, double stale_t, double *weights,
+                                                         double *w_rank) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  Key *keys = reinterpret_cast<Key *>(sm);
+  __shared__ double red[33];
+  rank_weights(scores, unseen, n, temperature, w_rank, keys, red);
+  mix_staleness(w_rank, staleness, unseen, n, coef, stale_t, weights, red);
+}
+
+static double *g_dscratch = nullptr;
+static size_t g_dscratch_n = 0;
+static int g_dscratch_dev = -1;
+static int ensure_dscratch(size_t n) {
+  int dev = 0;
+  PCK(cudaGetDevice(&dev));
+  if (g_dscratch_dev != dev || g_dscratch_n < n) {
+    if (g_dscratch) cudaFree(g_dscratch);
+    g_dscratch = nullptr;
+    PCK(cudaMalloc((void **)&g_dscratch, n * sizeof(double)));
+    g_dscratch_n = n; g_dscratch_dev = dev;
+  }
+  return 0;
+}
+static size_t sort_smem(int n) {
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  return (size_t)n2 * sizeof(Key);
+}
+
+extern "C" int mgplr_plr_sample_weights(const double *scores, const double *staleness, const double *unseen, int32_t n,
+                                        double temperature, double staleness_coef, double staleness_temperature,
+                                        double *weights, void *stream) {
+  if (!scores || !staleness || !unseen || !weights || n < 1 || n > kMaxBuf)
+    return pfail(MGPLR_E_BADARG, "mgplr_plr_sample_weights: bad arguments (n must be in [1, 8192])");
+  if (int rc = ensure_dscratch(2 * (size_t)kMaxBuf)) return rc;
+  const size_t smem = sort_smem(n);
+  PCK(cudaFuncSetAttribute(k_sample_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_sample_weights<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, temperature, staleness_coef,
+                                                           staleness_temperature, weights, g_dscratch);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+// n_draws sequential draws.  The rank part is fixed across the batch (scores do not change); the staleness
+// part is recomputed after every draw ("all +1, chosen -> 0").  Inverse CDF: np.random.choice(p=w) =
+// cumsum -> /cdf[-1] -> searchsorted(u, side='right') = #{cdf <= u}.
+__global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, double *staleness, const double *unseen, int n,
+                                                        double temperature, double coef, double stale_t, const double *u,
+                                                        int n_draws, int32_t *out_index, double *w_rank, double *weights) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  Key *keys = reinterpret_cast<Key *>(sm);
+  __shared__ double red[33];
+  __shared__ double wsum[32];
+  __shared__ int s_pick;
+  rank_weights(scores, unseen, n, temperature, w_rank, keys, red);
+  // contiguous chunk per thread so the scan is a per-thread serial cumsum + a block scan of chunk sums
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  for (int dr = 0; dr < n_draws; dr++) {
+    mix_staleness(w_rank, staleness, unseen, n, coef, stale_t, weights, red);
+    double local = 0.0;
+    for (int i = lo; i < hi; i++) local += weights[i];
+    // block exclusive scan of `local`
+    double x = local;
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double w = (threadIdx.x < (blockDim.x >> 5)) ? wsum[threadIdx.x] : 0.0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      wsum[threadIdx.x] = w;
+    }
+    if (threadIdx.x == 0) s_pick = n;  // searchsorted returns n if u >= cdf[-1]
+    __syncthreads();
+    const double total = wsum[(blockDim.x >> 5) - 1];
+    double run = ((threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0.0) + x - local;
+    const double uu = u[dr];
+    // first index whose normalised cdf exceeds u
+    for (int i = lo; i < hi; i++) {
+      run += weights[i];
+      if (run / total > uu) { atomicMin(&s_pick, i); break; }
+    }
+    __syncthreads();
+    const int pick = min(s_pick, n - 1);
+    if (threadIdx.x == 0) out_index[dr] = pick;
+    if (coef > 0) {  // _update_staleness (level_sampler.py:601-604)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) staleness[i] = (i == pick) ? 0.0 : staleness[i] + 1.0;
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, const double *unseen, int32_t n,
+                                       double temperature, double staleness_coef, double staleness_temperature,
+                                       const double *u, int32_t n_draws, int32_t *out_index, void *stream) {
+  if (!scores || !staleness || !unseen || !u || !out_index || n < 1 || n > kMaxBuf || n_draws < 1)
+    return pfail(MGPLR_E_BADARG, "mgplr_plr_sample_replay: bad arguments (n must be in [1, 8192])");
+  if (int rc = ensure_dscratch(2 * (size_t)kMaxBuf)) return rc;
+  const size_t smem = sort_smem(n);
+  PCK(cudaFuncSetAttribute(k_sample_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_sample_replay<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, temperature, staleness_coef,
+                                                          staleness_temperature, u, n_draws, out_index, g_dscratch,
+                                                          g_dscratch + kMaxBuf);
+  PCK(cudaGetLastError());
+  return 0;
+}

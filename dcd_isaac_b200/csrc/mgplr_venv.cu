@@ -1,0 +1,830 @@
+// mgplr_venv.cu -- kernels and C-ABI entry points for the batched MultiGrid adversarial env (sm_100a).
+//
+// Hot kernel: k_step_env -- one CTA stages a tile of TILE envs in shared memory (wall bit-plane rows,
+// struct-of-arrays so the bank index is the thread index), one thread steps one env, the rendered
+// float32 observations of the whole tile are assembled in shared memory and leave the SM as ONE
+// contiguous bulk asynchronous copy (cp.async.bulk, TMA engine) straight into the rollout-storage
+// tensor.  See DESIGN.md for the byte accounting and the roofline.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "mgplr_env.cuh"
+
+using namespace mgplr;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char *where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return (int)e;
+}
+#define CK(call)                                              \
+  do {                                                        \
+    cudaError_t _e = (call);                                  \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call);       \
+  } while (0)
+
+extern "C" const char *mgplr_last_error(void) { return g_err; }
+extern "C" int mgplr_set_error_(int code, const char *msg) { return fail(code, msg); }
+extern "C" int mgplr_abi_version(void) { return MGPLR_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------ handle
+struct mgplr_venv {
+  Dev d;
+  int device;
+  int64_t bytes;
+  // scratch for host->device argument staging
+  uint32_t *seed_scratch;  // [4][N]
+  int64_t *act_dev;        // [N]   (mgplr_step_env_host)
+  uint8_t *res_dev;        // packed results [N*13]
+  int sm_count;
+};
+
+constexpr int TILE = 128;  // envs (= threads) per CTA in the hot kernels
+
+// dynamic shared memory of the step kernels: obs tile [TILE][75] f32 then wall rows [W][TILE] u32
+static size_t step_smem_bytes(int W) { return (size_t)TILE * kObsFloats * 4 + (size_t)W * TILE * 4; }
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared -> global bulk asynchronous copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------ obs emit (cold paths)
+struct OutPtrs {
+  float *image, *direction;
+  uint8_t *image_u8;
+};
+__device__ __noinline__ void emit_direct(const Rows &R, const Env &e, const Cfg &c, const OutPtrs &o, int row) {
+  if (!o.image && !o.image_u8 && !o.direction) return;
+  View v = c.see_through ? render_view<true>(R, e, c.W) : render_view<false>(R, e, c.W);
+  if (o.image) emit_obs_f32(v, o.image + (size_t)row * kObsFloats);
+  if (o.image_u8) emit_obs_u8(v, o.image_u8 + (size_t)row * kObsFloats);
+  if (o.direction) o.direction[row] = (float)e.adir;
+}
+
+// ------------------------------------------------------------------------------------------ kernels: level ops
+__global__ void k_init(Dev d) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  Rows R{d.wall + e, d.N};
+  gen_grid(R, d.c.W);
+  Env s{};
+  s.gx = s.gy = s.sx = s.sy = kNone;
+  d.hot[e] = pack(s);
+  d.adv[e] = (uint32_t)(d.c.n_clutter + 2) << 12;
+  d.metrics[e] = make_int4(0, -1, -1, (d.c.W - 2) * (d.c.W - 2) + 1);
+  d.mti[e] = 0; d.words[e] = 0; d.err[e] = 0;
+  d.limbs[e] = 0; d.limbs[(size_t)d.N + e] = 0; d.limbs[2 * (size_t)d.N + e] = 1;
+}
+
+// scratch: [0][k] lo, [1][k] hi, [2][k] count, [3][k] env index
+__global__ void k_seed(Dev d, const uint32_t *scratch, int n, int stride, int has_index) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int e = has_index ? (int)scratch[3 * (size_t)stride + k] : k;
+  if (e < 0 || e >= d.N) return;
+  const uint32_t lo = scratch[k], hi = scratch[(size_t)stride + k], cnt = scratch[2 * (size_t)stride + k];
+  d.limbs[e] = lo; d.limbs[(size_t)d.N + e] = hi; d.limbs[2 * (size_t)d.N + e] = cnt;
+  mt_seed(d, e, lo, hi, (int)cnt);
+}
+
+__global__ void k_reset(Dev d) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  uint32_t adv = d.adv[e];
+  int4 met;
+  Rng rng(d, e);
+  reset_adversary(R, s, adv, met, rng, d.c);
+  rng.store();
+  d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
+}
+
+__global__ void k_step_adversary(Dev d, const int64_t *loc, uint8_t *done) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  uint32_t adv = d.adv[e], err = 0;
+  int4 met = d.metrics[e];
+  Rng rng(d, e);
+  const long long l = loc[e];
+  const bool dn = step_adversary(R, s, adv, met, rng, d.c, (l < 0 || l > 0x7fffffff) ? -1 : (int)l, err);
+  rng.store();
+  d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
+  if (err) d.err[e] |= err;
+  if (done) done[e] = dn ? 1 : 0;
+}
+
+// Adversary observation image f32 [N][3][W][W] = Grid.encode()/10 with channels first
+// (adversarial.py:222-227,532-537; obs_wrappers.py:104-110).  One thread per (env, cell): for a fixed
+// channel consecutive threads write consecutive floats, so all three stores are coalesced.
+__global__ void k_adv_image(Dev d, float *image, float *time_step) {
+  const int W = d.c.W, WW = W * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d.N * WW) return;
+  const int e = (int)(idx / WW), cell = (int)(idx % WW), x = cell / W, y = cell % W;
+  const Env s = unpack(d.hot[e]);
+  float t, c, st = 0.f;
+  if (s.has_agent && x == s.ax && y == s.ay) { t = 1.0f; c = 0.0f; st = s.adir == 0 ? 0.0f : s.adir == 1 ? 0.1f : s.adir == 2 ? 0.2f : 0.3f; }
+  else if ((d.wall[(size_t)y * d.N + e] >> x) & 1u) { t = 0.2f; c = 0.5f; }
+  else if (x == s.gx && y == s.gy) { t = 0.8f; c = 0.1f; }
+  else { t = 0.1f; c = 0.0f; }
+  float *o = image + (size_t)e * 3 * WW + cell;
+  o[0] = t; o[WW] = c; o[2 * WW] = st;
+  if (time_step && cell == 0) time_step[e] = (float)(d.adv[e] & 0xfff);
+}
+
+__global__ void k_reset_agent(Dev d, OutPtrs o) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  if (!reset_agent(s)) { d.err[e] |= kErrNoStart; d.hot[e] = pack(s); return; }
+  s.ep_ret = 0.f; s.ep_len = 0;  // VecMonitor.reset_agent (vec_monitor.py:42-46)
+  d.hot[e] = pack(s);
+  emit_direct(R, s, d.c, o, e);
+}
+
+__global__ void k_reset_random(Dev d, const int32_t *n_walls, OutPtrs o) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  uint32_t adv = d.adv[e], err = 0;
+  int4 met;
+  Rng rng(d, e);
+  const int nw = (d.c.resample && n_walls) ? n_walls[e] : -1;
+  reset_random(R, s, adv, met, rng, d, e, nw, err);
+  rng.store();
+  s.ep_ret = 0.f; s.ep_len = 0;  // VecMonitor.reset_random (vec_monitor.py:48-52)
+  d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
+  if (err) d.err[e] |= err;
+  emit_direct(R, s, d.c, o, e);
+}
+
+// reset_to_level, byte form (adversarial.py:271-294, multigrid.py:264-280): reset() draws a FRESH start
+// direction; the encoding's agent dir byte is not restored.
+__global__ void k_reset_to_encoding(Dev d, const uint8_t *enc, const int32_t *index, int n, OutPtrs o) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int e = index ? index[k] : k;
+  if (e < 0 || e >= d.N) return;
+  const int W = d.c.W;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  uint32_t adv = d.adv[e];
+  int4 met;
+  Rng rng(d, e);
+  reset_adversary(R, s, adv, met, rng, d.c);
+  rng.store();
+  const uint8_t *src = enc + (size_t)k * W * W * 3;
+  for (int y = 0; y < W; y++) {
+    uint32_t row = 0;
+    for (int x = 0; x < W; x++) {
+      const uint8_t t = src[((size_t)x * W + y) * 3];
+      if (t == 2) row |= 1u << x;
+      else if (t == 8) { s.gx = x; s.gy = y; }
+      else if (t == 10) { s.sx = x; s.sy = y; }
+    }
+    R.set(y, row);
+  }
+  // set_encoding visits i (x) outer, j (y) inner: with several goals/agents the LAST in that order wins
+  // (multigrid.py:267-280); single-goal/agent levels are order independent.
+  met = compute_metrics(R, s, W, false);
+  if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+  d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
+  emit_direct(R, s, d.c, o, e);
+}
+
+// reset_to_level, action-string form (adversarial.py:274-283).
+__global__ void k_reset_to_actions(Dev d, const int32_t *locs, int len, const int32_t *index, int n, OutPtrs o) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int e = index ? index[k] : k;
+  if (e < 0 || e >= d.N) return;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  uint32_t adv = d.adv[e], err = 0;
+  int4 met;
+  Rng rng(d, e);
+  reset_adversary(R, s, adv, met, rng, d.c);
+  if (d.c.resample) adv = (adv & ~(0xfffu << 12)) | ((uint32_t)len << 12);
+  for (int i = 0; i < len; i++) {
+    if (step_adversary(R, s, adv, met, rng, d.c, locs[(size_t)k * len + i], err))
+      if (!reset_agent(s)) err |= kErrNoStart;
+  }
+  rng.store();
+  s.elapsed = 0;
+  d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
+  if (err) d.err[e] |= err;
+  emit_direct(R, s, d.c, o, e);
+}
+
+// free-cell test used by mutate_level's fallbacks: free_mask == "grid cell is None" 
+__device__ __forceinline__ int count_free(const Rows &R, const Env &s, int W, int pick, int &sel) {
+  int cnt = 0;
+  sel = -1;
+  for (int y = 1; y < W - 1; y++)
+    for (int x = 1; x < W - 1; x++)
+      if (is_empty(R, s, x, y)) { if (cnt == pick) sel = (y - 1) * (W - 2) + (x - 1); cnt++; }
+  return cnt;
+}
+
+// mutate_level, edit phase (adversarial.py:317-368).
+__global__ void k_mutate_edits(Dev d, const int32_t *locs, const int32_t *ops, const int32_t *n_edits, int max_edits,
+                               uint8_t *need, int32_t *n_free) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const int W = d.c.W, I = W - 2;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  const int k = n_edits[e];
+  for (int n = 0; n < k && n < max_edits; n++) {
+    const int loc = locs[(size_t)e * max_edits + n], op = ops[(size_t)e * max_edits + n];
+    const int x = loc % I + 1, y = loc / I + 1;
+    // editor action: 0 '-', 1 '.', then ('a','g') for the 4-action set, 'g' for the 3-action set
+    const bool is_a = (d.c.n_editor == 4 && op == 2), is_g = (d.c.n_editor == 4 && op == 3) || (d.c.n_editor == 3 && op == 2);
+    // _clean_loc (adversarial.py:296-306)
+    R.set(y, R.get(y) & ~(1u << x));
+    if (x == s.gx && y == s.gy) { s.gx = s.gy = kNone; }
+    else if (s.has_agent && x == s.ax && y == s.ay) { s.sx = s.sy = kNone; s.has_agent = 0; }
+    if (op == 0) R.set(y, R.get(y) | (1u << x));
+    else if (is_a) { s.has_agent = 1; s.ax = x; s.ay = y; s.adir = 0; s.sx = x; s.sy = y; }
+    else if (is_g) { s.gx = x; s.gy = y; }
+  }
+  int sel;
+  const bool need_g = s.gx == kNone, need_a = s.sx == kNone;
+  const int nf = (need_g || need_a) ? count_free(R, s, W, -1, sel) : 0;
+  if (need) { need[2 * e] = need_g; need[2 * e + 1] = need_a; }
+  if (n_free) { n_free[2 * e] = need_g ? nf : 0; n_free[2 * e + 1] = need_a ? (need_g ? nf - 1 : nf) : 0; }
+  d.hot[e] = pack(s);
+}
+
+// mutate_level, fallback placement + metrics + reset_agent (adversarial.py:370-397).
+__global__ void k_mutate_finalize(Dev d, const int32_t *choice, OutPtrs o) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const int W = d.c.W, I = W - 2;
+  Rows R{d.wall + e, d.N};
+  Env s = unpack(d.hot[e]);
+  int sel;
+  if (s.gx == kNone) {
+    count_free(R, s, W, choice ? choice[2 * e] : 0, sel);
+    if (sel >= 0) { s.gx = sel % I + 1; s.gy = sel / I + 1; }
+  }
+  if (s.sx == kNone) {
+    count_free(R, s, W, choice ? choice[2 * e + 1] : 0, sel);
+    if (sel >= 0) { s.sx = sel % I + 1; s.sy = sel / I + 1; s.has_agent = 1; s.ax = s.sx; s.ay = s.sy; }
+  }
+  s.step_count = 0;
+  d.adv[e] = d.adv[e] & ~0xfffu;  // adversary_step_count = 0
+  d.metrics[e] = compute_metrics(R, s, W, true);
+  if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+  d.hot[e] = pack(s);
+  emit_direct(R, s, d.c, o, e);
+}
+
+// AdversarialEnv.encoding (adversarial.py:162-164): u8 [N][W][W][3] indexed [x][y][c]; one thread per cell.
+__global__ void k_encode(Dev d, uint8_t *enc) {
+  const int W = d.c.W, WW = W * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)d.N * WW) return;
+  const int e = (int)(idx / WW), cell = (int)(idx % WW), x = cell / W, y = cell % W;
+  const Env s = unpack(d.hot[e]);
+  uint8_t t, c, st = 0;
+  if (s.has_agent && x == s.ax && y == s.ay) { t = 10; c = 0; st = (uint8_t)s.adir; }
+  else if ((d.wall[(size_t)y * d.N + e] >> x) & 1u) { t = 2; c = 5; }
+  else if (x == s.gx && y == s.gy) { t = 8; c = 1; }
+  else { t = 1; c = 0; }
+  uint8_t *o = enc + idx * 3;
+  o[0] = t; o[1] = c; o[2] = st;
+}
+
+__global__ void k_get_metrics(Dev d, int32_t *m) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const int4 v = d.metrics[e];
+  m[4 * e] = v.x; m[4 * e + 1] = v.y; m[4 * e + 2] = v.z; m[4 * e + 3] = v.w;
+}
+__global__ void k_get_agent_state(Dev d, int32_t *o) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const Env s = unpack(d.hot[e]);
+  const uint32_t adv = d.adv[e];
+  int32_t *p = o + 8 * (size_t)e;
+  p[0] = s.ax; p[1] = s.ay; p[2] = s.adir; p[3] = s.step_count; p[4] = s.elapsed;
+  p[5] = adv & 0xfff; p[6] = (adv >> 12) & 0xfff; p[7] = (int32_t)d.words[e];
+}
+__global__ void k_get_errors(Dev d, uint32_t *o, int clear) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  o[e] = d.err[e];
+  if (clear) d.err[e] = 0;
+}
+
+// ------------------------------------------------------------------------------------------ hot kernel: step_env
+struct StepArgs {
+  const int64_t *action;
+  const int32_t *n_walls;
+  int last_step;  // bit0: last rollout step (adversarial_runner.py:521-530), bit1: use_proper_time_limits
+  mgplr_step_out o;
+};
+
+// One env transition for the thread's env.  `R` are the env's wall rows in shared memory.  Returns flags.
+template <bool SEE, bool RR>
+__device__ __forceinline__ uint32_t step_one(const Dev &d, const Rows &R, Env &s, int e, int a, const StepArgs &A, float *s_obs,
+                                             float &rew_out, bool &rows_dirty) {
+  const Cfg &c = d.c;
+  uint32_t flags = 0, err = 0;
+  double rew = 0.0;
+  // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
+  s.step_count++;
+  const int fx = s.ax + ((s.adir == 0) - (s.adir == 2)), fy = s.ay + ((s.adir == 1) - (s.adir == 3));
+  if (a == 0) s.adir = (s.adir + 3) & 3;
+  else if (a == 1) s.adir = (s.adir + 1) & 3;
+  else if (a == 2) {
+    if (fx == s.gx && fy == s.gy) {
+      // agent_is_done (multigrid.py:821-838): remove the agent, done, respawn at a random empty cell with the
+      // env RNG (dir forced to 0, multigrid.py:668-672); reward = MiniGridEnv._reward()
+      Rng rng(d, e);
+      s.has_agent = 0; s.done_flag = 1;
+      int px = s.ax, py = s.ay;
+      place_random(R, s, rng, c.W, -1, px, py);
+      rng.store();
+      s.has_agent = 1; s.ax = px; s.ay = py; s.adir = 0;
+      rew = __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)s.step_count, (double)c.max_steps)));
+      flags |= MGPLR_F_GOAL;
+    } else if (!is_wall(R, fx, fy)) { s.ax = fx; s.ay = fy; }
+  }
+  bool done = s.done_flag || s.step_count >= c.max_steps;
+  // TimeLimit.step (time_limit.py:24-33)
+  s.elapsed++;
+  if (s.elapsed >= c.max_episode_steps) {
+    flags |= MGPLR_F_TRUNC_KEY | (done ? 0u : MGPLR_F_TRUNC_VAL);
+    if (A.o.trunc_image || A.o.trunc_direction) {
+      OutPtrs tp{A.o.trunc_image, A.o.trunc_direction, nullptr};
+      emit_direct(R, s, c, tp, e);
+    }
+    done = true;
+  }
+  // VecMonitor.step_wait (vec_monitor.py:60-85): eprets(f32) += rews(f64) is evaluated in double
+  s.ep_ret = (float)__dadd_rn((double)s.ep_ret, rew);
+  s.ep_len += 1;
+  if (done) {
+    flags |= MGPLR_F_DONE;
+    if (A.o.ep_return) A.o.ep_return[e] = s.ep_ret;
+    if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
+    s.ep_ret = 0.f; s.ep_len = 0;
+    // worker.step_env (parallel_wrappers.py:27-37)
+    if (RR) {
+      uint32_t adv = d.adv[e];
+      int4 met;
+      Rng rng(d, e);
+      reset_random(R, s, adv, met, rng, d, e, (c.resample && A.n_walls) ? A.n_walls[e] : -1, err);
+      rng.store();
+      d.adv[e] = adv; d.metrics[e] = met;
+      rows_dirty = true;
+    } else if (!reset_agent(s)) err |= kErrNoStart;
+  } else if ((A.last_step & 3) == 3 && (A.o.trunc_image || A.o.trunc_direction)) {
+    // runner-side cliffhanger: truncated_obs = the current obs (adversarial_runner.py:523-528)
+    OutPtrs tp{A.o.trunc_image, A.o.trunc_direction, nullptr};
+    emit_direct(R, s, c, tp, e);
+  }
+  if (err) d.err[e] |= err;
+  const View v = render_view<SEE>(R, s, c.W);
+  emit_obs_f32(v, s_obs);
+  if (A.o.image_u8) emit_obs_u8(v, A.o.image_u8 + (size_t)e * kObsFloats);
+  rew_out = (float)rew;
+  return flags;
+}
+
+__device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, const Env &s, uint32_t flags, float rew) {
+  const mgplr_step_out &o = A.o;
+  if (o.direction) o.direction[e] = (float)s.adir;
+  if (o.reward) o.reward[e] = rew;
+  if (o.flags) o.flags[e] = (uint8_t)flags;
+  const bool done = flags & MGPLR_F_DONE, last = A.last_step & 1, cliff = last && (A.last_step & 2) && !done;
+  if (o.masks) o.masks[e] = (done || last) ? 0.f : 1.f;
+  if (o.bad_masks) o.bad_masks[e] = ((flags & MGPLR_F_TRUNC_KEY) || cliff) ? 0.f : 1.f;
+  if (o.cliffhanger_masks) o.cliffhanger_masks[e] = cliff ? 0.f : 1.f;
+}
+
+// Store the CTA's observation tile: n_envs*75 contiguous floats starting at gdst.
+__device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, int n_envs) {
+  const uint32_t bytes = (uint32_t)n_envs * kObsFloats * 4u;
+  if ((bytes & 15u) == 0 && (((uintptr_t)gdst) & 15u) == 0) {
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) { bulk_store(gdst, s_obs, bytes); bulk_commit_wait(); }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_envs * kObsFloats; i += blockDim.x) gdst[i] = s_obs[i];
+  }
+}
+
+template <bool SEE, bool RR>
+__global__ void __launch_bounds__(TILE) k_step_env(Dev d, StepArgs A) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float *s_obs = reinterpret_cast<float *>(smem);
+  uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem + (size_t)TILE * kObsFloats * 4);
+  const int tid = threadIdx.x, base = blockIdx.x * TILE, e = base + tid, W = d.c.W;
+  const bool valid = e < d.N;
+  if (valid) {
+    // stage this env's wall rows: coalesced across the warp (row-major struct-of-arrays in HBM)
+#pragma unroll 5
+    for (int r = 0; r < W; r++) s_rows[r * TILE + tid] = d.wall[(size_t)r * d.N + e];
+    Env s = unpack(d.hot[e]);
+    const int a = (int)A.action[e];
+    const Rows R{s_rows + tid, TILE};
+    float rew;
+    bool dirty = false;
+    const uint32_t flags = step_one<SEE, RR>(d, R, s, e, a, A, s_obs + tid * kObsFloats, rew, dirty);
+    d.hot[e] = pack(s);
+    if (RR && dirty)
+      for (int r = 0; r < W; r++) d.wall[(size_t)r * d.N + e] = s_rows[r * TILE + tid];
+    write_step_scalars(A, e, s, flags, rew);
+  }
+  if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, min(TILE, d.N - base));
+}
+
+// T transitions in one launch from a recorded action stream u8 [T][N]; state stays on chip.
+template <bool SEE, bool RR>
+__global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions, int T, StepArgs A0) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float *s_obs = reinterpret_cast<float *>(smem);
+  uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem + (size_t)TILE * kObsFloats * 4);
+  const int tid = threadIdx.x, base = blockIdx.x * TILE, e = base + tid, W = d.c.W, N = d.N;
+  const bool valid = e < N;
+  Env s{};
+  const Rows R{s_rows + tid, TILE};
+  bool dirty = false;
+  if (valid) {
+    for (int r = 0; r < W; r++) s_rows[r * TILE + tid] = d.wall[(size_t)r * N + e];
+    s = unpack(d.hot[e]);
+  }
+  const int n_tile = min(TILE, N - base);
+  for (int t = 0; t < T; t++) {
+    StepArgs A = A0;
+    const size_t off = (size_t)t * N;
+    // advance the [T]-leading output pointers
+    if (A.o.image) A.o.image += off * kObsFloats;
+    if (A.o.direction) A.o.direction += off;
+    if (A.o.reward) A.o.reward += off;
+    if (A.o.flags) A.o.flags += off;
+    if (A.o.ep_return) A.o.ep_return += off;
+    if (A.o.ep_length) A.o.ep_length += off;
+    if (A.o.trunc_image) A.o.trunc_image += off * kObsFloats;
+    if (A.o.trunc_direction) A.o.trunc_direction += off;
+    if (A.o.masks) A.o.masks += off;
+    if (A.o.bad_masks) A.o.bad_masks += off;
+    if (A.o.cliffhanger_masks) A.o.cliffhanger_masks += off;
+    if (A.o.image_u8) A.o.image_u8 += off * kObsFloats;
+    A.last_step = (t == T - 1) ? A0.last_step : 0;
+    if (valid) {
+      float rew;
+      const uint32_t flags = step_one<SEE, RR>(d, R, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats, rew, dirty);
+      write_step_scalars(A, e, s, flags, rew);
+    }
+    if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, n_tile);
+    __syncthreads();  // tile buffer is reused by the next step
+  }
+  if (valid) {
+    d.hot[e] = pack(s);
+    if (RR && dirty)
+      for (int r = 0; r < W; r++) d.wall[(size_t)r * N + e] = s_rows[r * TILE + tid];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int grid_for(int n, int block) { return (n + block - 1) / block; }
+
+static int check_cfg(const mgplr_env_config *c) {
+  if (!c) return fail(MGPLR_E_BADARG, "config is NULL");
+  if (c->width < 5 || c->width > 32) return fail(MGPLR_E_UNSUPPORTED, "width must be in [5, 32]");
+  if (c->agent_view_size != 5) return fail(MGPLR_E_UNSUPPORTED, "agent_view_size must be 5");
+  if (c->max_steps < 1 || c->max_steps > 65535) return fail(MGPLR_E_UNSUPPORTED, "max_steps must be in [1, 65535]");
+  if (c->max_episode_steps < 1 || c->max_episode_steps > 32767)
+    return fail(MGPLR_E_UNSUPPORTED, "max_episode_steps must be in [1, 32767]");
+  if (c->n_clutter < 0 || c->n_clutter > 4000) return fail(MGPLR_E_UNSUPPORTED, "n_clutter must be in [0, 4000]");
+  if (c->n_editor_actions < 2 || c->n_editor_actions > 4) return fail(MGPLR_E_BADARG, "n_editor_actions must be 2, 3 or 4");
+  return 0;
+}
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t count, int64_t &total) {
+  total += (int64_t)(count * sizeof(T));
+  return cudaMalloc((void **)p, count * sizeof(T));
+}
+
+extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, int32_t device, mgplr_venv **out) {
+  if (!out) return fail(MGPLR_E_BADARG, "out is NULL");
+  *out = nullptr;
+  if (int rc = check_cfg(cfg)) return rc;
+  if (num_envs < 1) return fail(MGPLR_E_BADARG, "num_envs must be >= 1");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(ce != cudaSuccess ? (int)ce : (int)cudaErrorNoDevice,
+                "mgplr: no CUDA device -- this library has no CPU fallback");
+  CK(cudaSetDevice(device));
+  mgplr_venv *v = new (std::nothrow) mgplr_venv();
+  if (!v) return fail(MGPLR_E_BADARG, "out of host memory");
+  memset(v, 0, sizeof(*v));
+  v->device = device;
+  Dev &d = v->d;
+  d.N = num_envs;
+  d.c = Cfg{cfg->width, cfg->max_steps, cfg->max_episode_steps, cfg->see_through_walls != 0, cfg->n_clutter,
+            cfg->resample_n_clutter != 0, cfg->choose_goal_last != 0, cfg->fixed_environment != 0, cfg->n_editor_actions};
+  const size_t N = (size_t)num_envs;
+  int64_t total = 0;
+  CK(dalloc(&d.wall, (size_t)cfg->width * N, total));
+  CK(dalloc(&d.hot, N, total));
+  CK(dalloc(&d.adv, N, total));
+  CK(dalloc(&d.metrics, N, total));
+  CK(dalloc(&d.mt, 624 * N, total));
+  CK(dalloc(&d.mti, N, total));
+  CK(dalloc(&d.limbs, 3 * N, total));
+  CK(dalloc(&d.words, N, total));
+  CK(dalloc(&d.err, N, total));
+  CK(dalloc(&v->seed_scratch, 4 * N, total));
+  CK(dalloc(&v->act_dev, N, total));
+  CK(dalloc(&v->res_dev, 16 * N, total));
+  v->bytes = total;
+  CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device));
+  const size_t smem = step_smem_bytes(cfg->width);
+  CK(cudaFuncSetAttribute(k_step_env<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_step_env<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_step_env<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_step_env<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_rollout<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_rollout<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_rollout<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(k_rollout<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaMemset(d.mt, 0, 624 * N * sizeof(uint32_t)));
+  k_init<<<grid_for(num_envs, 256), 256>>>(d);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  *out = v;
+  return 0;
+}
+
+extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
+  if (!v) return;
+  cudaSetDevice(v->device);
+  Dev &d = v->d;
+  cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
+  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->res_dev);
+  delete v;
+}
+
+extern "C" int32_t mgplr_venv_num_envs(const mgplr_venv *v) { return v ? v->d.N : 0; }
+extern "C" int64_t mgplr_venv_state_bytes(const mgplr_venv *v) { return v ? v->bytes : 0; }
+
+#define NEED(v)                                                 \
+  if (!(v)) return fail(MGPLR_E_BADARG, "venv handle is NULL"); \
+  CK(cudaSetDevice((v)->device));                               \
+  cudaStream_t st = (cudaStream_t)stream
+
+extern "C" int mgplr_seed(mgplr_venv *v, const uint32_t *limbs_host, const int32_t *n_limbs_host, const int32_t *index_host,
+                          int32_t n, void *stream) {
+  NEED(v);
+  if (!limbs_host || !n_limbs_host || n < 1 || n > v->d.N) return fail(MGPLR_E_BADARG, "mgplr_seed: bad arguments");
+  const size_t N = (size_t)v->d.N;
+  uint32_t *tmp = (uint32_t *)malloc(4 * (size_t)n * sizeof(uint32_t));
+  if (!tmp) return fail(MGPLR_E_BADARG, "out of host memory");
+  for (int k = 0; k < n; k++) {
+    tmp[k] = limbs_host[2 * k]; tmp[(size_t)n + k] = limbs_host[2 * k + 1];
+    tmp[2 * (size_t)n + k] = (uint32_t)n_limbs_host[k]; tmp[3 * (size_t)n + k] = index_host ? (uint32_t)index_host[k] : (uint32_t)k;
+    if (n_limbs_host[k] < 1 || n_limbs_host[k] > 2) { free(tmp); return fail(MGPLR_E_BADARG, "seed limb count must be 1 or 2"); }
+  }
+  (void)N;
+  cudaError_t e = cudaMemcpyAsync(v->seed_scratch, tmp, 4 * (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  free(tmp);
+  if (e != cudaSuccess) return cuda_fail(e, "mgplr_seed copy");
+  k_seed<<<grid_for(n, 128), 128, 0, st>>>(v->d, v->seed_scratch, n, n, index_host != nullptr);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_adv_image(mgplr_venv *v, float *adv_image, float *time_step, cudaStream_t st) {
+  if (!adv_image) return 0;
+  const size_t total = (size_t)v->d.N * v->d.c.W * v->d.c.W;
+  k_adv_image<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v->d, adv_image, time_step);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_reset(mgplr_venv *v, float *adv_image, float *time_step, void *stream) {
+  NEED(v);
+  k_reset<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d);
+  CK(cudaGetLastError());
+  return launch_adv_image(v, adv_image, time_step, st);
+}
+
+extern "C" int mgplr_step_adversary(mgplr_venv *v, const int64_t *loc, float *adv_image, float *time_step, uint8_t *done,
+                                    void *stream) {
+  NEED(v);
+  if (!loc) return fail(MGPLR_E_BADARG, "loc is NULL");
+  k_step_adversary<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, loc, done);
+  CK(cudaGetLastError());
+  return launch_adv_image(v, adv_image, time_step, st);
+}
+
+static OutPtrs outptrs(const mgplr_step_out *o) {
+  OutPtrs p{nullptr, nullptr, nullptr};
+  if (o) { p.image = o->image; p.direction = o->direction; p.image_u8 = o->image_u8; }
+  return p;
+}
+
+extern "C" int mgplr_reset_agent(mgplr_venv *v, const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  k_reset_agent<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, outptrs(out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_reset_random(mgplr_venv *v, const int32_t *n_walls, const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  k_reset_random<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, n_walls, outptrs(out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_reset_to_encoding(mgplr_venv *v, const uint8_t *enc, const int32_t *index, int32_t n,
+                                       const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  if (!enc || n < 1 || n > v->d.N) return fail(MGPLR_E_BADARG, "mgplr_reset_to_encoding: bad arguments");
+  k_reset_to_encoding<<<grid_for(n, 128), 128, 0, st>>>(v->d, enc, index, n, outptrs(out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_reset_to_actions(mgplr_venv *v, const int32_t *locs, int32_t len, const int32_t *index, int32_t n,
+                                      const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  if (!locs || len < 0 || len > 4095 || n < 1 || n > v->d.N) return fail(MGPLR_E_BADARG, "mgplr_reset_to_actions: bad arguments");
+  k_reset_to_actions<<<grid_for(n, 128), 128, 0, st>>>(v->d, locs, len, index, n, outptrs(out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_mutate_edits(mgplr_venv *v, const int32_t *locs, const int32_t *ops, const int32_t *n_edits,
+                                  int32_t max_edits, uint8_t *need, int32_t *n_free, void *stream) {
+  NEED(v);
+  if (!locs || !ops || !n_edits || max_edits < 0) return fail(MGPLR_E_BADARG, "mgplr_mutate_edits: bad arguments");
+  k_mutate_edits<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, locs, ops, n_edits, max_edits, need, n_free);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_mutate_finalize(mgplr_venv *v, const int32_t *choice, const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  k_mutate_finalize<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, choice, outptrs(out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls, int32_t last_step,
+                       const mgplr_step_out *out, cudaStream_t st) {
+  StepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.action = action; A.n_walls = n_walls; A.last_step = last_step;
+  if (out) A.o = *out;
+  const int grid = grid_for(v->d.N, TILE);
+  const size_t smem = step_smem_bytes(v->d.c.W);
+  const bool see = v->d.c.see_through;
+  if (see && !reset_random) k_step_env<true, false><<<grid, TILE, smem, st>>>(v->d, A);
+  else if (see && reset_random) k_step_env<true, true><<<grid, TILE, smem, st>>>(v->d, A);
+  else if (!see && !reset_random) k_step_env<false, false><<<grid, TILE, smem, st>>>(v->d, A);
+  else k_step_env<false, true><<<grid, TILE, smem, st>>>(v->d, A);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls,
+                              int32_t last_step, const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  if (!action) return fail(MGPLR_E_BADARG, "action is NULL");
+  return launch_step(v, action, reset_random, n_walls, last_step, out, st);
+}
+
+extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
+                                   const mgplr_step_out *out_dev, float *reward_host, uint8_t *flags_host,
+                                   float *ep_return_host, int32_t *ep_length_host, void *stream) {
+  NEED(v);
+  if (!action_host) return fail(MGPLR_E_BADARG, "action_host is NULL");
+  const size_t N = (size_t)v->d.N;
+  CK(cudaMemcpyAsync(v->act_dev, action_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  mgplr_step_out o;
+  memset(&o, 0, sizeof(o));
+  if (out_dev) o = *out_dev;
+  // packed device staging: reward f32 [N] | ep_return f32 [N] | ep_length i32 [N] | flags u8 [N]
+  float *rew_d = (float *)v->res_dev;
+  float *epr_d = rew_d + N;
+  int32_t *epl_d = (int32_t *)(epr_d + N);
+  uint8_t *flg_d = (uint8_t *)(epl_d + N);
+  // the device-side destinations requested by the caller keep working: copy after the kernel
+  mgplr_step_out k = o;
+  k.reward = rew_d; k.ep_return = epr_d; k.ep_length = epl_d; k.flags = flg_d;
+  if (int rc = launch_step(v, v->act_dev, reset_random, nullptr, last_step, &k, st)) return rc;
+  if (o.reward) CK(cudaMemcpyAsync(o.reward, rew_d, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (o.flags) CK(cudaMemcpyAsync(o.flags, flg_d, N, cudaMemcpyDeviceToDevice, st));
+  if (o.ep_return) CK(cudaMemcpyAsync(o.ep_return, epr_d, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (o.ep_length) CK(cudaMemcpyAsync(o.ep_length, epl_d, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (reward_host) CK(cudaMemcpyAsync(reward_host, rew_d, N * 4, cudaMemcpyDeviceToHost, st));
+  if (ep_return_host) CK(cudaMemcpyAsync(ep_return_host, epr_d, N * 4, cudaMemcpyDeviceToHost, st));
+  if (ep_length_host) CK(cudaMemcpyAsync(ep_length_host, epl_d, N * 4, cudaMemcpyDeviceToHost, st));
+  if (flags_host) CK(cudaMemcpyAsync(flags_host, flg_d, N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random,
+                             const mgplr_step_out *out_t0, void *stream) {
+  NEED(v);
+  if (!actions || T < 1) return fail(MGPLR_E_BADARG, "mgplr_rollout: bad arguments");
+  StepArgs A;
+  memset(&A, 0, sizeof(A));
+  if (out_t0) A.o = *out_t0;
+  const int grid = grid_for(v->d.N, TILE);
+  const size_t smem = step_smem_bytes(v->d.c.W);
+  const bool see = v->d.c.see_through;
+  if (see && !reset_random) k_rollout<true, false><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
+  else if (see && reset_random) k_rollout<true, true><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
+  else if (!see && !reset_random) k_rollout<false, false><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
+  else k_rollout<false, true><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_get_encodings(mgplr_venv *v, uint8_t *enc, void *stream) {
+  NEED(v);
+  if (!enc) return fail(MGPLR_E_BADARG, "enc is NULL");
+  const size_t total = (size_t)v->d.N * v->d.c.W * v->d.c.W;
+  k_encode<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v->d, enc);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mgplr_get_metrics(mgplr_venv *v, int32_t *metrics, void *stream) {
+  NEED(v);
+  if (!metrics) return fail(MGPLR_E_BADARG, "metrics is NULL");
+  k_get_metrics<<<grid_for(v->d.N, 256), 256, 0, st>>>(v->d, metrics);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mgplr_get_agent_state(mgplr_venv *v, int32_t *state, void *stream) {
+  NEED(v);
+  if (!state) return fail(MGPLR_E_BADARG, "state is NULL");
+  k_get_agent_state<<<grid_for(v->d.N, 256), 256, 0, st>>>(v->d, state);
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int mgplr_get_errors(mgplr_venv *v, uint32_t *errors, int32_t clear, void *stream) {
+  NEED(v);
+  if (!errors) return fail(MGPLR_E_BADARG, "errors is NULL");
+  k_get_errors<<<grid_for(v->d.N, 256), 256, 0, st>>>(v->d, errors, clear);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// host-side replay of the incremental generator on a copy of one env's state (no device mutation)
+extern "C" int mgplr_peek_rng(mgplr_venv *v, int32_t index, uint32_t *words_host, int32_t count) {
+  if (!v) return fail(MGPLR_E_BADARG, "venv handle is NULL");
+  CK(cudaSetDevice(v->device));
+  if (index < 0 || index >= v->d.N || !words_host || count < 0) return fail(MGPLR_E_BADARG, "mgplr_peek_rng: bad arguments");
+  CK(cudaDeviceSynchronize());
+  uint32_t mt[624], idx = 0;
+  CK(cudaMemcpy2D(mt, sizeof(uint32_t), v->d.mt + index, (size_t)v->d.N * sizeof(uint32_t), sizeof(uint32_t), 624,
+                  cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&idx, v->d.mti + index, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < count; k++) {
+    const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
+    uint32_t y = (mt[i] & 0x80000000u) | (mt[i1] & 0x7fffffffu);
+    y = mt[im] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    mt[i] = y; idx = i1;
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+    words_host[k] = y;
+  }
+  return 0;
+}

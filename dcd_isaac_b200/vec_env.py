@@ -1,0 +1,462 @@
+"""CudaAdversarialVecEnv -- the reference's vectorised adversarial-env API on top of libmgplr.so.
+
+It stands in for the whole stack `ParallelAdversarialVecEnv -> VecMonitor -> VecNormalize(ob=False) ->
+VecPreprocessImageWrapper` that util.create_parallel_env builds (util/__init__.py:184-220): same method
+names, argument meaning, return conventions and error behaviour as envs/wrappers/parallel_wrappers.py:232-460
+and envs/wrappers/obs_wrappers.py:157-230, but the N environments live in HBM and every call is one or two
+kernel launches.  Observations come back as float32 CUDA tensors already scaled by 1/10 and channels-first;
+`done` is a host numpy bool array and `infos` a list of dicts, exactly what
+envs/runners/adversarial_runner.py:497-588 consumes.
+
+No CPU fallback: constructing this class without the CUDA library or a CUDA device raises.
+"""
+import ctypes as C
+import hashlib
+import struct
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EnvConfig, StepOut, check, ptr
+from .registry import EDITOR_ACTION_SPACES, env_spec
+from .spaces import Box, Discrete
+
+F_DONE, F_TRUNC_KEY, F_TRUNC_VAL, F_GOAL = 1, 2, 4, 8
+
+
+def seed_limbs(seed):
+    """gym 0.15.7 `seeding.np_random(seed)`: limbs of hash_seed(seed) fed to RandomState.seed([...])
+    (reached from MultiGridEnv.seed, envs/multigrid/multigrid.py:465-468)."""
+    h = hashlib.sha512(str(int(seed) % 2 ** 64).encode('utf8')).digest()[:8]
+    lo, hi = struct.unpack('<2I', h)
+    if hi:
+        return (lo, hi, 2)
+    return (lo, 0, 1)
+
+
+class CudaAdversarialVecEnv(object):
+    def __init__(self, env_name, num_envs, device='cuda:0', seed=None, fixed_environment=None, **overrides):
+        spec = env_spec(env_name, fixed_environment=fixed_environment, **overrides)
+        self.env_name = env_name
+        self.spec = spec
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.MgplrError('CudaAdversarialVecEnv needs a CUDA device (no CPU fallback)')
+        if not torch.cuda.is_available():
+            raise _lib.MgplrError('no CUDA device visible: the MultiGrid path has no CPU fallback')
+        self.L = _lib.load()
+        self.W = int(spec['size'])
+        self.editor_actions = list(EDITOR_ACTION_SPACES[spec['editor_actions']])
+        self.cfg = EnvConfig(self.W, 5, spec['max_steps'], spec['max_episode_steps'], int(spec['see_through_walls']),
+                             spec['n_clutter'], int(spec['resample_n_clutter']), int(spec['choose_goal_last']),
+                             int(spec['fixed_environment']), len(self.editor_actions))
+        self.n_clutter = spec['n_clutter']
+        self.resample_n_clutter = bool(spec['resample_n_clutter'])
+        self.random_z_dim = 50
+        self.adversary_max_steps = self.n_clutter + 2
+        self.adversary_action_dim = (self.W - 2) ** 2
+        h = C.c_void_p()
+        torch.cuda.set_device(self.device)
+        check(self.L.mgplr_venv_create(C.byref(self.cfg), self.num_envs, self.device.index or 0, C.byref(h)),
+              'mgplr_venv_create')
+        self.h = h
+        self.closed = False
+        self.tstart = time.time()
+        self.seed_values = [seed] * self.num_envs
+        # spaces (multigrid.py:407-440, adversarial.py:126-145, obs_wrappers.py:118-155 transposes 'image')
+        N = self.num_envs
+        self.observation_space = {'image': Box(0, 255, (3, 5, 5), 'uint8'), 'direction': Box(0, 3, (1,), 'uint8')}
+        self.action_space = Discrete(7)
+        self.adversary_observation_space = {
+            'image': Box(0, 255, (3, self.W, self.W), 'uint8'),
+            'time_step': Box(0, self.adversary_max_steps, (1,), 'uint8'),
+            'random_z': Box(0, 1.0, (self.random_z_dim,), 'float32')}
+        self.adversary_action_space = Discrete(self.adversary_action_dim)
+        self.processed_action_dim = 1
+        # persistent small device buffers
+        dev = self.device
+        self._flags = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._ep_r = torch.zeros(N, dtype=torch.float32, device=dev)
+        self._ep_l = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._done_adv = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._errors = torch.zeros(N, dtype=torch.int32, device=dev)
+        # pinned host staging for the host-driven step (reward f32 | ep_r f32 | ep_l i32 | flags u8)
+        self._h_action = torch.zeros(N, dtype=torch.int64).pin_memory()
+        self._h_reward = torch.zeros(N, dtype=torch.float32).pin_memory()
+        self._h_ep_r = torch.zeros(N, dtype=torch.float32).pin_memory()
+        self._h_ep_l = torch.zeros(N, dtype=torch.int32).pin_memory()
+        self._h_flags = torch.zeros(N, dtype=torch.uint8).pin_memory()
+        if seed is not None:
+            self.set_seed([seed] * N)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _assert_not_closed(self):
+        assert not self.closed, 'Trying to operate on a CudaAdversarialVecEnv after calling close()'
+
+    def _new_obs(self, n=None, u8=False):
+        n = self.num_envs if n is None else n
+        obs = {'image': torch.empty(n, 3, 5, 5, dtype=torch.float32, device=self.device),
+               'direction': torch.empty(n, 1, dtype=torch.float32, device=self.device)}
+        return obs
+
+    def _out(self, obs=None, **kw):
+        o = StepOut()
+        if obs is not None:
+            o.image = ptr(obs['image'])
+            o.direction = ptr(obs['direction'])
+        for k, v in kw.items():
+            setattr(o, k, ptr(v))
+        return o
+
+    def _raise_errors(self):
+        """Surface device-side error flags with the reference's exception types."""
+        check(self.L.mgplr_get_errors(self.h, ptr(self._errors), 1, self._stream()), 'mgplr_get_errors')
+        e = self._errors.cpu().numpy()
+        if not e.any():
+            return
+        if (e & 4).any():
+            raise ValueError('Position passed to step_adversary is outside the grid.')
+        if (e & 2).any():
+            raise ValueError('Trying to place agent at empty start position.')
+        if (e & 1).any():
+            raise RuntimeError('Rejection sampling failed in place_obj')  # gym.error.RetriesExceededError analogue
+
+    def _adv_obs(self, image, time_step):
+        # random_z: np.random.uniform(size=(50,)).astype(float32) per env, in env order (adversarial.py:449-450)
+        z = np.random.uniform(size=(self.num_envs, self.random_z_dim)).astype(np.float32)
+        return {'image': image, 'time_step': time_step, 'random_z': torch.from_numpy(z).to(self.device)}
+
+    # ------------------------------------------------------------------ seeding
+    def set_seed(self, seeds):
+        """venv.set_seed(seeds) (parallel_wrappers.py:415-416): per-env MultiGridEnv.seed."""
+        self._assert_not_closed()
+        seeds = list(seeds)
+        assert len(seeds) == self.num_envs
+        limbs = np.zeros((self.num_envs, 2), np.uint32)
+        cnt = np.zeros(self.num_envs, np.int32)
+        for i, s in enumerate(seeds):
+            limbs[i, 0], limbs[i, 1], cnt[i] = seed_limbs(s)
+        check(self.L.mgplr_seed(self.h, ptr(limbs), ptr(cnt), None, self.num_envs, self._stream()), 'mgplr_seed')
+        self.seed_values = seeds
+        return [[s] for s in seeds]
+
+    def seed(self, seed, index):
+        """venv.seed(seed, index) (parallel_wrappers.py:268-270)."""
+        self._assert_not_closed()
+        lo, hi, c = seed_limbs(seed)
+        limbs = np.array([[lo, hi]], np.uint32)
+        cnt = np.array([c], np.int32)
+        idx = np.array([index], np.int32)
+        check(self.L.mgplr_seed(self.h, ptr(limbs), ptr(cnt), ptr(idx), 1, self._stream()), 'mgplr_seed')
+        self.seed_values[index] = seed
+        return [seed]
+
+    def get_seed(self):
+        return list(self.seed_values)
+
+    # ------------------------------------------------------------------ adversary phase
+    def reset(self):
+        """venv.reset(): AdversarialEnv.reset on every env (adversarial.py:194-229)."""
+        self._assert_not_closed()
+        N, W = self.num_envs, self.W
+        image = torch.empty(N, 3, W, W, dtype=torch.float32, device=self.device)
+        ts = torch.empty(N, 1, dtype=torch.float32, device=self.device)
+        check(self.L.mgplr_reset(self.h, ptr(image), ptr(ts), self._stream()), 'mgplr_reset')
+        return self._adv_obs(image, ts)
+
+    def step_adversary(self, action):
+        """venv.step_adversary(action) (parallel_wrappers.py:288-297, obs_wrappers.py:183-190)."""
+        self._assert_not_closed()
+        N, W = self.num_envs, self.W
+        a = torch.as_tensor(action)
+        if a.device.type != 'cuda':
+            a_host = a.reshape(-1).to(torch.int64)
+            if a_host.numel() and int(a_host.max()) >= self.adversary_action_dim:
+                raise ValueError('Position passed to step_adversary is outside the grid.')
+            a = a_host.to(self.device)
+        a = a.reshape(-1).to(torch.int64).contiguous()
+        assert a.numel() == N
+        image = torch.empty(N, 3, W, W, dtype=torch.float32, device=self.device)
+        ts = torch.empty(N, 1, dtype=torch.float32, device=self.device)
+        check(self.L.mgplr_step_adversary(self.h, ptr(a), ptr(image), ptr(ts), ptr(self._done_adv), self._stream()),
+              'mgplr_step_adversary')
+        done = self._done_adv.cpu().numpy().astype(bool)
+        rew = torch.zeros(N, 1, dtype=torch.float32, device=self.device)
+        return self._adv_obs(image, ts), rew, done, [{} for _ in range(N)]
+
+    # ------------------------------------------------------------------ level resets
+    def reset_agent(self):
+        self._assert_not_closed()
+        obs = self._new_obs()
+        o = self._out(obs)
+        check(self.L.mgplr_reset_agent(self.h, C.byref(o), self._stream()), 'mgplr_reset_agent')
+        self._raise_errors()
+        return obs
+
+    def reset_random(self):
+        self._assert_not_closed()
+        obs = self._new_obs()
+        o = self._out(obs)
+        nw = None
+        if self.resample_n_clutter:  # _resample_n_clutter: np.random.randint(0, n_clutter) per env (adversarial.py:151-156)
+            nw = torch.from_numpy(np.random.randint(0, self.n_clutter, size=self.num_envs).astype(np.int32)).to(self.device)
+        check(self.L.mgplr_reset_random(self.h, ptr(nw), C.byref(o), self._stream()), 'mgplr_reset_random')
+        self._raise_errors()
+        return obs
+
+    def _levels_to_device(self, levels):
+        """list of levels -> ('bytes', u8 [n,W,W,3]) or ('str', i32 [n,len])."""
+        if isinstance(levels[0], str):
+            locs = [[int(a) for a in l.split()] for l in levels]
+            ln = len(locs[0])
+            assert all(len(l) == ln for l in locs), 'action-string levels must have equal length'
+            return 'str', torch.tensor(locs, dtype=torch.int32).reshape(len(levels), ln).to(self.device), ln
+        arr = np.stack([np.asarray(l, dtype=np.uint8).reshape(self.W, self.W, 3) for l in levels])
+        return 'bytes', torch.from_numpy(np.ascontiguousarray(arr)).to(self.device), 0
+
+    def _reset_to_levels(self, levels, index):
+        kind, data, ln = self._levels_to_device(levels)
+        n = len(levels)
+        obs = self._new_obs()
+        o = self._out(obs)
+        idx = None if index is None else torch.tensor(index, dtype=torch.int32, device=self.device)
+        if kind == 'bytes':
+            check(self.L.mgplr_reset_to_encoding(self.h, ptr(data), ptr(idx), n, C.byref(o), self._stream()),
+                  'mgplr_reset_to_encoding')
+        else:
+            check(self.L.mgplr_reset_to_actions(self.h, ptr(data), ln, ptr(idx), n, C.byref(o), self._stream()),
+                  'mgplr_reset_to_actions')
+        self._raise_errors()
+        return obs
+
+    def reset_to_level(self, level, index):
+        """venv.reset_to_level(level, index) -> obs of that env, leading dim 1 (parallel_wrappers.py:334-340)."""
+        self._assert_not_closed()
+        obs = self._reset_to_levels([level], [int(index)])
+        return {k: v[index:index + 1].clone() for k, v in obs.items()}
+
+    def reset_to_level_batch(self, level):
+        self._assert_not_closed()
+        assert len(level) == self.num_envs
+        return self._reset_to_levels(list(level), None)
+
+    def mutate_level(self, num_edits, edits=None):
+        """venv.mutate_level(num_edits) (parallel_wrappers.py:352-359 -> adversarial.py:317-397).
+
+        The GLOBAL np.random draws are made here on the host, per env in env order, exactly as the reference
+        makes them; `edits` = (locs[N][k], ops[N][k], n_edits[N], choice[N][2]) replays recorded draws.
+        Returns the agent observation (not used by the runner)."""
+        self._assert_not_closed()
+        N = self.num_envs
+        num_tiles = (self.W - 2) ** 2
+        if edits is None:
+            locs_l, ops_l = [], []
+            for _ in range(N):
+                edit_locs = list(set(np.random.randint(0, num_tiles, num_edits)))
+                action_idx = np.random.randint(0, len(self.editor_actions), len(edit_locs))
+                locs_l.append(edit_locs)
+                ops_l.append(action_idx)
+            choice = None
+        else:
+            locs_l, ops_l, n_l, choice = edits
+            locs_l = [list(l[:n]) for l, n in zip(locs_l, n_l)]
+            ops_l = [list(o[:n]) for o, n in zip(ops_l, n_l)]
+        mx = max(1, max(len(l) for l in locs_l))
+        locs = np.zeros((N, mx), np.int32)
+        ops = np.zeros((N, mx), np.int32)
+        n_ed = np.zeros(N, np.int32)
+        for i in range(N):
+            n_ed[i] = len(locs_l[i])
+            locs[i, :n_ed[i]] = locs_l[i]
+            ops[i, :n_ed[i]] = ops_l[i]
+        d_locs, d_ops, d_n = (torch.from_numpy(a).to(self.device) for a in (locs, ops, n_ed))
+        need = torch.zeros(N, 2, dtype=torch.uint8, device=self.device)
+        nfree = torch.zeros(N, 2, dtype=torch.int32, device=self.device)
+        check(self.L.mgplr_mutate_edits(self.h, ptr(d_locs), ptr(d_ops), ptr(d_n), mx, ptr(need), ptr(nfree), self._stream()),
+              'mgplr_mutate_edits')
+        if choice is None:
+            need_h, nfree_h = need.cpu().numpy(), nfree.cpu().numpy()
+            choice = np.zeros((N, 2), np.int32)
+            for i in range(N):  # np.random.choice(free_idx) (adversarial.py:308-315), goal first then agent
+                for k in range(2):
+                    if need_h[i, k]:
+                        if nfree_h[i, k] <= 0:
+                            raise ValueError("'a' cannot be empty unless no samples are taken")
+                        choice[i, k] = np.random.choice(int(nfree_h[i, k]))
+        d_choice = torch.from_numpy(np.ascontiguousarray(choice, dtype=np.int32)).to(self.device)
+        obs = self._new_obs()
+        o = self._out(obs)
+        check(self.L.mgplr_mutate_finalize(self.h, ptr(d_choice), C.byref(o), self._stream()), 'mgplr_mutate_finalize')
+        self._raise_errors()
+        self.last_mutation = (need, nfree)
+        return obs
+
+    # ------------------------------------------------------------------ student phase
+    def step_env(self, action, reset_random=False):
+        """venv.step_env(action, reset_random) -> (obs, reward f32 [N,1], done np.bool_[N], infos[N])
+        (vec_env.py:113-118; folded wrappers: time_limit.py:24-33, vec_monitor.py:60-85, obs_wrappers.py:168-181)."""
+        self._assert_not_closed()
+        N = self.num_envs
+        obs = self._new_obs()
+        tr = self._new_obs()
+        rew = torch.empty(N, 1, dtype=torch.float32, device=self.device)
+        o = self._out(obs, reward=rew, flags=self._flags, ep_return=self._ep_r, ep_length=self._ep_l,
+                      trunc_image=tr['image'], trunc_direction=tr['direction'])
+        a = torch.as_tensor(action)
+        if reset_random and self.resample_n_clutter:
+            raise NotImplementedError('step_env(reset_random=True) with resample_n_clutter: use step_env_device')
+        if a.device.type == 'cuda':
+            a = a.reshape(-1).to(torch.int64).contiguous()
+            check(self.L.mgplr_step_env(self.h, ptr(a), int(bool(reset_random)), None, 0, C.byref(o), self._stream()),
+                  'mgplr_step_env')
+            flags = self._flags.cpu().numpy().copy()
+            ep_r = self._ep_r.cpu().numpy().copy()
+            ep_l = self._ep_l.cpu().numpy().copy()
+        else:
+            self._h_action.copy_(a.reshape(-1))
+            check(self.L.mgplr_step_env_host(self.h, ptr(self._h_action), int(bool(reset_random)), 0, C.byref(o),
+                                             ptr(self._h_reward), ptr(self._h_flags), ptr(self._h_ep_r), ptr(self._h_ep_l),
+                                             self._stream()), 'mgplr_step_env_host')
+            flags = self._h_flags.numpy().copy()
+            ep_r = self._h_ep_r.numpy().copy()
+            ep_l = self._h_ep_l.numpy().copy()
+        done = (flags & F_DONE) != 0
+        infos = [{} for _ in range(N)]
+        if flags.any():
+            t_now = round(time.time() - self.tstart, 6)
+            for i in np.nonzero(flags & (F_DONE | F_TRUNC_KEY))[0]:
+                info = infos[i]
+                if flags[i] & F_TRUNC_KEY:
+                    info['truncated'] = bool(flags[i] & F_TRUNC_VAL)
+                    info['truncated_obs'] = {'image': tr['image'][i], 'direction': tr['direction'][i]}
+                if flags[i] & F_DONE:
+                    info['episode'] = {'r': ep_r[i], 'l': ep_l[i], 't': t_now}
+            if (flags & F_DONE).any():
+                self._check_errors_lazily()
+        return obs, rew, done, infos
+
+    def _check_errors_lazily(self):
+        self._raise_errors()
+
+    def step_env_device(self, action, out, reset_random=False, last_step=0, n_walls=None):
+        """Device-resident step: `action` i64 [N] CUDA tensor, `out` a StepOut of raw pointers into rollout storage.
+        No host synchronisation; the caller reads flags/rewards from its own tensors."""
+        check(self.L.mgplr_step_env(self.h, ptr(action), int(bool(reset_random)), ptr(n_walls), int(last_step),
+                                    C.byref(out), self._stream()), 'mgplr_step_env')
+
+    def rollout_device(self, actions_u8, out, reset_random=False, last_step=0):
+        """T transitions in one launch from a recorded u8 [T, N] action stream (mgplr_rollout)."""
+        T = int(actions_u8.shape[0])
+        o = out
+        if last_step:
+            raise NotImplementedError
+        check(self.L.mgplr_rollout(self.h, ptr(actions_u8), T, int(bool(reset_random)), C.byref(o), self._stream()),
+              'mgplr_rollout')
+
+    def step(self, action):
+        raise NotImplementedError('step() auto-reset()s to an EMPTY adversarial grid in the reference '
+                                  '(parallel_wrappers.py:20-25); evaluation envs are not part of this build yet')
+
+    # ------------------------------------------------------------------ getters
+    def get_encodings(self, index=None):
+        """list of np.uint8 [W,W,3] (parallel_wrappers.py:422-423 -> adversarial.py:162-164)."""
+        enc = self.get_encodings_device().cpu().numpy()
+        if index is None or len(index) == 0:
+            return [enc[i] for i in range(self.num_envs)]
+        return [enc[i] for i in index]
+
+    def get_encodings_device(self):
+        enc = torch.empty(self.num_envs, self.W, self.W, 3, dtype=torch.uint8, device=self.device)
+        check(self.L.mgplr_get_encodings(self.h, ptr(enc), self._stream()), 'mgplr_get_encodings')
+        return enc
+
+    def _metrics(self):
+        m = torch.empty(self.num_envs, 4, dtype=torch.int32, device=self.device)
+        check(self.L.mgplr_get_metrics(self.h, ptr(m), self._stream()), 'mgplr_get_metrics')
+        return m.cpu().numpy()
+
+    def get_num_blocks(self):
+        return [int(v) for v in self._metrics()[:, 0]]
+
+    def get_distance_to_goal(self):
+        return [int(v) for v in self._metrics()[:, 1]]
+
+    def get_passable(self):
+        return [(-1 if v < 0 else bool(v)) for v in self._metrics()[:, 2]]
+
+    def get_shortest_path_length(self):
+        return [int(v) for v in self._metrics()[:, 3]]
+
+    def get_agent_state(self):
+        """int32 [N,8]: x, y, dir, step_count, elapsed, adversary_step_count, adversary_max_steps, rng words used."""
+        s = torch.empty(self.num_envs, 8, dtype=torch.int32, device=self.device)
+        check(self.L.mgplr_get_agent_state(self.h, ptr(s), self._stream()), 'mgplr_get_agent_state')
+        return s.cpu().numpy()
+
+    def peek_rng(self, index, count=4):
+        w = np.zeros(count, np.uint32)
+        check(self.L.mgplr_peek_rng(self.h, int(index), ptr(w), count), 'mgplr_peek_rng')
+        return w
+
+    def get_max_episode_steps(self):
+        return self.spec['max_episode_steps']
+
+    def get_observation_space(self):
+        return self.observation_space
+
+    def get_adversary_observation_space(self):
+        return self.adversary_observation_space
+
+    def get_adversary_action_space(self):
+        return self.adversary_action_space
+
+    def remote_attr(self, name, data=None, flatten=False, index=None):
+        table = {'encoding': self.get_encodings, 'n_clutter_placed': self.get_num_blocks, 'passable': self.get_passable,
+                 'shortest_path_length': self.get_shortest_path_length, 'distance_to_goal': self.get_distance_to_goal,
+                 'seed_value': self.get_seed}
+        if name not in table:
+            raise NotImplementedError(name)
+        res = table[name]()
+        if index is not None and len(index) > 0:
+            res = [res[i] for i in index]
+        return res if flatten else [[r] for r in res]
+
+    def get_images(self):
+        raise NotImplementedError('RGB screenshots are out of scope (SURVEY.md 8f rank 4)')
+
+    def state_bytes(self):
+        return int(self.L.mgplr_venv_state_bytes(self.h))
+
+    def close(self):
+        if not self.closed and getattr(self, 'h', None):
+            self.L.mgplr_venv_destroy(self.h)
+            self.h = None
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def create_parallel_env(args, adversary=True, device='cuda:0'):
+    """Drop-in for util.create_parallel_env (util/__init__.py:184-220): returns (venv, ued_venv) with
+    ued_venv is venv for MultiGrid, seeded [0..N-1] (or [args.seed]*N for singleton_env)."""
+    if not args.env_name.startswith('MultiGrid'):
+        raise NotImplementedError('only the MultiGrid adversarial environments are built (SURVEY.md 8)')
+    singleton = bool(getattr(args, 'singleton_env', False))
+    venv = CudaAdversarialVecEnv(args.env_name, args.num_processes, device=device,
+                                 fixed_environment=True if singleton else None)
+    if singleton:
+        seeds = [args.seed] * args.num_processes
+    else:
+        seeds = [i for i in range(args.num_processes)]
+    venv.set_seed(seeds)
+    return venv, venv

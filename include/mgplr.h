@@ -1,0 +1,216 @@
+/*
+ * mgplr.h -- C ABI of the B200-native MultiGrid / PLR hot path (libmgplr.so).
+ *
+ * Plain pointers and sizes only: no torch types.  Device pointers are raw CUDA device addresses
+ * (a PyTorch tensor's data_ptr()), `stream` is a cudaStream_t passed as void* (0 = legacy default
+ * stream).  Every entry point returns 0 on success, a positive cudaError_t, or a negative
+ * MGPLR_E_* argument error; mgplr_last_error() returns a thread-local message.
+ *
+ * The reference (linjiw/dcd-isaac) has no FFI layer: its boundary is the duck-typed Python objects
+ * consumed by envs/runners/adversarial_runner.py.  Each entry point below therefore names the
+ * reference method it replaces (file:line relative to the reference root); the Python mirror of
+ * those objects lives in dcd_isaac_b200/{vec_env,level_sampler,level_store}.py and binds these
+ * symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * State layout, kernels and rooflines: DESIGN.md.
+ */
+#ifndef MGPLR_H
+#define MGPLR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGPLR_ABI_VERSION 1
+
+#define MGPLR_E_BADARG (-1)
+#define MGPLR_E_UNSUPPORTED (-2)
+
+/* step_env / info flag bits (uint8 per env) */
+#define MGPLR_F_DONE 1u      /* done returned to the runner (goal, env max_steps or TimeLimit) */
+#define MGPLR_F_TRUNC_KEY 2u /* 'truncated' in info (envs/wrappers/time_limit.py:28-31) */
+#define MGPLR_F_TRUNC_VAL 4u /* info['truncated'] is True */
+#define MGPLR_F_GOAL 8u      /* goal reached this step (reward != 0) */
+
+/* AdversarialEnv constructor arguments (envs/multigrid/adversarial.py:67-79) + the registered
+ * TimeLimit (envs/registration.py:118-120, envs/wrappers/time_limit.py:15-22). */
+typedef struct mgplr_env_config {
+  int32_t width;              /* size: grid side W, 5 <= W <= 32 */
+  int32_t agent_view_size;    /* must be 5 (every registered adversarial env) */
+  int32_t max_steps;          /* env max_steps */
+  int32_t max_episode_steps;  /* TimeLimit._max_episode_steps (< 32768) */
+  int32_t see_through_walls;  /* 1: no occlusion; 0: gym_minigrid process_vis occlusion */
+  int32_t n_clutter;
+  int32_t resample_n_clutter;
+  int32_t choose_goal_last;
+  int32_t fixed_environment;
+  int32_t n_editor_actions;   /* 2 '-.', 3 '-.g', 4 '-.ag' (adversarial.py:40-56) */
+} mgplr_env_config;
+
+typedef struct mgplr_venv mgplr_venv; /* opaque: N environments resident in HBM */
+
+/* Destinations of one vectorised step (all device pointers; any may be NULL = not wanted).
+ * Layouts are those of algos/storage.py:62-112 so the kernel writes straight into
+ * RolloutStorage: obs['image'][t+1], obs['direction'][t+1], rewards[t], masks[t+1], ... */
+typedef struct mgplr_step_out {
+  float *image;             /* f32 [N][3][5][5] = uint8/10.0, channels first (obs_wrappers.py:104-110) */
+  float *direction;         /* f32 [N][1] */
+  float *reward;            /* f32 [N][1] */
+  uint8_t *flags;           /* u8  [N]  MGPLR_F_* */
+  float *ep_return;         /* f32 [N]  VecMonitor info['episode']['r'], valid where DONE */
+  int32_t *ep_length;       /* i32 [N]  info['episode']['l'], valid where DONE */
+  float *trunc_image;       /* f32 [N][3][5][5] info['truncated_obs'], written where TRUNC_KEY */
+  float *trunc_direction;   /* f32 [N][1] */
+  float *masks;             /* f32 [N][1] 1-done            (adversarial_runner.py:566-567) */
+  float *bad_masks;         /* f32 [N][1] 0 iff TRUNC_KEY   (adversarial_runner.py:568-570) */
+  float *cliffhanger_masks; /* f32 [N][1] 0 iff cliffhanger (adversarial_runner.py:571-573) */
+  uint8_t *image_u8;        /* u8  [N][5][5][3] raw gym_minigrid encoding (packed secondary layout) */
+} mgplr_step_out;
+
+const char *mgplr_last_error(void);
+int mgplr_abi_version(void);
+
+/* util.create_parallel_env (util/__init__.py:184-220): allocate N envs on `device`; each starts as
+ * the empty walled grid of AdversarialEnv.__init__ -> reset(). */
+int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, int32_t device, mgplr_venv **out);
+void mgplr_venv_destroy(mgplr_venv *v);
+int32_t mgplr_venv_num_envs(const mgplr_venv *v);
+/* bytes of HBM held by the handle */
+int64_t mgplr_venv_state_bytes(const mgplr_venv *v);
+
+/* venv.set_seed / venv.seed(seed, index) (parallel_wrappers.py:268-270,415-416 -> multigrid.py:465-468
+ * -> gym seeding.np_random): limbs = _int_list_from_bigint(hash_seed(seed)), HOST array [n][2] (+ count
+ * [n]); index = NULL seeds envs 0..n-1.  Runs MT19937 init_by_array on the device. */
+int mgplr_seed(mgplr_venv *v, const uint32_t *limbs_host, const int32_t *n_limbs_host, const int32_t *index_host,
+               int32_t n, void *stream);
+
+/* venv.reset() -> AdversarialEnv.reset (adversarial.py:194-229).  adv_image f32 [N][3][W][W] (=/10, CHW),
+ * time_step f32 [N][1].  random_z is drawn by the host (global np.random, adversarial.py:449-450). */
+int mgplr_reset(mgplr_venv *v, float *adv_image, float *time_step, void *stream);
+
+/* venv.step_adversary(action) (parallel_wrappers.py:288-297 -> adversarial.py:452-539).  loc i64 [N].
+ * done u8 [N].  Out-of-range locations set the env's error flag (mgplr_get_errors) and do nothing. */
+int mgplr_step_adversary(mgplr_venv *v, const int64_t *loc, float *adv_image, float *time_step, uint8_t *done,
+                         void *stream);
+
+/* venv.reset_agent() (parallel_wrappers.py:314-321 -> adversarial.py:238-269, time_limit.py:46-48,
+ * vec_monitor.py:42-46).  Only `image`, `direction`, `image_u8` of `out` are used. */
+int mgplr_reset_agent(mgplr_venv *v, const mgplr_step_out *out, void *stream);
+
+/* venv.reset_random() (parallel_wrappers.py:324-331 -> adversarial.py:541-581).  n_walls i32 [N] or NULL:
+ * the global-rng draw of _resample_n_clutter for resample_n_clutter envs (else int(n_clutter/2)). */
+int mgplr_reset_random(mgplr_venv *v, const int32_t *n_walls, const mgplr_step_out *out, void *stream);
+
+/* venv.reset_to_level(level, index) / reset_to_level_batch(levels), byte form
+ * (parallel_wrappers.py:334-349 -> adversarial.py:271-294, multigrid.py:264-280).
+ * enc u8 [n][W][W][3] (device); index i32 [n] (device) or NULL = envs 0..n-1.  Outputs (only image /
+ * direction / image_u8) are written at row `index[k]` of the full-N arrays. */
+int mgplr_reset_to_encoding(mgplr_venv *v, const uint8_t *enc, const int32_t *index, int32_t n,
+                            const mgplr_step_out *out, void *stream);
+
+/* Same, action-string form: locs i32 [n][len] (device), replayed through step_adversary. */
+int mgplr_reset_to_actions(mgplr_venv *v, const int32_t *locs, int32_t len, const int32_t *index, int32_t n,
+                           const mgplr_step_out *out, void *stream);
+
+/* venv.mutate_level(num_edits) (parallel_wrappers.py:352-359 -> adversarial.py:317-397) in two phases so the
+ * host can make the global-np.random draws exactly where the reference makes them:
+ *  edits:    locs i32 [N][max_edits], ops i32 [N][max_edits], n_edits i32 [N] (iteration order of
+ *            list(set(randint)), editor-action indices).  need u8 [N][2] / n_free i32 [N][2] report which
+ *            fallbacks (goal, agent) are required and the length of the free-cell list.
+ *  finalize: choice i32 [N][2] = index into the row-major free list picked by np.random.choice; then metrics
+ *            and reset_agent.  */
+int mgplr_mutate_edits(mgplr_venv *v, const int32_t *locs, const int32_t *ops, const int32_t *n_edits,
+                       int32_t max_edits, uint8_t *need, int32_t *n_free, void *stream);
+int mgplr_mutate_finalize(mgplr_venv *v, const int32_t *choice, const mgplr_step_out *out, void *stream);
+
+/* venv.step_env(action, reset_random) (vec_env.py:113-118, parallel_wrappers.py:27-37,299-311) with the
+ * wrapper chain folded in (time_limit.py:24-33, vec_monitor.py:60-85, obs_wrappers.py:168-181).
+ * action i64 [N] (device).  last_step != 0 additionally applies adversarial_runner.py:521-530 to the
+ * mask outputs (done forced, cliffhanger for not-done envs).  n_walls as in mgplr_reset_random. */
+int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls,
+                   int32_t last_step, const mgplr_step_out *out, void *stream);
+
+/* The same transition driven from HOST buffers (the reference's calling convention: actions arrive as a
+ * CPU tensor, adversarial_runner.py:512-517; reward / done / info come back to the host).  Observations
+ * stay in HBM at out->image (rollout storage).  Copies: action H2D 8 B/env; reward 4 + flags 1 +
+ * ep_return 4 + ep_length 4 B/env D2H.  Synchronises `stream` before returning. */
+int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
+                        const mgplr_step_out *out_dev, float *reward_host, uint8_t *flags_host,
+                        float *ep_return_host, int32_t *ep_length_host, void *stream);
+
+/* T consecutive step_env transitions in ONE launch from a recorded action stream u8 [T][N]: env state
+ * stays in shared memory / registers across steps (replayed-seed evaluation, random-policy rollouts).
+ * Outputs are the [T]-leading versions of mgplr_step_out fields: image f32 [T][N][3][5][5], direction
+ * [T][N][1], reward [T][N][1], flags u8 [T][N]; masks f32 [T][N][1] etc.  Any may be NULL. */
+int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random,
+                  const mgplr_step_out *out_t0, void *stream);
+
+/* Getters (parallel_wrappers.py:422-448): encodings u8 [N][W][W][3] = AdversarialEnv.encoding;
+ * metrics i32 [N][4] = n_clutter_placed, distance_to_goal, passable, shortest_path_length. */
+int mgplr_get_encodings(mgplr_venv *v, uint8_t *enc, void *stream);
+int mgplr_get_metrics(mgplr_venv *v, int32_t *metrics, void *stream);
+/* i32 [N][8]: agent x, y, dir, step_count, elapsed, adversary_step_count, adversary_max_steps, rng words used */
+int mgplr_get_agent_state(mgplr_venv *v, int32_t *state, void *stream);
+/* u32 [N]: bit0 RetriesExceeded (multigrid.py:597-599), bit1 reset_agent without start position
+ * (adversarial.py:248-249), bit2 step_adversary loc out of range (adversarial.py:465-466).  Sticky until read
+ * with clear != 0. */
+int mgplr_get_errors(mgplr_venv *v, uint32_t *errors, int32_t clear, void *stream);
+/* next `count` raw MT19937 words of env `index` WITHOUT consuming them (test introspection) */
+int mgplr_peek_rng(mgplr_venv *v, int32_t index, uint32_t *words_host, int32_t count);
+
+/* ---- rollout math (algos/storage.py, level_replay/level_sampler.py); stateless launchers ---- */
+
+/* RolloutStorage.compute_gae_returns (algos/storage.py:233-256).  rewards f32 [T][N], value_preds f32
+ * [T+1][N] (already the truncated/denormalised buffer the reference would use, with value_preds[T] =
+ * next_value), masks f32 [T+1][N]; returns f32 [T+1][N] gets rows 0..T-1.  Bit-identical op order. */
+int mgplr_gae(const float *rewards, const float *value_preds, const float *masks, float *returns, int32_t T,
+              int32_t N, double gamma, double gae_lambda, void *stream);
+
+#define MGPLR_SCORE_POSITIVE_VALUE_LOSS 0
+#define MGPLR_SCORE_SIGNED_VALUE_LOSS 1
+#define MGPLR_SCORE_VALUE_L1 2
+#define MGPLR_SCORE_MAX_MC 3 /* per-episode pieces of grounded_* : sum of rewards and value sums */
+
+/* Episode record produced by the scoring kernel, in the reference's actor-major / time-minor order. */
+typedef struct mgplr_episode {
+  int32_t actor;
+  int32_t t_start;
+  int32_t t_end;      /* exclusive: the done step */
+  int32_t seed;       /* level_seeds[t_start][actor] */
+  float mean_score;   /* strategy mean over the episode */
+  float max_score;    /* strategy max over the episode */
+  float reward_sum;   /* sum of rewards[t_start:t_end] (grounded value, level_sampler.py:534) */
+  float value_sum;    /* sum of value_preds[t_start:t_end] */
+  float value_min;    /* min of value_preds[t_start:t_end] (max of grounded - v) */
+  int32_t cliffhanger; /* cliffhanger_masks[t_end][actor] == 0 -> skipped by the sampler */
+} mgplr_episode;
+
+/* LevelSampler._update_with_rollouts segmentation + score functions (level_sampler.py:486-549,307-349).
+ * masks / cliffhanger_masks f32 [T+1][N], returns / value_preds f32 [T+1][N], rewards f32 [T][N],
+ * level_seeds i32 [T][N].  Writes up to max_episodes records to `episodes` (device) in canonical order and
+ * the count to n_episodes (device i32). */
+int mgplr_plr_episode_scores(const float *masks, const float *cliffhanger_masks, const float *returns,
+                             const float *value_preds, const float *rewards, const int32_t *level_seeds, int32_t T,
+                             int32_t N, int32_t strategy, mgplr_episode *episodes, int32_t max_episodes,
+                             int32_t *n_episodes, void *stream);
+
+/* LevelSampler.sample_weights (level_sampler.py:726-785), rank transform + power staleness, fp64.
+ * scores / staleness / unseen f64 [n] -> weights f64 [n].  Ties in the rank transform are broken by
+ * index (higher index = better rank), the order numpy's stable-on-ties flip(argsort) would give. */
+int mgplr_plr_sample_weights(const double *scores, const double *staleness, const double *unseen, int32_t n,
+                             double temperature, double staleness_coef, double staleness_temperature,
+                             double *weights, void *stream);
+
+/* n_draws sequential _sample_replay_level draws (level_sampler.py:664-680 + 601-604) with recorded uniforms
+ * u f64 [n_draws] (np.random.choice's single random_sample each): staleness is updated between draws
+ * exactly as the reference does.  out_index i32 [n_draws]; staleness f64 [n] updated in place. */
+int mgplr_plr_sample_replay(const double *scores, double *staleness, const double *unseen, int32_t n,
+                            double temperature, double staleness_coef, double staleness_temperature,
+                            const double *u, int32_t n_draws, int32_t *out_index, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGPLR_H */
