@@ -81,17 +81,19 @@ struct Rows {
 // producing one word per draw in place is output-identical to the batch twist and never stalls a
 // lane for 624 dependent iterations.
 struct Rng {
-  uint32_t *mt;
+  uint32_t *mt, *mti_p, *words_p;
   int N, e;
   uint32_t idx, used;
   bool loaded;
-  const Dev *d;
-  __device__ Rng(const Dev &dev, int env) : mt(dev.mt), N(dev.N), e(env), idx(0), used(0), loaded(false), d(&dev) {}
+  __device__ Rng(const Dev &dev, int env)
+      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), loaded(false) {}
+  __device__ Rng(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env)
+      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), loaded(false) {}
   __device__ __forceinline__ void load() {
-    if (!loaded) { idx = d->mti[e]; used = d->words[e]; loaded = true; }
+    if (!loaded) { idx = mti_p[e]; used = words_p[e]; loaded = true; }
   }
   __device__ __forceinline__ void store() {
-    if (loaded) { d->mti[e] = idx; d->words[e] = used; }
+    if (loaded) { mti_p[e] = idx; words_p[e] = used; }
   }
   __device__ uint32_t next() {
     load();

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -48,10 +49,17 @@ struct mgplr_venv {
   int sm_count;
 };
 
-constexpr int TILE = 128;  // envs (= threads) per CTA in the hot kernels
-
-// dynamic shared memory of the step kernels: obs tile [TILE][75] f32 then wall rows [W][TILE] u32
-static size_t step_smem_bytes(int W) { return (size_t)TILE * kObsFloats * 4 + (size_t)W * TILE * 4; }
+// envs (= threads) per CTA in the hot kernels; MGPLR_TILE=64|128 overrides (tuning)
+static int step_tile() {
+  static int tile = 0;
+  if (!tile) {
+    const char *e = getenv("MGPLR_TILE");
+    tile = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  return tile;
+}
+// dynamic shared memory: `bufs` obs tiles [TILE][75] f32 then wall rows [W][TILE] u32
+static size_t step_smem_bytes(int W, int tile, int bufs) { return (size_t)bufs * tile * kObsFloats * 4 + (size_t)W * tile * 4; }
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,10 +69,6 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
                : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------ obs emit (cold paths)
@@ -350,12 +354,50 @@ struct StepArgs {
   mgplr_step_out o;
 };
 
-// One env transition for the thread's env.  `R` are the env's wall rows in shared memory.  Returns flags.
+// ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
+
+// agent_is_done's respawn (multigrid.py:821-838): a random empty cell drawn with the env RNG.  Returns x | y<<8.
+__device__ __noinline__ uint32_t rare_respawn(uint32_t *mt, uint32_t *mti, uint32_t *words, int N, int e, uint32_t *rows,
+                                              int stride, int W, int gx, int gy) {
+  Rng rng(mt, mti, words, N, e);
+  Env s{};
+  s.gx = gx; s.gy = gy; s.has_agent = 0;
+  int px = 0, py = 0;
+  place_random(Rows{rows, stride}, s, rng, W, -1, px, py);
+  rng.store();
+  return (uint32_t)px | ((uint32_t)py << 8);
+}
+
+// info['truncated_obs'] (time_limit.py:29-31) / runner cliffhanger obs (adversarial_runner.py:523-528)
+__device__ __noinline__ void rare_emit_trunc(uint32_t *rows, int stride, uint4 hot, int W, int see, float *image, float *direction,
+                                             int e) {
+  const Env s = unpack(hot);
+  const Rows R{rows, stride};
+  const View v = see ? render_view<true>(R, s, W) : render_view<false>(R, s, W);
+  if (image) emit_obs_f32(v, image + (size_t)e * kObsFloats);
+  if (direction) direction[e] = (float)s.adir;
+}
+
+// worker.step_env's reset_random branch (parallel_wrappers.py:30-33)
+__device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int stride, uint4 hot, int e, int n_walls) {
+  Env s = unpack(hot);
+  uint32_t adv = d.adv[e], err = 0;
+  int4 met;
+  Rng rng(d, e);
+  reset_random(Rows{rows, stride}, s, adv, met, rng, d, e, n_walls, err);
+  rng.store();
+  d.adv[e] = adv; d.metrics[e] = met;
+  if (err) d.err[e] |= err;
+  return pack(s);
+}
+
+// One env transition for the thread's env; `rows` = this env's wall rows in shared memory.  Returns flags.
 template <bool SEE, bool RR>
-__device__ __forceinline__ uint32_t step_one(const Dev &d, const Rows &R, Env &s, int e, int a, const StepArgs &A, float *s_obs,
-                                             float &rew_out, bool &rows_dirty) {
+__device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int stride, Env &s, int e, int a, const StepArgs &A,
+                                             float *s_obs, float &rew_out, bool &rows_dirty) {
   const Cfg &c = d.c;
-  uint32_t flags = 0, err = 0;
+  const Rows R{rows, stride};
+  uint32_t flags = 0;
   double rew = 0.0;
   // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
   s.step_count++;
@@ -364,14 +406,9 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, const Rows &R, Env &s
   else if (a == 1) s.adir = (s.adir + 1) & 3;
   else if (a == 2) {
     if (fx == s.gx && fy == s.gy) {
-      // agent_is_done (multigrid.py:821-838): remove the agent, done, respawn at a random empty cell with the
-      // env RNG (dir forced to 0, multigrid.py:668-672); reward = MiniGridEnv._reward()
-      Rng rng(d, e);
-      s.has_agent = 0; s.done_flag = 1;
-      int px = s.ax, py = s.ay;
-      place_random(R, s, rng, c.W, -1, px, py);
-      rng.store();
-      s.has_agent = 1; s.ax = px; s.ay = py; s.adir = 0;
+      // agent_is_done: remove the agent, done, respawn (dir forced to 0, multigrid.py:668-672); reward = _reward()
+      const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.N, e, rows, stride, c.W, s.gx, s.gy);
+      s.done_flag = 1; s.has_agent = 1; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
       rew = __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)s.step_count, (double)c.max_steps)));
       flags |= MGPLR_F_GOAL;
     } else if (!is_wall(R, fx, fy)) { s.ax = fx; s.ay = fy; }
@@ -381,14 +418,12 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, const Rows &R, Env &s
   s.elapsed++;
   if (s.elapsed >= c.max_episode_steps) {
     flags |= MGPLR_F_TRUNC_KEY | (done ? 0u : MGPLR_F_TRUNC_VAL);
-    if (A.o.trunc_image || A.o.trunc_direction) {
-      OutPtrs tp{A.o.trunc_image, A.o.trunc_direction, nullptr};
-      emit_direct(R, s, c, tp, e);
-    }
+    if (A.o.trunc_image || A.o.trunc_direction)
+      rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
     done = true;
   }
   // VecMonitor.step_wait (vec_monitor.py:60-85): eprets(f32) += rews(f64) is evaluated in double
-  s.ep_ret = (float)__dadd_rn((double)s.ep_ret, rew);
+  if (flags & MGPLR_F_GOAL) s.ep_ret = (float)__dadd_rn((double)s.ep_ret, rew);
   s.ep_len += 1;
   if (done) {
     flags |= MGPLR_F_DONE;
@@ -397,20 +432,12 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, const Rows &R, Env &s
     s.ep_ret = 0.f; s.ep_len = 0;
     // worker.step_env (parallel_wrappers.py:27-37)
     if (RR) {
-      uint32_t adv = d.adv[e];
-      int4 met;
-      Rng rng(d, e);
-      reset_random(R, s, adv, met, rng, d, e, (c.resample && A.n_walls) ? A.n_walls[e] : -1, err);
-      rng.store();
-      d.adv[e] = adv; d.metrics[e] = met;
+      s = unpack(rare_reset_random(d, rows, stride, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1));
       rows_dirty = true;
-    } else if (!reset_agent(s)) err |= kErrNoStart;
+    } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
   } else if ((A.last_step & 3) == 3 && (A.o.trunc_image || A.o.trunc_direction)) {
-    // runner-side cliffhanger: truncated_obs = the current obs (adversarial_runner.py:523-528)
-    OutPtrs tp{A.o.trunc_image, A.o.trunc_direction, nullptr};
-    emit_direct(R, s, c, tp, e);
+    rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
   }
-  if (err) d.err[e] |= err;
   const View v = render_view<SEE>(R, s, c.W);
   emit_obs_f32(v, s_obs);
   if (A.o.image_u8) emit_obs_u8(v, A.o.image_u8 + (size_t)e * kObsFloats);
@@ -429,64 +456,129 @@ __device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, con
   if (o.cliffhanger_masks) o.cliffhanger_masks[e] = cliff ? 0.f : 1.f;
 }
 
-// Store the CTA's observation tile: n_envs*75 contiguous floats starting at gdst.
-__device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, int n_envs) {
+// ---- TMA bulk copies + mbarrier (PTX; SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk asynchronous copy completing on an mbarrier; bytes % 16 == 0, 16-byte aligned addresses
+__device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk stores have finished READING shared memory (the global writes complete before the grid does)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Stage the wall rows of envs [base, base+n_tile) into s_rows[r*TILE + i]: W bulk copies of TILE*4 bytes when the
+// tile is full and 16-byte aligned (one elected thread, completion on `bar`), plain coalesced loads otherwise.
+template <int TILE>
+__device__ __forceinline__ bool stage_rows_begin(const Dev &d, uint32_t *s_rows, uint64_t *bar, int base, int n_tile) {
+  const int W = d.c.W;
+  const bool bulk = (n_tile == TILE) && ((d.N & 3) == 0);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (uint32_t)(W * TILE * 4));
+      for (int r = 0; r < W; r++) bulk_load(s_rows + r * TILE, d.wall + (size_t)r * d.N + base, TILE * 4, bar);
+    }
+  } else if ((int)threadIdx.x < n_tile) {
+    uint32_t tmp[32];
+#pragma unroll
+    for (int r = 0; r < 32; r++) tmp[r] = (r < W) ? d.wall[(size_t)r * d.N + base + threadIdx.x] : 0u;
+#pragma unroll
+    for (int r = 0; r < 32; r++)
+      if (r < W) s_rows[r * TILE + threadIdx.x] = tmp[r];
+  }
+  return bulk;
+}
+
+// Store the CTA's observation tile: n_envs*75 contiguous floats starting at gdst.  All threads must call.
+__device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, int n_envs, bool wait_now) {
   const uint32_t bytes = (uint32_t)n_envs * kObsFloats * 4u;
   if ((bytes & 15u) == 0 && (((uintptr_t)gdst) & 15u) == 0) {
     fence_proxy_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) { bulk_store(gdst, s_obs, bytes); bulk_commit_wait(); }
+    if (threadIdx.x == 0) {
+      bulk_store(gdst, s_obs, bytes);
+      bulk_commit();
+      if (wait_now) bulk_wait_read0();
+    }
   } else {
     __syncthreads();
     for (int i = threadIdx.x; i < n_envs * kObsFloats; i += blockDim.x) gdst[i] = s_obs[i];
   }
 }
 
-template <bool SEE, bool RR>
+template <bool SEE, bool RR, int TILE>
 __global__ void __launch_bounds__(TILE) k_step_env(Dev d, StepArgs A) {
   extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
   float *s_obs = reinterpret_cast<float *>(smem);
   uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem + (size_t)TILE * kObsFloats * 4);
   const int tid = threadIdx.x, base = blockIdx.x * TILE, e = base + tid, W = d.c.W;
-  const bool valid = e < d.N;
+  const int n_tile = min(TILE, d.N - base);
+  const bool valid = tid < n_tile;
+  const bool bulk = stage_rows_begin<TILE>(d, s_rows, &bar, base, n_tile);
+  // independent of the rows: this env's scalars and action (coalesced 16 B / 8 B per thread)
+  uint4 h = make_uint4(0, 0, 0, 0);
+  int a = 6;
+  if (valid) { h = d.hot[e]; a = (int)A.action[e]; }
+  if (bulk) mbar_wait(&bar, 0);
   if (valid) {
-    // stage this env's wall rows: coalesced across the warp (row-major struct-of-arrays in HBM)
-#pragma unroll 5
-    for (int r = 0; r < W; r++) s_rows[r * TILE + tid] = d.wall[(size_t)r * d.N + e];
-    Env s = unpack(d.hot[e]);
-    const int a = (int)A.action[e];
-    const Rows R{s_rows + tid, TILE};
+    Env s = unpack(h);
     float rew;
     bool dirty = false;
-    const uint32_t flags = step_one<SEE, RR>(d, R, s, e, a, A, s_obs + tid * kObsFloats, rew, dirty);
+    const uint32_t flags = step_one<SEE, RR>(d, s_rows + tid, TILE, s, e, a, A, s_obs + tid * kObsFloats, rew, dirty);
     d.hot[e] = pack(s);
     if (RR && dirty)
       for (int r = 0; r < W; r++) d.wall[(size_t)r * d.N + e] = s_rows[r * TILE + tid];
     write_step_scalars(A, e, s, flags, rew);
   }
-  if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, min(TILE, d.N - base));
+  if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, n_tile, true);
 }
 
-// T transitions in one launch from a recorded action stream u8 [T][N]; state stays on chip.
-template <bool SEE, bool RR>
+// T transitions in one launch from a recorded action stream u8 [T][N]; state stays on chip and the observation
+// tile is double-buffered so step t's bulk store overlaps step t+1's compute.
+template <bool SEE, bool RR, int TILE>
 __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions, int T, StepArgs A0) {
   extern __shared__ __align__(128) uint8_t smem[];
-  float *s_obs = reinterpret_cast<float *>(smem);
-  uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem + (size_t)TILE * kObsFloats * 4);
+  __shared__ __align__(8) uint64_t bar;
+  float *s_obs0 = reinterpret_cast<float *>(smem);
+  float *s_obs1 = reinterpret_cast<float *>(smem + (size_t)TILE * kObsFloats * 4);
+  uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem + 2 * (size_t)TILE * kObsFloats * 4);
   const int tid = threadIdx.x, base = blockIdx.x * TILE, e = base + tid, W = d.c.W, N = d.N;
-  const bool valid = e < N;
-  Env s{};
-  const Rows R{s_rows + tid, TILE};
-  bool dirty = false;
-  if (valid) {
-    for (int r = 0; r < W; r++) s_rows[r * TILE + tid] = d.wall[(size_t)r * N + e];
-    s = unpack(d.hot[e]);
-  }
   const int n_tile = min(TILE, N - base);
+  const bool valid = tid < n_tile;
+  const bool bulk = stage_rows_begin<TILE>(d, s_rows, &bar, base, n_tile);
+  Env s{};
+  if (valid) s = unpack(d.hot[e]);
+  if (bulk) mbar_wait(&bar, 0);
+  else __syncthreads();
+  bool dirty = false;
   for (int t = 0; t < T; t++) {
     StepArgs A = A0;
     const size_t off = (size_t)t * N;
-    // advance the [T]-leading output pointers
     if (A.o.image) A.o.image += off * kObsFloats;
     if (A.o.direction) A.o.direction += off;
     if (A.o.reward) A.o.reward += off;
@@ -500,14 +592,18 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
     if (A.o.cliffhanger_masks) A.o.cliffhanger_masks += off;
     if (A.o.image_u8) A.o.image_u8 += off * kObsFloats;
     A.last_step = (t == T - 1) ? A0.last_step : 0;
+    float *s_obs = (t & 1) ? s_obs1 : s_obs0;
+    // the store that last used this buffer (step t-2) must have finished reading it: at most one group pending
+    if (tid == 0 && t >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
     if (valid) {
       float rew;
-      const uint32_t flags = step_one<SEE, RR>(d, R, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats, rew, dirty);
+      const uint32_t flags = step_one<SEE, RR>(d, s_rows + tid, TILE, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats, rew, dirty);
       write_step_scalars(A, e, s, flags, rew);
     }
-    if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, n_tile);
-    __syncthreads();  // tile buffer is reused by the next step
+    if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, n_tile, false);
   }
+  if (tid == 0) bulk_wait_read0();
   if (valid) {
     d.hot[e] = pack(s);
     if (RR && dirty)
@@ -571,15 +667,17 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(dalloc(&v->res_dev, 16 * N, total));
   v->bytes = total;
   CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device));
-  const size_t smem = step_smem_bytes(cfg->width);
-  CK(cudaFuncSetAttribute(k_step_env<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_step_env<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_step_env<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_step_env<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_rollout<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_rollout<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_rollout<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CK(cudaFuncSetAttribute(k_rollout<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    const int smem64 = (int)step_smem_bytes(cfg->width, 64, 1), smem128 = (int)step_smem_bytes(cfg->width, 128, 1);
+    const int r64 = (int)step_smem_bytes(cfg->width, 64, 2), r128 = (int)step_smem_bytes(cfg->width, 128, 2);
+#define SET_ATTR(SEE, RR)                                                                                              \
+  CK(cudaFuncSetAttribute(k_step_env<SEE, RR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));              \
+  CK(cudaFuncSetAttribute(k_step_env<SEE, RR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));            \
+  CK(cudaFuncSetAttribute(k_rollout<SEE, RR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, r64));                  \
+  CK(cudaFuncSetAttribute(k_rollout<SEE, RR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, r128));
+    SET_ATTR(true, false) SET_ATTR(true, true) SET_ATTR(false, false) SET_ATTR(false, true)
+#undef SET_ATTR
+  }
   CK(cudaMemset(d.mt, 0, 624 * N * sizeof(uint32_t)));
   k_init<<<grid_for(num_envs, 256), 256>>>(d);
   CK(cudaGetLastError());
@@ -711,13 +809,22 @@ static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_rando
   memset(&A, 0, sizeof(A));
   A.action = action; A.n_walls = n_walls; A.last_step = last_step;
   if (out) A.o = *out;
-  const int grid = grid_for(v->d.N, TILE);
-  const size_t smem = step_smem_bytes(v->d.c.W);
-  const bool see = v->d.c.see_through;
-  if (see && !reset_random) k_step_env<true, false><<<grid, TILE, smem, st>>>(v->d, A);
-  else if (see && reset_random) k_step_env<true, true><<<grid, TILE, smem, st>>>(v->d, A);
-  else if (!see && !reset_random) k_step_env<false, false><<<grid, TILE, smem, st>>>(v->d, A);
-  else k_step_env<false, true><<<grid, TILE, smem, st>>>(v->d, A);
+  const int tile = step_tile();
+  const int grid = grid_for(v->d.N, tile);
+  const size_t smem = step_smem_bytes(v->d.c.W, tile, 1);
+  const int key = (v->d.c.see_through ? 4 : 0) | (reset_random ? 2 : 0) | (tile == 128 ? 1 : 0);
+#define LAUNCH(SEE, RR, TL) k_step_env<SEE, RR, TL><<<grid, TL, smem, st>>>(v->d, A)
+  switch (key) {
+    case 7: LAUNCH(true, true, 128); break;
+    case 6: LAUNCH(true, true, 64); break;
+    case 5: LAUNCH(true, false, 128); break;
+    case 4: LAUNCH(true, false, 64); break;
+    case 3: LAUNCH(false, true, 128); break;
+    case 2: LAUNCH(false, true, 64); break;
+    case 1: LAUNCH(false, false, 128); break;
+    default: LAUNCH(false, false, 64); break;
+  }
+#undef LAUNCH
   CK(cudaGetLastError());
   return 0;
 }
@@ -767,13 +874,22 @@ extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, i
   StepArgs A;
   memset(&A, 0, sizeof(A));
   if (out_t0) A.o = *out_t0;
-  const int grid = grid_for(v->d.N, TILE);
-  const size_t smem = step_smem_bytes(v->d.c.W);
-  const bool see = v->d.c.see_through;
-  if (see && !reset_random) k_rollout<true, false><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
-  else if (see && reset_random) k_rollout<true, true><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
-  else if (!see && !reset_random) k_rollout<false, false><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
-  else k_rollout<false, true><<<grid, TILE, smem, st>>>(v->d, actions, T, A);
+  const int tile = step_tile();
+  const int grid = grid_for(v->d.N, tile);
+  const size_t smem = step_smem_bytes(v->d.c.W, tile, 2);
+  const int key = (v->d.c.see_through ? 4 : 0) | (reset_random ? 2 : 0) | (tile == 128 ? 1 : 0);
+#define LAUNCH(SEE, RR, TL) k_rollout<SEE, RR, TL><<<grid, TL, smem, st>>>(v->d, actions, T, A)
+  switch (key) {
+    case 7: LAUNCH(true, true, 128); break;
+    case 6: LAUNCH(true, true, 64); break;
+    case 5: LAUNCH(true, false, 128); break;
+    case 4: LAUNCH(true, false, 64); break;
+    case 3: LAUNCH(false, true, 128); break;
+    case 2: LAUNCH(false, true, 64); break;
+    case 1: LAUNCH(false, false, 128); break;
+    default: LAUNCH(false, false, 64); break;
+  }
+#undef LAUNCH
   CK(cudaGetLastError());
   return 0;
 }
