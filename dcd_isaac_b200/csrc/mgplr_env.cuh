@@ -31,7 +31,7 @@ struct Dev {
   int N;
   Cfg c;
   uint32_t *wall;    // [W][N] wall bit-plane rows (bit x of row y)
-  uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx6|gy6|sx6|sy6|sdir2  z: elapsed16|eplen16  w: ep_ret bits
+  uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx5|gy5|hasgoal1|sx5|sy5|hasstart1|sdir2|pending8  z: elapsed16|eplen16  w: ep_ret bits
   uint32_t *adv;     // [N] adversary_step_count12 | adversary_max_steps12 | n_clutter_sampled1
   int4 *metrics;     // [N] n_clutter_placed, distance_to_goal, passable, shortest_path_length
   uint32_t *mt;      // [624][N] MT19937 state (numpy RandomState of each env)
@@ -41,9 +41,15 @@ struct Dev {
   uint32_t *err;     // [N] sticky error bits
 };
 
+// `pending` = goal respawns (multigrid.py:821-838) whose env-RNG draws have not been made yet.  A respawn draw
+// depends only on the level (walls + goal; the agent is off the grid while it is drawn) and its result is
+// overwritten by reset_agent before anything observes it, so the step kernel only counts it and the draws are
+// replayed -- in order, against the unchanged level -- by flush_pending() before the next consumer of the env
+// RNG or the next level edit.  This keeps serial MT19937 traffic out of the hot kernel.
+constexpr int kMaxPending = 255;
 struct Env {
   int ax, ay, adir, has_agent, done_flag, step_count;
-  int gx, gy, sx, sy, sdir;
+  int gx, gy, sx, sy, sdir, pending;
   int elapsed, ep_len;
   float ep_ret;
 };
@@ -52,7 +58,10 @@ __device__ __forceinline__ Env unpack(const uint4 h) {
   Env e;
   e.ax = h.x & 63; e.ay = (h.x >> 6) & 63; e.adir = (h.x >> 12) & 3; e.has_agent = (h.x >> 14) & 1;
   e.done_flag = (h.x >> 15) & 1; e.step_count = h.x >> 16;
-  e.gx = h.y & 63; e.gy = (h.y >> 6) & 63; e.sx = (h.y >> 12) & 63; e.sy = (h.y >> 18) & 63; e.sdir = (h.y >> 24) & 3;
+  const bool hg = (h.y >> 10) & 1, hs = (h.y >> 21) & 1;
+  e.gx = hg ? (int)(h.y & 31) : kNone; e.gy = hg ? (int)((h.y >> 5) & 31) : kNone;
+  e.sx = hs ? (int)((h.y >> 11) & 31) : kNone; e.sy = hs ? (int)((h.y >> 16) & 31) : kNone;
+  e.sdir = (h.y >> 22) & 3; e.pending = h.y >> 24;
   e.elapsed = h.z & 0xffff; e.ep_len = h.z >> 16;
   e.ep_ret = __uint_as_float(h.w);
   return e;
@@ -61,7 +70,9 @@ __device__ __forceinline__ uint4 pack(const Env &e) {
   uint4 h;
   h.x = (uint32_t)e.ax | ((uint32_t)e.ay << 6) | ((uint32_t)e.adir << 12) | ((uint32_t)e.has_agent << 14) |
         ((uint32_t)e.done_flag << 15) | ((uint32_t)e.step_count << 16);
-  h.y = (uint32_t)e.gx | ((uint32_t)e.gy << 6) | ((uint32_t)e.sx << 12) | ((uint32_t)e.sy << 18) | ((uint32_t)e.sdir << 24);
+  const uint32_t hg = e.gx != kNone, hs = e.sx != kNone;
+  h.y = ((uint32_t)e.gx & 31u) | (((uint32_t)e.gy & 31u) << 5) | (hg << 10) | (((uint32_t)e.sx & 31u) << 11) |
+        (((uint32_t)e.sy & 31u) << 16) | (hs << 21) | ((uint32_t)e.sdir << 22) | ((uint32_t)e.pending << 24);
   h.z = ((uint32_t)e.elapsed & 0xffff) | ((uint32_t)e.ep_len << 16);
   h.w = __float_as_uint(e.ep_ret);
   return h;
@@ -183,6 +194,19 @@ __device__ __noinline__ bool place_random(const Rows &R, const Env &e, Rng &rng,
   }
 }
 
+// Replay `count` deferred goal respawns (place_one_agent over the whole grid with the agent off the grid).
+// Returns the last position as x | y<<8.
+__device__ __noinline__ uint32_t replay_respawns(const Rows &R, int gx, int gy, Rng &rng, int W, int count) {
+  Env t{};
+  t.gx = gx; t.gy = gy; t.has_agent = 0;
+  int px = 0, py = 0;
+  for (int i = 0; i < count; i++) place_random(R, t, rng, W, -1, px, py);
+  return (uint32_t)px | ((uint32_t)py << 8);
+}
+__device__ __forceinline__ void flush_pending(const Rows &R, Env &e, Rng &rng, int W) {
+  if (e.pending) { replay_respawns(R, e.gx, e.gy, rng, W, e.pending); e.pending = 0; }
+}
+
 // reset_metrics + compute_metrics (adversarial.py:184-192,407-447): interior wall count, Manhattan
 // distance, and reachability / hop count by a bit-parallel flood fill over the interior rows.
 __device__ __noinline__ int4 compute_metrics(const Rows &R, const Env &e, int W, bool do_reset) {
@@ -226,6 +250,7 @@ __device__ __forceinline__ bool reset_agent(Env &e) {
 
 // AdversarialEnv.reset (adversarial.py:194-229).
 __device__ inline void reset_adversary(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Cfg &c) {
+  flush_pending(R, e, rng, c.W);
   e.step_count = 0;
   uint32_t adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
   if (c.resample) sampled = 0;
@@ -242,6 +267,7 @@ __device__ inline bool step_adversary(const Rows &R, Env &e, uint32_t &adv, int4
                                       uint32_t &err) {
   const int W = c.W, I = W - 2, A = I * I;
   if (loc < 0 || loc >= A) { err |= kErrBadLoc; return false; }
+  flush_pending(R, e, rng, W);
   int adv_step = adv & 0xfff, adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
   if (c.resample && !sampled) {
     adv_max = (int)(((double)loc / (double)A) * (double)c.n_clutter) + 2;
@@ -278,6 +304,7 @@ __device__ __noinline__ void reset_random(const Rows &R, Env &e, uint32_t &adv, 
                                     int n_walls, uint32_t &err) {
   const Cfg &c = d.c;
   const int W = c.W;
+  flush_pending(R, e, rng, W);
   if (c.fixed_env) {  // self.seed(self.seed_value) (adversarial.py:542-543)
     mt_seed(d, env, d.limbs[env], d.limbs[(size_t)d.N + env], (int)d.limbs[2 * (size_t)d.N + env]);
     rng.loaded = false;
@@ -316,34 +343,38 @@ struct View {
   int gvx, gvy;
 };
 
-template <bool SEE_THROUGH>
-__device__ __forceinline__ View render_view(const Rows &R, const Env &e, int W) {
+template <bool SEE_THROUGH, typename EXT>
+__device__ __forceinline__ View render_view_t(const Rows &R, const Env &e, int W) {
   View v;
-  // 64-bit extended rows: bit (x+8) of E = wall at x, everything outside [0,W) is wall
+  // extended rows: bit (x+PAD) of E = wall at x, everything outside [0,W) is wall.  EXT = uint32_t needs
+  // W + 2*PAD <= 32 (W <= 24, the 15x15 mazes); uint64_t covers W <= 32.
+  constexpr int PAD = 4;
   const int d = e.adir;
-  const bool vertical = d & 1;             // facing down/up: view rows are world rows
+  const bool vertical = d & 1;                  // facing down/up: view rows are world rows
   const int sgn = (d == 0 || d == 1) ? 1 : -1;  // forward sign along its axis
-  uint64_t E[kV];
+  const EXT ones = ~(EXT)0;
+  const EXT border = ((EXT)15) | (ones << (W + PAD));
+  EXT E[kV];
 #pragma unroll
   for (int k = 0; k < kV; k++) {
-    // vertical: world row for view row vy=k is ay + sgn*(4-k); horizontal: world row for view column vx=k
-    // is ay + ry*(k-2) with r = (-f.y, f.x): dir 0 -> r=(0,1) ; dir 2 -> r=(0,-1)
+    // vertical: world row of view row vy=k is ay + sgn*(4-k); horizontal: world row of view column vx=k is
+    // ay + r.y*(k-2) with r = (-f.y, f.x): dir 0 -> r=(0,1), dir 2 -> r=(0,-1)
     const int wy = vertical ? (e.ay + sgn * (kV - 1 - k)) : (e.ay + sgn * (k - kV / 2));
-    uint64_t row = ~0ull;
-    if (wy >= 0 && wy < W) row = ((uint64_t)R.get(wy) << 8) | 0xffull | (~0ull << (W + 8));
+    EXT row = ones;
+    if (wy >= 0 && wy < W) row = ((EXT)R.get(wy) << PAD) | border;
     E[k] = row;
   }
 #pragma unroll
   for (int vy = 0; vy < kV; vy++) {
     uint32_t m = 0;
     if (vertical) {
-      // wx for vx: dir 3 (up): ax + (vx-2) ; dir 1 (down): r = (-1,0): ax - (vx-2)
-      const uint32_t five = (uint32_t)(E[vy] >> (e.ax - 2 + 8)) & 31u;
+      // dir 3 (up): wx = ax + (vx-2); dir 1 (down): r = (-1,0): wx = ax - (vx-2)
+      const uint32_t five = (uint32_t)(E[vy] >> (e.ax - 2 + PAD)) & 31u;
       m = (d == 3) ? five : (__brev(five) >> 27);
     } else {
       const int wx = e.ax + sgn * (kV - 1 - vy);
 #pragma unroll
-      for (int vx = 0; vx < kV; vx++) m |= (uint32_t)((E[vx] >> (wx + 8)) & 1ull) << vx;
+      for (int vx = 0; vx < kV; vx++) m |= (uint32_t)((E[vx] >> (wx + PAD)) & 1) << vx;
     }
     v.w[vy] = m;
   }
@@ -383,6 +414,11 @@ __device__ __forceinline__ View render_view(const Rows &R, const Env &e, int W) 
   return v;
 }
 
+template <bool SEE_THROUGH>
+__device__ __forceinline__ View render_view(const Rows &R, const Env &e, int W) {
+  return render_view_t<SEE_THROUGH, uint64_t>(R, e, W);
+}
+
 // cell code of view cell (vx,vy): 0 unseen, 1 empty, 2 wall, 3 goal
 __device__ __forceinline__ int view_code(const View &v, int vx, int vy) {
   if (!((v.vis[vy] >> vx) & 1u)) return 0;
@@ -396,7 +432,27 @@ __device__ __forceinline__ int view_code(const View &v, int vx, int vy) {
 __device__ __forceinline__ float type_f(int code) { return code == 0 ? 0.0f : code == 1 ? 0.1f : code == 2 ? 0.2f : 0.8f; }
 __device__ __forceinline__ float color_f(int code) { return code == 2 ? 0.5f : code == 3 ? 0.1f : 0.0f; }
 
-// write the preprocessed observation [3][5][5] (c, vx, vy) to `o` (shared or global)
+// write the preprocessed observation [3][5][5] (c, vx, vy) to `o` (shared or global): per cell
+// type = unseen 0 | wall 0.2 | goal 0.8 | empty 0.1, colour = wall 0.5 | goal 0.1 | 0, state = 0.  The agent's own
+// cell (V/2, V-1) never holds a wall or the goal, so it renders as empty without a special case.
+template <bool SEE_THROUGH>
+__device__ __forceinline__ void emit_obs_f32_fast(const View &v, float *o) {
+#pragma unroll
+  for (int vy = 0; vy < kV; vy++) {
+    const uint32_t vis = SEE_THROUGH ? 31u : v.vis[vy];
+    const uint32_t w = v.w[vy] & vis;
+    const uint32_t g = (vy == v.gvy) ? ((1u << v.gvx) & vis & ~w) : 0u;
+#pragma unroll
+    for (int vx = 0; vx < kV; vx++) {
+      const bool bw = (w >> vx) & 1u, bg = (g >> vx) & 1u, bv = (vis >> vx) & 1u;
+      float t = bw ? 0.2f : (bg ? 0.8f : 0.1f);
+      if (!SEE_THROUGH) t = bv ? t : 0.0f;
+      o[vx * kV + vy] = t;
+      o[kV * kV + vx * kV + vy] = bw ? 0.5f : (bg ? 0.1f : 0.0f);
+      o[2 * kV * kV + vx * kV + vy] = 0.0f;
+    }
+  }
+}
 __device__ __forceinline__ void emit_obs_f32(const View &v, float *o) {
 #pragma unroll
   for (int vx = 0; vx < kV; vx++)

@@ -1,10 +1,9 @@
 // mgplr_venv.cu -- kernels and C-ABI entry points for the batched MultiGrid adversarial env (sm_100a).
 //
-// Hot kernel: k_step_env -- one CTA stages a tile of TILE envs in shared memory (wall bit-plane rows,
-// struct-of-arrays so the bank index is the thread index), one thread steps one env, the rendered
-// float32 observations of the whole tile are assembled in shared memory and leave the SM as ONE
-// contiguous bulk asynchronous copy (cp.async.bulk, TMA engine) straight into the rollout-storage
-// tensor.  See DESIGN.md for the byte accounting and the roofline.
+// Hot kernel: k_step_env -- persistent and warp-pipelined: each warp stages 32-env tiles of the wall bit-plane
+// in shared memory with TMA bulk loads (struct-of-arrays, bank index = lane), one thread steps one env, and
+// each tile's float32 observations leave the SM as ONE 9600-byte bulk asynchronous store straight into the
+// rollout-storage tensor while the next tile computes.  See DESIGN.md for the byte accounting and the roofline.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -49,15 +48,6 @@ struct mgplr_venv {
   int sm_count;
 };
 
-// envs (= threads) per CTA in the hot kernels; MGPLR_TILE=64|128 overrides (tuning)
-static int step_tile() {
-  static int tile = 0;
-  if (!tile) {
-    const char *e = getenv("MGPLR_TILE");
-    tile = (e && atoi(e) == 128) ? 128 : 64;
-  }
-  return tile;
-}
 // dynamic shared memory: `bufs` obs tiles [TILE][75] f32 then wall rows [W][TILE] u32
 static size_t step_smem_bytes(int W, int tile, int bufs) { return (size_t)bufs * tile * kObsFloats * 4 + (size_t)W * tile * 4; }
 
@@ -108,6 +98,9 @@ __global__ void k_seed(Dev d, const uint32_t *scratch, int n, int stride, int ha
   const uint32_t lo = scratch[k], hi = scratch[(size_t)stride + k], cnt = scratch[2 * (size_t)stride + k];
   d.limbs[e] = lo; d.limbs[(size_t)d.N + e] = hi; d.limbs[2 * (size_t)d.N + e] = cnt;
   mt_seed(d, e, lo, hi, (int)cnt);
+  uint4 h = d.hot[e];  // re-seeding replaces the stream: deferred draws of the old stream are moot
+  h.y &= 0x00ffffffu;
+  d.hot[e] = h;
 }
 
 __global__ void k_reset(Dev d) {
@@ -163,6 +156,11 @@ __global__ void k_reset_agent(Dev d, OutPtrs o) {
   if (e >= d.N) return;
   Rows R{d.wall + e, d.N};
   Env s = unpack(d.hot[e]);
+  if (s.pending) {  // replay the deferred respawn draws of the last rollout (level unchanged since)
+    Rng rng(d, e);
+    flush_pending(R, s, rng, d.c.W);
+    rng.store();
+  }
   if (!reset_agent(s)) { d.err[e] |= kErrNoStart; d.hot[e] = pack(s); return; }
   s.ep_ret = 0.f; s.ep_len = 0;  // VecMonitor.reset_agent (vec_monitor.py:42-46)
   d.hot[e] = pack(s);
@@ -262,6 +260,7 @@ __global__ void k_mutate_edits(Dev d, const int32_t *locs, const int32_t *ops, c
   const int W = d.c.W, I = W - 2;
   Rows R{d.wall + e, d.N};
   Env s = unpack(d.hot[e]);
+  if (s.pending) { Rng rng(d, e); flush_pending(R, s, rng, W); rng.store(); }
   const int k = n_edits[e];
   for (int n = 0; n < k && n < max_edits; n++) {
     const int loc = locs[(size_t)e * max_edits + n], op = ops[(size_t)e * max_edits + n];
@@ -324,6 +323,19 @@ __global__ void k_encode(Dev d, uint8_t *enc) {
   o[0] = t; o[1] = c; o[2] = st;
 }
 
+// replay deferred respawn draws so that the RNG state seen by the host is the reference's
+__global__ void k_flush(Dev d) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  Env s = unpack(d.hot[e]);
+  if (!s.pending) return;
+  Rows R{d.wall + e, d.N};
+  Rng rng(d, e);
+  flush_pending(R, s, rng, d.c.W);
+  rng.store();
+  d.hot[e] = pack(s);
+}
+
 __global__ void k_get_metrics(Dev d, int32_t *m) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
@@ -356,16 +368,14 @@ struct StepArgs {
 
 // ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
 
-// agent_is_done's respawn (multigrid.py:821-838): a random empty cell drawn with the env RNG.  Returns x | y<<8.
+// agent_is_done's respawn (multigrid.py:821-838): `count` random empty cells drawn with the env RNG (the deferred
+// ones first, see Env::pending).  Returns the last one as x | y<<8.
 __device__ __noinline__ uint32_t rare_respawn(uint32_t *mt, uint32_t *mti, uint32_t *words, int N, int e, uint32_t *rows,
-                                              int stride, int W, int gx, int gy) {
+                                              int stride, int W, int gx, int gy, int count) {
   Rng rng(mt, mti, words, N, e);
-  Env s{};
-  s.gx = gx; s.gy = gy; s.has_agent = 0;
-  int px = 0, py = 0;
-  place_random(Rows{rows, stride}, s, rng, W, -1, px, py);
+  const uint32_t p = replay_respawns(Rows{rows, stride}, gx, gy, rng, W, count);
   rng.store();
-  return (uint32_t)px | ((uint32_t)py << 8);
+  return p;
 }
 
 // info['truncated_obs'] (time_limit.py:29-31) / runner cliffhanger obs (adversarial_runner.py:523-528)
@@ -392,13 +402,15 @@ __device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int strid
 }
 
 // One env transition for the thread's env; `rows` = this env's wall rows in shared memory.  Returns flags.
-template <bool SEE, bool RR>
+// In reset_agent mode a goal's respawn draw is DEFERRED (Env::pending, mgplr_env.cuh).
+template <bool SEE, bool RR, typename EXT>
 __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int stride, Env &s, int e, int a, const StepArgs &A,
                                              float *s_obs, float &rew_out, bool &rows_dirty) {
   const Cfg &c = d.c;
   const Rows R{rows, stride};
   uint32_t flags = 0;
   double rew = 0.0;
+  const bool want_trunc = A.o.trunc_image || A.o.trunc_direction;
   // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
   s.step_count++;
   const int fx = s.ax + ((s.adir == 0) - (s.adir == 2)), fy = s.ay + ((s.adir == 1) - (s.adir == 3));
@@ -407,8 +419,11 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
   else if (a == 2) {
     if (fx == s.gx && fy == s.gy) {
       // agent_is_done: remove the agent, done, respawn (dir forced to 0, multigrid.py:668-672); reward = _reward()
-      const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.N, e, rows, stride, c.W, s.gx, s.gy);
-      s.done_flag = 1; s.has_agent = 1; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
+      s.done_flag = 1;
+      if (RR || (want_trunc && s.elapsed + 1 >= c.max_episode_steps) || s.pending >= kMaxPending) {
+        const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.N, e, rows, stride, c.W, s.gx, s.gy, s.pending + 1);
+        s.pending = 0; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
+      } else s.pending++;
       rew = __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)s.step_count, (double)c.max_steps)));
       flags |= MGPLR_F_GOAL;
     } else if (!is_wall(R, fx, fy)) { s.ax = fx; s.ay = fy; }
@@ -418,8 +433,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
   s.elapsed++;
   if (s.elapsed >= c.max_episode_steps) {
     flags |= MGPLR_F_TRUNC_KEY | (done ? 0u : MGPLR_F_TRUNC_VAL);
-    if (A.o.trunc_image || A.o.trunc_direction)
-      rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+    if (want_trunc) rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
     done = true;
   }
   // VecMonitor.step_wait (vec_monitor.py:60-85): eprets(f32) += rews(f64) is evaluated in double
@@ -435,11 +449,11 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
       s = unpack(rare_reset_random(d, rows, stride, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1));
       rows_dirty = true;
     } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
-  } else if ((A.last_step & 3) == 3 && (A.o.trunc_image || A.o.trunc_direction)) {
+  } else if ((A.last_step & 3) == 3 && want_trunc) {
     rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
   }
-  const View v = render_view<SEE>(R, s, c.W);
-  emit_obs_f32(v, s_obs);
+  const View v = render_view_t<SEE, EXT>(R, s, c.W);
+  emit_obs_f32_fast<SEE>(v, s_obs);
   if (A.o.image_u8) emit_obs_u8(v, A.o.image_u8 + (size_t)e * kObsFloats);
   rew_out = (float)rew;
   return flags;
@@ -503,12 +517,7 @@ __device__ __forceinline__ bool stage_rows_begin(const Dev &d, uint32_t *s_rows,
       for (int r = 0; r < W; r++) bulk_load(s_rows + r * TILE, d.wall + (size_t)r * d.N + base, TILE * 4, bar);
     }
   } else if ((int)threadIdx.x < n_tile) {
-    uint32_t tmp[32];
-#pragma unroll
-    for (int r = 0; r < 32; r++) tmp[r] = (r < W) ? d.wall[(size_t)r * d.N + base + threadIdx.x] : 0u;
-#pragma unroll
-    for (int r = 0; r < 32; r++)
-      if (r < W) s_rows[r * TILE + threadIdx.x] = tmp[r];
+    for (int r = 0; r < W; r++) s_rows[r * TILE + threadIdx.x] = d.wall[(size_t)r * d.N + base + threadIdx.x];
   }
   return bulk;
 }
@@ -530,37 +539,161 @@ __device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, 
   }
 }
 
-template <bool SEE, bool RR, int TILE>
-__global__ void __launch_bounds__(TILE) k_step_env(Dev d, StepArgs A) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
-  float *s_obs = reinterpret_cast<float *>(smem);
-  uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem + (size_t)TILE * kObsFloats * 4);
-  const int tid = threadIdx.x, base = blockIdx.x * TILE, e = base + tid, W = d.c.W;
-  const int n_tile = min(TILE, d.N - base);
-  const bool valid = tid < n_tile;
-  const bool bulk = stage_rows_begin<TILE>(d, s_rows, &bar, base, n_tile);
-  // independent of the rows: this env's scalars and action (coalesced 16 B / 8 B per thread)
-  uint4 h = make_uint4(0, 0, 0, 0);
-  int a = 6;
-  if (valid) { h = d.hot[e]; a = (int)A.action[e]; }
-  if (bulk) mbar_wait(&bar, 0);
-  if (valid) {
-    Env s = unpack(h);
-    float rew;
-    bool dirty = false;
-    const uint32_t flags = step_one<SEE, RR>(d, s_rows + tid, TILE, s, e, a, A, s_obs + tid * kObsFloats, rew, dirty);
-    d.hot[e] = pack(s);
-    if (RR && dirty)
-      for (int r = 0; r < W; r++) d.wall[(size_t)r * d.N + e] = s_rows[r * TILE + tid];
-    write_step_scalars(A, e, s, flags, rew);
+// ---- hot kernel: persistent, warp-pipelined step_env -------------------------------------------------------
+// Each WARP owns tiles of 32 consecutive envs (tile = global_warp + k * total_warps) and runs a software
+// pipeline with no CTA-level synchronisation:
+//   * the wall rows of tile k+1 are prefetched by W bulk asynchronous copies (TMA, 128 B each) into the other
+//     half of a double buffer while tile k computes; completion is signalled on a per-warp mbarrier;
+//   * the hot record / action of tile k+1 are prefetched into registers;
+//   * the 32x75 float32 observations of tile k leave shared memory as one 9600-byte bulk asynchronous store
+//     that drains while tile k+1 steps and renders; the single obs buffer is only re-acquired
+//     (cp.async.bulk.wait_group.read) right before tile k+1 emits.
+constexpr int kWarpTile = 32;
+__host__ __device__ inline size_t warp_smem_bytes(int W) {
+  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + 127) & ~(size_t)127;
+}
+
+__device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot, int W, int see, uint8_t *image_u8, int e) {
+  const Env s = unpack(hot);
+  const Rows R{rows, stride};
+  const View v = see ? render_view<true>(R, s, W) : render_view<false>(R, s, W);
+  emit_obs_u8(v, image_u8 + (size_t)e * kObsFloats);
+}
+
+// rows of one 32-env tile -> shared memory: bulk copies onto `bar` when the tile is full and aligned
+__device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, uint64_t *bar, int base, bool bulk, int lane) {
+  const int W = d.c.W;
+  if (bulk) {
+    if (lane == 0) {
+      mbar_expect_tx(bar, (uint32_t)(W * kWarpTile * 4));
+      for (int r = 0; r < W; r++) bulk_load(s_rows + r * kWarpTile, d.wall + (size_t)r * d.N + base, kWarpTile * 4, bar);
+    }
+  } else if (base + lane < d.N) {
+    for (int r = 0; r < W; r++) s_rows[r * kWarpTile + lane] = d.wall[(size_t)r * d.N + base + lane];
   }
-  if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, n_tile, true);
+}
+
+template <bool SEE, bool RR, typename EXT>
+__global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = d.c.W, N = d.N;
+  const int wpc = blockDim.x >> 5;
+  uint8_t *wbase = smem + (size_t)warp * warp_smem_bytes(W);
+  float *s_obs = reinterpret_cast<float *>(wbase);
+  uint32_t *s_rows = reinterpret_cast<uint32_t *>(wbase + (size_t)kWarpTile * kObsFloats * 4);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 2 * W * kWarpTile);
+  const int total = gridDim.x * wpc;
+  int tile = blockIdx.x * wpc + warp;
+  if (tile >= n_tiles) return;
+  const bool aligned = (N & 3) == 0;
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
+  __syncwarp();
+  // prologue: first tile's rows and scalars
+  bool cur_bulk = aligned && (tile + 1) * kWarpTile <= N;
+  warp_issue_rows(d, s_rows, &bars[0], tile * kWarpTile, cur_bulk, lane);
+  uint4 nh = make_uint4(0, 0, 0, 0);
+  int na = 6;
+  if (tile * kWarpTile + lane < N) { nh = d.hot[tile * kWarpTile + lane]; na = (int)A.action[tile * kWarpTile + lane]; }
+  uint32_t phase = 0;  // bit s = parity to wait for on bars[s]
+  for (int k = 0; tile < n_tiles; tile += total, k++) {
+    const int st = k & 1, base = tile * kWarpTile, e = base + lane;
+    const int n_tile = min(kWarpTile, N - base);
+    const bool valid = lane < n_tile;
+    const uint4 h = nh;
+    const int a = na;
+    uint32_t *rows = s_rows + st * W * kWarpTile;
+    // prefetch tile k+1 into the other stage (its last readers, tile k-1, are done: __syncwarp)
+    const int next = tile + total;
+    __syncwarp();
+    bool next_bulk = false;
+    if (next < n_tiles) {
+      next_bulk = aligned && (next + 1) * kWarpTile <= N;
+      warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next * kWarpTile, next_bulk, lane);
+      if (next * kWarpTile + lane < N) { nh = d.hot[next * kWarpTile + lane]; na = (int)A.action[next * kWarpTile + lane]; }
+    }
+    if (cur_bulk) { mbar_wait(&bars[st], (phase >> st) & 1u); phase ^= 1u << st; }
+    cur_bulk = next_bulk;
+
+    Env s = unpack(h);
+    const Cfg &c = d.c;
+    const Rows R{rows + lane, kWarpTile};
+    uint32_t flags = 0;
+    double rew = 0.0;
+    bool dirty = false;
+    if (valid) {
+      const bool want_trunc = A.o.trunc_image || A.o.trunc_direction;
+      // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
+      s.step_count++;
+      const int fx = s.ax + ((s.adir == 0) - (s.adir == 2)), fy = s.ay + ((s.adir == 1) - (s.adir == 3));
+      if (a == 0) s.adir = (s.adir + 3) & 3;
+      else if (a == 1) s.adir = (s.adir + 1) & 3;
+      else if (a == 2) {
+        if (fx == s.gx && fy == s.gy) {
+          // agent_is_done (multigrid.py:821-838): done; the respawn draw is deferred unless something observes it
+          s.done_flag = 1;
+          if (RR || (want_trunc && s.elapsed + 1 >= c.max_episode_steps) || s.pending >= kMaxPending) {
+            const uint32_t p = rare_respawn(d.mt, d.mti, d.words, N, e, rows + lane, kWarpTile, W, s.gx, s.gy, s.pending + 1);
+            s.pending = 0; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
+          } else s.pending++;
+          rew = __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)s.step_count, (double)c.max_steps)));  // _reward()
+          flags |= MGPLR_F_GOAL;
+        } else if (!is_wall(R, fx, fy)) { s.ax = fx; s.ay = fy; }
+      }
+      bool done = s.done_flag || s.step_count >= c.max_steps;
+      // TimeLimit.step (time_limit.py:24-33)
+      s.elapsed++;
+      if (s.elapsed >= c.max_episode_steps) {
+        flags |= MGPLR_F_TRUNC_KEY | (done ? 0u : MGPLR_F_TRUNC_VAL);
+        if (want_trunc) rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+        done = true;
+      }
+      // VecMonitor.step_wait (vec_monitor.py:60-85): eprets(f32) += rews(f64) is evaluated in double
+      if (flags & MGPLR_F_GOAL) s.ep_ret = (float)__dadd_rn((double)s.ep_ret, rew);
+      s.ep_len += 1;
+      if (done) {
+        flags |= MGPLR_F_DONE;
+        if (A.o.ep_return) A.o.ep_return[e] = s.ep_ret;
+        if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
+        s.ep_ret = 0.f; s.ep_len = 0;
+        if (RR) {  // worker.step_env (parallel_wrappers.py:27-37)
+          s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1));
+          dirty = true;
+        } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+      } else if ((A.last_step & 3) == 3 && want_trunc) {
+        rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+      }
+    }
+    const View v = render_view_t<SEE, EXT>(R, s, W);
+    // re-acquire the observation buffer: the previous tile's bulk store must have finished reading it
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    emit_obs_f32_fast<SEE>(v, s_obs + lane * kObsFloats);
+    if (A.o.image) {
+      float *gdst = A.o.image + (size_t)base * kObsFloats;
+      if (aligned && n_tile == kWarpTile) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { bulk_store(gdst, s_obs, kWarpTile * kObsFloats * 4); bulk_commit(); }
+      } else {
+        __syncwarp();
+        for (int i = lane; i < n_tile * kObsFloats; i += 32) gdst[i] = s_obs[i];
+        __syncwarp();
+      }
+    }
+    if (valid) {
+      d.hot[e] = pack(s);
+      write_step_scalars(A, e, s, flags, (float)rew);
+      if (A.o.image_u8) rare_emit_u8(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.image_u8, e);
+      if (RR && dirty)
+        for (int r = 0; r < W; r++) d.wall[(size_t)r * N + e] = rows[r * kWarpTile + lane];
+    }
+  }
+  if (lane == 0) bulk_wait_read0();
 }
 
 // T transitions in one launch from a recorded action stream u8 [T][N]; state stays on chip and the observation
 // tile is double-buffered so step t's bulk store overlaps step t+1's compute.
-template <bool SEE, bool RR, int TILE>
+template <bool SEE, bool RR, int TILE, typename EXT>
 __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions, int T, StepArgs A0) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -598,7 +731,8 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
     __syncthreads();
     if (valid) {
       float rew;
-      const uint32_t flags = step_one<SEE, RR>(d, s_rows + tid, TILE, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats, rew, dirty);
+      const uint32_t flags = step_one<SEE, RR, EXT>(d, s_rows + tid, TILE, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats,
+                                                    rew, dirty);
       write_step_scalars(A, e, s, flags, rew);
     }
     if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, n_tile, false);
@@ -668,15 +802,18 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   v->bytes = total;
   CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device));
   {
-    const int smem64 = (int)step_smem_bytes(cfg->width, 64, 1), smem128 = (int)step_smem_bytes(cfg->width, 128, 1);
-    const int r64 = (int)step_smem_bytes(cfg->width, 64, 2), r128 = (int)step_smem_bytes(cfg->width, 128, 2);
-#define SET_ATTR(SEE, RR)                                                                                              \
-  CK(cudaFuncSetAttribute(k_step_env<SEE, RR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));              \
-  CK(cudaFuncSetAttribute(k_step_env<SEE, RR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128));            \
-  CK(cudaFuncSetAttribute(k_rollout<SEE, RR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, r64));                  \
-  CK(cudaFuncSetAttribute(k_rollout<SEE, RR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, r128));
-    SET_ATTR(true, false) SET_ATTR(true, true) SET_ATTR(false, false) SET_ATTR(false, true)
-#undef SET_ATTR
+    const int W = cfg->width;
+    const int step_smem = (int)(4 * warp_smem_bytes(W));
+#define SET_STEP(SEE, RR, EXT) CK(cudaFuncSetAttribute(k_step_env<SEE, RR, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, step_smem));
+#define SET_ROLL(SEE, RR, TL, EXT) \
+  CK(cudaFuncSetAttribute(k_rollout<SEE, RR, TL, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes(W, TL, 2)));
+#define SET_ALL(EXT)                                                                                  \
+  SET_STEP(true, false, EXT) SET_STEP(true, true, EXT) SET_STEP(false, false, EXT) SET_STEP(false, true, EXT) \
+  SET_ROLL(true, false, 64, EXT) SET_ROLL(true, true, 64, EXT) SET_ROLL(false, false, 64, EXT) SET_ROLL(false, true, 64, EXT)
+    if (W <= 24) { SET_ALL(uint32_t) } else { SET_ALL(uint64_t) }
+#undef SET_ALL
+#undef SET_ROLL
+#undef SET_STEP
   }
   CK(cudaMemset(d.mt, 0, 624 * N * sizeof(uint32_t)));
   k_init<<<grid_for(num_envs, 256), 256>>>(d);
@@ -698,9 +835,16 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
 extern "C" int32_t mgplr_venv_num_envs(const mgplr_venv *v) { return v ? v->d.N : 0; }
 extern "C" int64_t mgplr_venv_state_bytes(const mgplr_venv *v) { return v ? v->bytes : 0; }
 
+// make the handle's device current only when it is not already (cudaGetDevice is a thread-local read)
+static inline cudaError_t use_device(int device) {
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) return e;
+  return cur == device ? cudaSuccess : cudaSetDevice(device);
+}
 #define NEED(v)                                                 \
   if (!(v)) return fail(MGPLR_E_BADARG, "venv handle is NULL"); \
-  CK(cudaSetDevice((v)->device));                               \
+  CK(use_device((v)->device));                                  \
   cudaStream_t st = (cudaStream_t)stream
 
 extern "C" int mgplr_seed(mgplr_venv *v, const uint32_t *limbs_host, const int32_t *n_limbs_host, const int32_t *index_host,
@@ -809,21 +953,25 @@ static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_rando
   memset(&A, 0, sizeof(A));
   A.action = action; A.n_walls = n_walls; A.last_step = last_step;
   if (out) A.o = *out;
-  const int tile = step_tile();
-  const int grid = grid_for(v->d.N, tile);
-  const size_t smem = step_smem_bytes(v->d.c.W, tile, 1);
-  const int key = (v->d.c.see_through ? 4 : 0) | (reset_random ? 2 : 0) | (tile == 128 ? 1 : 0);
-#define LAUNCH(SEE, RR, TL) k_step_env<SEE, RR, TL><<<grid, TL, smem, st>>>(v->d, A)
-  switch (key) {
-    case 7: LAUNCH(true, true, 128); break;
-    case 6: LAUNCH(true, true, 64); break;
-    case 5: LAUNCH(true, false, 128); break;
-    case 4: LAUNCH(true, false, 64); break;
-    case 3: LAUNCH(false, true, 128); break;
-    case 2: LAUNCH(false, true, 64); break;
-    case 1: LAUNCH(false, false, 128); break;
-    default: LAUNCH(false, false, 64); break;
-  }
+  // persistent grid: as many 4-warp CTAs as fit on the chip (shared-memory bound), capped by the tile count
+  const int W = v->d.c.W, wpc = 4;
+  const size_t smem = wpc * warp_smem_bytes(W);
+  const int n_tiles = (v->d.N + kWarpTile - 1) / kWarpTile;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
+  int grid = v->sm_count * per_sm;
+  const int need = (n_tiles + wpc - 1) / wpc;
+  if (grid > need) grid = need;
+  const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
+#define LAUNCH(SEE, RR, EXT) k_step_env<SEE, RR, EXT><<<grid, wpc * 32, smem, st>>>(v->d, A, n_tiles)
+#define BY_MODE(EXT)                                  \
+  do {                                                \
+    if (see && rr) LAUNCH(true, true, EXT);           \
+    else if (see) LAUNCH(true, false, EXT);           \
+    else if (rr) LAUNCH(false, true, EXT);            \
+    else LAUNCH(false, false, EXT);                   \
+  } while (0)
+  if (narrow) BY_MODE(uint32_t); else BY_MODE(uint64_t);
+#undef BY_MODE
 #undef LAUNCH
   CK(cudaGetLastError());
   return 0;
@@ -874,21 +1022,20 @@ extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, i
   StepArgs A;
   memset(&A, 0, sizeof(A));
   if (out_t0) A.o = *out_t0;
-  const int tile = step_tile();
+  const int tile = 64;
   const int grid = grid_for(v->d.N, tile);
   const size_t smem = step_smem_bytes(v->d.c.W, tile, 2);
-  const int key = (v->d.c.see_through ? 4 : 0) | (reset_random ? 2 : 0) | (tile == 128 ? 1 : 0);
-#define LAUNCH(SEE, RR, TL) k_rollout<SEE, RR, TL><<<grid, TL, smem, st>>>(v->d, actions, T, A)
-  switch (key) {
-    case 7: LAUNCH(true, true, 128); break;
-    case 6: LAUNCH(true, true, 64); break;
-    case 5: LAUNCH(true, false, 128); break;
-    case 4: LAUNCH(true, false, 64); break;
-    case 3: LAUNCH(false, true, 128); break;
-    case 2: LAUNCH(false, true, 64); break;
-    case 1: LAUNCH(false, false, 128); break;
-    default: LAUNCH(false, false, 64); break;
-  }
+  const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = v->d.c.W <= 24;
+#define LAUNCH(SEE, RR, EXT) k_rollout<SEE, RR, 64, EXT><<<grid, 64, smem, st>>>(v->d, actions, T, A)
+#define BY_MODE(EXT)                                  \
+  do {                                                \
+    if (see && rr) LAUNCH(true, true, EXT);           \
+    else if (see) LAUNCH(true, false, EXT);           \
+    else if (rr) LAUNCH(false, true, EXT);            \
+    else LAUNCH(false, false, EXT);                   \
+  } while (0)
+  if (narrow) BY_MODE(uint32_t); else BY_MODE(uint64_t);
+#undef BY_MODE
 #undef LAUNCH
   CK(cudaGetLastError());
   return 0;
@@ -912,6 +1059,7 @@ extern "C" int mgplr_get_metrics(mgplr_venv *v, int32_t *metrics, void *stream) 
 extern "C" int mgplr_get_agent_state(mgplr_venv *v, int32_t *state, void *stream) {
   NEED(v);
   if (!state) return fail(MGPLR_E_BADARG, "state is NULL");
+  k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d);
   k_get_agent_state<<<grid_for(v->d.N, 256), 256, 0, st>>>(v->d, state);
   CK(cudaGetLastError());
   return 0;
@@ -929,6 +1077,8 @@ extern "C" int mgplr_peek_rng(mgplr_venv *v, int32_t index, uint32_t *words_host
   if (!v) return fail(MGPLR_E_BADARG, "venv handle is NULL");
   CK(cudaSetDevice(v->device));
   if (index < 0 || index >= v->d.N || !words_host || count < 0) return fail(MGPLR_E_BADARG, "mgplr_peek_rng: bad arguments");
+  k_flush<<<grid_for(v->d.N, 128), 128>>>(v->d);
+  CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   uint32_t mt[624], idx = 0;
   CK(cudaMemcpy2D(mt, sizeof(uint32_t), v->d.mt + index, (size_t)v->d.N * sizeof(uint32_t), sizeof(uint32_t), 624,

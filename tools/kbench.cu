@@ -1,0 +1,58 @@
+// kbench.cu -- C-side micro-benchmark of the step kernel through the C ABI (no Python in the loop).
+//   nvcc -O2 -o gpurun_out/kbench tools/kbench.cu -Ldcd_isaac_b200 -lmgplr -Xlinker -rpath=$PWD/dcd_isaac_b200
+// usage: kbench N W T reps ablate   (ablate bits: 1 no image, 2 no scalar outputs, 4 no masks)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../include/mgplr.h"
+
+#define CKC(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("cuda %s line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+#define CKM(x) do { int rc = (x); if (rc) { printf("mgplr rc=%d %s line %d\n", rc, mgplr_last_error(), __LINE__); exit(1);} } while (0)
+
+int main(int argc, char **argv) {
+  int N = argc > 1 ? atoi(argv[1]) : 131072, W = argc > 2 ? atoi(argv[2]) : 15, T = argc > 3 ? atoi(argv[3]) : 64;
+  int reps = argc > 4 ? atoi(argv[4]) : 5, ablate = argc > 5 ? atoi(argv[5]) : 0, see = argc > 6 ? atoi(argv[6]) : 1, amode = argc > 7 ? atoi(argv[7]) : 0;
+  mgplr_env_config cfg = {W, 5, 250, 250, see, 50, 0, 1, 0, 4};
+  mgplr_venv *v;
+  CKM(mgplr_venv_create(&cfg, N, 0, &v));
+  std::vector<uint32_t> limbs(2 * N); std::vector<int32_t> cnt(N, 2);
+  for (int i = 0; i < N; i++) { limbs[2 * i] = 12345u + 977u * i; limbs[2 * i + 1] = 99u + i; }
+  CKM(mgplr_seed(v, limbs.data(), cnt.data(), nullptr, N, 0));
+  CKM(mgplr_reset_random(v, nullptr, nullptr, 0));
+  float *img, *dir, *rew, *mk, *bm, *cm; uint8_t *fl; int64_t *act; float *epr; int32_t *epl;
+  CKC(cudaMalloc(&img, (size_t)(T + 1) * N * 300)); CKC(cudaMalloc(&dir, (size_t)(T + 1) * N * 4)); CKC(cudaMalloc(&rew, (size_t)T * N * 4));
+  CKC(cudaMalloc(&mk, (size_t)(T + 1) * N * 4)); CKC(cudaMalloc(&bm, (size_t)(T + 1) * N * 4)); CKC(cudaMalloc(&cm, (size_t)(T + 1) * N * 4));
+  CKC(cudaMalloc(&fl, (size_t)T * N)); CKC(cudaMalloc(&act, (size_t)T * N * 8)); CKC(cudaMalloc(&epr, N * 4)); CKC(cudaMalloc(&epl, N * 4));
+  std::vector<int64_t> h((size_t)T * N);
+  srand(1);
+  for (auto &x : h) x = amode == 1 ? (rand() & 1) : ((rand() & 1) ? 2 : rand() % 7);
+  CKC(cudaMemcpy(act, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+  cudaStream_t st; CKC(cudaStreamCreate(&st));
+  auto steps = [&]() {
+    mgplr_step_out ro = {}; ro.image = img; ro.direction = dir;
+    CKM(mgplr_reset_agent(v, &ro, st));  // start of a rollout (also replays deferred respawn draws)
+    for (int t = 0; t < T; t++) {
+      mgplr_step_out o = {};
+      if (!(ablate & 1)) o.image = img + (size_t)(t + 1) * N * 75;
+      if (!(ablate & 2)) { o.direction = dir + (size_t)(t + 1) * N; o.reward = rew + (size_t)t * N; o.flags = fl + (size_t)t * N; o.ep_return = epr; o.ep_length = epl; }
+      if (!(ablate & 4)) { o.masks = mk + (size_t)(t + 1) * N; o.bad_masks = bm + (size_t)(t + 1) * N; o.cliffhanger_masks = cm + (size_t)(t + 1) * N; }
+      CKM(mgplr_step_env(v, act + (size_t)t * N, 0, nullptr, 0, &o, st));
+    }
+  };
+  steps(); CKC(cudaStreamSynchronize(st));
+  cudaGraph_t g; cudaGraphExec_t ge;
+  CKC(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal)); steps(); CKC(cudaStreamEndCapture(st, &g));
+  CKC(cudaGraphInstantiate(&ge, g, 0));
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  CKC(cudaGraphLaunch(ge, st)); CKC(cudaStreamSynchronize(st));
+  cudaEventRecord(a, st);
+  for (int r = 0; r < reps; r++) CKC(cudaGraphLaunch(ge, st));
+  cudaEventRecord(b, st); CKC(cudaStreamSynchronize(st));
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  double us = ms * 1e3 / (reps * (double)T);  // includes 1/T of the reset_agent launch
+  printf("amode=%d ", amode); printf("N=%d W=%d T=%d see=%d ablate=%d tile=%s: %.2f us/launch  %.3f Gsteps/s  %.0f GB/s@360B\n", N, W, T, see, ablate,
+         getenv("MGPLR_TILE") ? getenv("MGPLR_TILE") : "def", us, N / us * 1e-3, N * 360.0 / us * 1e-3);
+  mgplr_venv_destroy(v);
+  return 0;
+}
