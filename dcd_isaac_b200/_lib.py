@@ -101,8 +101,8 @@ def load():
     L.mgplr_peek_rng.argtypes = [vp, i32, vp, i32]
     L.mgplr_gae.argtypes = [vp, vp, vp, vp, i32, i32, f64, f64, vp]
     L.mgplr_plr_episode_scores.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp]
-    L.mgplr_plr_sample_weights.argtypes = [vp, vp, vp, i32, f64, f64, f64, vp, vp]
-    L.mgplr_plr_sample_replay.argtypes = [vp, vp, vp, i32, f64, f64, f64, vp, i32, vp, vp]
+    L.mgplr_plr_sample_weights.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, i32, f64, vp, vp]
+    L.mgplr_plr_sample_replay.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, i32, f64, vp, i32, vp, vp]
     _lib = L
     return L
 

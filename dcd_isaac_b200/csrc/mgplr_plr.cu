@@ -57,6 +57,7 @@ __global__ void k_count_episodes(const float *__restrict__ masks, int T, int N, 
   if (e >= N) return;
   int c = 0;
   for (int t = 1; t <= T; t++) c += !(masks[(size_t)t * N + e] > 0.f);
+  c += (masks[(size_t)T * N + e] > 0.f);  // trailing partial episode (level_sampler.py:551-578)
   counts[e] = c;
 }
 
@@ -128,6 +129,14 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
       k++;
       start = t_end; sum = 0.0; vsum = 0.0; mx = -INFINITY; rsum = 0.f; vmin = INFINITY;
     }
+  }
+  if (start < T && k < max_out) {  // not-done tail: a partial record (cliffhanger field = 2)
+    mgplr_episode ep;
+    ep.actor = e; ep.t_start = start; ep.t_end = T; ep.seed = seeds ? seeds[(size_t)start * N + e] : -1;
+    const int n = T - start;
+    ep.mean_score = (float)(sum / (double)n); ep.max_score = mx; ep.reward_sum = rsum;
+    ep.value_sum = (float)vsum; ep.value_min = vmin; ep.cliffhanger = 2;
+    out[k] = ep;
   }
 }
 
@@ -203,65 +212,82 @@ __device__ double block_sum(double v, double *red) {
   return r;
 }
 
-// rank weights (before staleness mixing) into w_rank[n] (global); uses dynamic smem for the keys
-__device__ void rank_weights(const double *scores, const double *unseen, int n, double temperature, double *w_rank, Key *keys,
-                             double *red) {
-  int n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-    Key k;
-    k.s = (i < n) ? scores[i] : -INFINITY; k.i = (i < n) ? i : -1 - i;
-    keys[i] = k;
-  }
-  __syncthreads();
-  block_sort_desc(keys, n2);
+// _score_transform (level_sampler.py:752-785) for the transforms the shipped configs use:
+//   1 rank:     w = 1 / rank^(1/T), rank 1 = highest value, ties by index (see before())
+//   2 power:    w = (clip(v, 0) + eps)^(1/T)
+//   0 constant: w = 1
+// out[i] receives the raw transform of vals[i]; `keys` is dynamic shared memory for the sort.
+__device__ void transform_vals(int transform, const double *vals, int n, double temperature, double eps, double *out, Key *keys) {
   const double inv_t = 1.0 / temperature;
-  double part = 0.0;
-  for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    const int i = keys[r].i;
-    const double w = (1.0 / pow((double)(r + 1), inv_t)) * (1.0 - unseen[i]);
-    w_rank[i] = w; part += w;
-  }
-  const double z = block_sum(part, red);
-  double nseen_part = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) nseen_part += (1.0 - unseen[i]);
-  const double nseen = block_sum(nseen_part, red);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    if (z > 0) w_rank[i] = w_rank[i] / z;
-    else w_rank[i] = ((1.0 / (double)n) * (1.0 - unseen[i])) / (nseen / (double)n);  // uniform over seen (level_sampler.py:733-736)
+  if (transform == 1) {
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      Key k;
+      k.s = (i < n) ? vals[i] : -INFINITY; k.i = (i < n) ? i : -1 - i;
+      keys[i] = k;
+    }
+    __syncthreads();
+    block_sort_desc(keys, n2);
+    for (int r = threadIdx.x; r < n; r += blockDim.x) out[keys[r].i] = 1.0 / pow((double)(r + 1), inv_t);
+  } else if (transform == 2) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = pow(fmax(vals[i], 0.0) + eps, inv_t);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = 1.0;
   }
   __syncthreads();
 }
 
-__device__ void mix_staleness(const double *w_rank, const double *staleness, const double *unseen, int n, double coef,
-                              double stale_t, double *weights, double *red) {
-  if (!(coef > 0)) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) weights[i] = w_rank[i];
+// mask by seen, normalise (uniform over seen when the mass is zero): level_sampler.py:728-736 / 741-746
+__device__ void mask_normalise(double *w, const double *unseen, int n, bool uniform_fallback_normalised, double *red) {
+  double part = 0.0, seen_part = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = w[i] * (1.0 - unseen[i]);
+    w[i] = v; part += v; seen_part += (1.0 - unseen[i]);
+  }
+  const double z = block_sum(part, red);
+  const double nseen = block_sum(seen_part, red);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (z > 0) w[i] = w[i] / z;
+    else {
+      const double u = (1.0 / (double)n) * (1.0 - unseen[i]);
+      w[i] = uniform_fallback_normalised ? u / (nseen / (double)n) : u;
+    }
+  }
+  __syncthreads();
+}
+
+struct WeightArgs {
+  int score_transform, stale_transform;
+  double temperature, eps, coef, stale_temperature;
+};
+
+__device__ void score_weights(const double *scores, const double *unseen, int n, const WeightArgs &a, double *w_score, Key *keys,
+                              double *red) {
+  transform_vals(a.score_transform, scores, n, a.temperature, a.eps, w_score, keys);
+  mask_normalise(w_score, unseen, n, true, red);
+}
+
+__device__ void mix_staleness(const double *w_score, const double *staleness, const double *unseen, int n, const WeightArgs &a,
+                              double *weights, Key *keys, double *red) {
+  if (!(a.coef > 0)) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) weights[i] = w_score[i];
     __syncthreads();
     return;
   }
-  const double inv_t = 1.0 / stale_t;
-  double part = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double s = pow(fmax(staleness[i], 0.0), inv_t) * (1.0 - unseen[i]);
-    weights[i] = s; part += s;
-  }
-  const double z = block_sum(part, red);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double s = (z > 0) ? weights[i] / z : (1.0 / (double)n) * (1.0 - unseen[i]);
-    weights[i] = (1.0 - coef) * w_rank[i] + coef * s;
-  }
+  transform_vals(a.stale_transform, staleness, n, a.stale_temperature, 0.0, weights, keys);
+  mask_normalise(weights, unseen, n, false, red);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) weights[i] = (1.0 - a.coef) * w_score[i] + a.coef * weights[i];
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024) k_sample_weights(const double *scores, const double *staleness, const double *unseen, int n,
-                                                         double temperature, double coef, double stale_t, double *weights,
-                                                         double *w_rank) {
+                                                         WeightArgs a, double *weights, double *w_score) {
   extern __shared__ __align__(16) uint8_t sm[];
   Key *keys = reinterpret_cast<Key *>(sm);
   __shared__ double red[33];
-  rank_weights(scores, unseen, n, temperature, w_rank, keys, red);
-  mix_staleness(w_rank, staleness, unseen, n, coef, stale_t, weights, red);
+  score_weights(scores, unseen, n, a, w_score, keys, red);
+  mix_staleness(w_score, staleness, unseen, n, a, weights, keys, red);
 }
 
 static double *g_dscratch = nullptr;
@@ -284,16 +310,21 @@ static size_t sort_smem(int n) {
   return (size_t)n2 * sizeof(Key);
 }
 
+static int check_transform(int t) { return (t >= 0 && t <= 2) ? 0 : pfail(MGPLR_E_UNSUPPORTED, "transform must be 0 constant, 1 rank or 2 power"); }
+
 extern "C" int mgplr_plr_sample_weights(const double *scores, const double *staleness, const double *unseen, int32_t n,
-                                        double temperature, double staleness_coef, double staleness_temperature,
-                                        double *weights, void *stream) {
+                                        int32_t score_transform, double temperature, double eps, double staleness_coef,
+                                        int32_t staleness_transform, double staleness_temperature, double *weights,
+                                        void *stream) {
   if (!scores || !staleness || !unseen || !weights || n < 1 || n > kMaxBuf)
     return pfail(MGPLR_E_BADARG, "mgplr_plr_sample_weights: bad arguments (n must be in [1, 8192])");
+  if (int rc = check_transform(score_transform)) return rc;
+  if (int rc = check_transform(staleness_transform)) return rc;
   if (int rc = ensure_dscratch(2 * (size_t)kMaxBuf)) return rc;
   const size_t smem = sort_smem(n);
   PCK(cudaFuncSetAttribute(k_sample_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_sample_weights<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, temperature, staleness_coef,
-                                                           staleness_temperature, weights, g_dscratch);
+  const WeightArgs a{score_transform, staleness_transform, temperature, eps, staleness_coef, staleness_temperature};
+  k_sample_weights<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, a, weights, g_dscratch);
   PCK(cudaGetLastError());
   return 0;
 }
@@ -302,19 +333,20 @@ extern "C" int mgplr_plr_sample_weights(const double *scores, const double *stal
 // part is recomputed after every draw ("all +1, chosen -> 0").  Inverse CDF: np.random.choice(p=w) =
 // cumsum -> /cdf[-1] -> searchsorted(u, side='right') = #{cdf <= u}.
 __global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, double *staleness, const double *unseen, int n,
-                                                        double temperature, double coef, double stale_t, const double *u,
-                                                        int n_draws, int32_t *out_index, double *w_rank, double *weights) {
+                                                        WeightArgs a, const double *u, int n_draws, int32_t *out_index,
+                                                        double *w_rank, double *weights) {
   extern __shared__ __align__(16) uint8_t sm[];
   Key *keys = reinterpret_cast<Key *>(sm);
   __shared__ double red[33];
   __shared__ double wsum[32];
   __shared__ int s_pick;
-  rank_weights(scores, unseen, n, temperature, w_rank, keys, red);
+  score_weights(scores, unseen, n, a, w_rank, keys, red);
+  const double coef = a.coef;
   // contiguous chunk per thread so the scan is a per-thread serial cumsum + a block scan of chunk sums
   const int per = (n + blockDim.x - 1) / blockDim.x;
   const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
   for (int dr = 0; dr < n_draws; dr++) {
-    mix_staleness(w_rank, staleness, unseen, n, coef, stale_t, weights, red);
+    mix_staleness(w_rank, staleness, unseen, n, a, weights, keys, red);
     double local = 0.0;
     for (int i = lo; i < hi; i++) local += weights[i];
     // block exclusive scan of `local`
@@ -354,15 +386,18 @@ __global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, do
 }
 
 extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, const double *unseen, int32_t n,
-                                       double temperature, double staleness_coef, double staleness_temperature,
-                                       const double *u, int32_t n_draws, int32_t *out_index, void *stream) {
+                                       int32_t score_transform, double temperature, double eps, double staleness_coef,
+                                       int32_t staleness_transform, double staleness_temperature, const double *u,
+                                       int32_t n_draws, int32_t *out_index, void *stream) {
   if (!scores || !staleness || !unseen || !u || !out_index || n < 1 || n > kMaxBuf || n_draws < 1)
     return pfail(MGPLR_E_BADARG, "mgplr_plr_sample_replay: bad arguments (n must be in [1, 8192])");
+  if (int rc = check_transform(score_transform)) return rc;
+  if (int rc = check_transform(staleness_transform)) return rc;
   if (int rc = ensure_dscratch(2 * (size_t)kMaxBuf)) return rc;
   const size_t smem = sort_smem(n);
   PCK(cudaFuncSetAttribute(k_sample_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_sample_replay<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, temperature, staleness_coef,
-                                                          staleness_temperature, u, n_draws, out_index, g_dscratch,
+  const WeightArgs a{score_transform, staleness_transform, temperature, eps, staleness_coef, staleness_temperature};
+  k_sample_replay<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, a, u, n_draws, out_index, g_dscratch,
                                                           g_dscratch + kMaxBuf);
   PCK(cudaGetLastError());
   return 0;

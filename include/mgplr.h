@@ -184,7 +184,7 @@ typedef struct mgplr_episode {
   float reward_sum;   /* sum of rewards[t_start:t_end] (grounded value, level_sampler.py:534) */
   float value_sum;    /* sum of value_preds[t_start:t_end] */
   float value_min;    /* min of value_preds[t_start:t_end] (max of grounded - v) */
-  int32_t cliffhanger; /* cliffhanger_masks[t_end][actor] == 0 -> skipped by the sampler */
+  int32_t cliffhanger; /* 1: cliffhanger_masks[t_end][actor] == 0 -> skipped by the sampler; 2: not-done tail (partial) */
 } mgplr_episode;
 
 /* LevelSampler._update_with_rollouts segmentation + score functions (level_sampler.py:486-549,307-349).
@@ -196,19 +196,25 @@ int mgplr_plr_episode_scores(const float *masks, const float *cliffhanger_masks,
                              int32_t N, int32_t strategy, mgplr_episode *episodes, int32_t max_episodes,
                              int32_t *n_episodes, void *stream);
 
-/* LevelSampler.sample_weights (level_sampler.py:726-785), rank transform + power staleness, fp64.
- * scores / staleness / unseen f64 [n] -> weights f64 [n].  Ties in the rank transform are broken by
- * index (higher index = better rank), the order numpy's stable-on-ties flip(argsort) would give. */
+#define MGPLR_TRANSFORM_CONSTANT 0
+#define MGPLR_TRANSFORM_RANK 1
+#define MGPLR_TRANSFORM_POWER 2
+
+/* LevelSampler.sample_weights / _score_transform (level_sampler.py:726-785) in fp64 for the constant / rank / power
+ * transforms (score and staleness): w = normalise(transform(scores) * seen); s = normalise(transform(staleness) *
+ * seen); weights = (1-c) w + c s.  scores / staleness / unseen f64 [n] -> weights f64 [n] (device).  Ties in the
+ * rank transform are broken by index (higher index = better rank): np.flip(np.argsort(scores, kind='stable')). */
 int mgplr_plr_sample_weights(const double *scores, const double *staleness, const double *unseen, int32_t n,
-                             double temperature, double staleness_coef, double staleness_temperature,
-                             double *weights, void *stream);
+                             int32_t score_transform, double temperature, double eps, double staleness_coef,
+                             int32_t staleness_transform, double staleness_temperature, double *weights, void *stream);
 
 /* n_draws sequential _sample_replay_level draws (level_sampler.py:664-680 + 601-604) with recorded uniforms
  * u f64 [n_draws] (np.random.choice's single random_sample each): staleness is updated between draws
  * exactly as the reference does.  out_index i32 [n_draws]; staleness f64 [n] updated in place. */
 int mgplr_plr_sample_replay(const double *scores, double *staleness, const double *unseen, int32_t n,
-                            double temperature, double staleness_coef, double staleness_temperature,
-                            const double *u, int32_t n_draws, int32_t *out_index, void *stream);
+                            int32_t score_transform, double temperature, double eps, double staleness_coef,
+                            int32_t staleness_transform, double staleness_temperature, const double *u, int32_t n_draws,
+                            int32_t *out_index, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,208 @@
+"""PLR-side golden fixtures, produced by EXECUTING the reference's level_replay/level_sampler.py,
+level_replay/level_store.py and algos/storage.py unmodified (TEST INFRASTRUCTURE ONLY).
+
+  python oracle/gen_golden.py --only plr
+"""
+import gzip
+import os
+import pickle
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+
+def _storage(T, N, rs, mean_len=12, handle_timelimits=True, dense_vals=True):
+    """A reference RolloutStorage filled like adversarial_runner.agent_rollout fills it."""
+    import numpy as np
+    import torch
+    from gym import spaces
+    from algos.storage import RolloutStorage
+    obs_space = {'image': spaces.Box(0, 255, (3, 5, 5), 'uint8'), 'direction': spaces.Box(0, 3, (1,), 'uint8')}
+    st = RolloutStorage(model=None, num_steps=T, num_processes=N, observation_space=obs_space,
+                        action_space=spaces.Discrete(7), recurrent_hidden_state_size=1,
+                        use_proper_time_limits=False)
+    done = rs.rand(T, N) < (1.0 / mean_len)
+    done[-1] = True  # the runner forces done on the last step (adversarial_runner.py:530)
+    goal = done & (rs.rand(T, N) < 0.5)
+    rewards = np.where(goal, 1.0 - 0.9 * rs.randint(1, 250, size=(T, N)) / 250.0, 0.0).astype(np.float32)
+    st.rewards.copy_(torch.from_numpy(rewards).unsqueeze(-1))
+    st.masks[1:].copy_(torch.from_numpy(1.0 - done.astype(np.float32)).unsqueeze(-1))
+    cliff = np.zeros((T, N), bool)
+    if handle_timelimits:
+        cliff[-1] = rs.rand(N) < 0.6  # not-done envs at the rollout end become cliffhangers (:521-528)
+    st.cliffhanger_masks[1:].copy_(torch.from_numpy(1.0 - cliff.astype(np.float32)).unsqueeze(-1))
+    st.value_preds.copy_(torch.from_numpy(rs.randn(T + 1, N, 1).astype(np.float32) * 0.3 + 0.4))
+    st.action_log_dist.copy_(torch.from_numpy(rs.randn(T, N, 7).astype(np.float32)))
+    return st, done
+
+
+def gen_gae():
+    import numpy as np
+    import torch
+    rs = np.random.RandomState(11)
+    out = {}
+    for tag, T, N in (('a', 256, 32), ('b', 64, 7), ('c', 5, 1)):
+        st, _ = _storage(T, N, rs)
+        nv = torch.from_numpy(rs.randn(N, 1).astype(np.float32))
+        st.compute_returns(nv, True, 0.995, 0.95)
+        out['rewards_' + tag] = st.rewards.numpy()[:, :, 0].copy()
+        out['values_' + tag] = st.value_preds.numpy()[:, :, 0].copy()
+        out['masks_' + tag] = st.masks.numpy()[:, :, 0].copy()
+        out['returns_' + tag] = st.returns.numpy()[:, :, 0].copy()
+    np.savez_compressed(os.path.join(GOLDEN, 'plr_gae.npz'), gamma=0.995, gae_lambda=0.95, **out)
+    print('gae fixtures', sorted(out)[:3])
+
+
+PLR_CASES = [
+    # tag, strategy, buffer, temperature, staleness_coef, replay_prob, rho, num_actors, T
+    ('pvl_small', 'positive_value_loss', 24, 0.3, 0.3, 0.8, 0.5, 8, 64),
+    ('maxmc_small', 'grounded_signed_value_loss', 24, 0.1, 0.3, 0.5, 0.5, 8, 64),
+    ('pvl_4000', 'positive_value_loss', 4000, 0.3, 0.3, 0.5, 0.01, 32, 256),
+    ('l1_nostale', 'value_l1', 16, 1.0, 0.0, 0.95, 0.25, 4, 48),
+    ('signed_power', 'signed_value_loss', 16, 0.5, 0.1, 0.9, 0.25, 4, 48),
+]
+
+
+def gen_sampler():
+    """A replayed PLR session: new levels observed, rollouts scored, buffer admission/eviction, replay
+    decisions and draws -- all from the reference LevelSampler/LevelStore with a seeded global np.random."""
+    import numpy as np
+    import torch
+    from level_replay import LevelSampler, LevelStore
+    from gym import spaces
+    for tag, strategy, buf, temp, sc, rp, rho, A, T in PLR_CASES:
+        np.random.seed(77)
+        rs = np.random.RandomState(5)
+        transform = 'power' if tag == 'signed_power' else 'rank'
+        sampler = LevelSampler([], {'image': spaces.Box(0, 255, (3, 5, 5), 'uint8')}, spaces.Discrete(7), num_actors=A,
+                               strategy=strategy, replay_schedule=('fixed' if tag == 'pvl_4000' else 'proportionate'), score_transform=transform,
+                               temperature=temp, eps=0.05, rho=rho, replay_prob=rp, alpha=1.0, staleness_coef=sc,
+                               staleness_transform='power', staleness_temperature=1.0, sample_full_distribution=True,
+                               seed_buffer_size=buf, seed_buffer_priority='replay_support', use_dense_rewards=False,
+                               gamma=0.995)
+        store = LevelStore(data_info={'numpy': True, 'dtype': np.uint8, 'shape': (15, 15, 3)})
+        log = []
+        n_cycles = 14 if buf <= 24 else 8
+        next_level = 0
+        for cyc in range(n_cycles):
+            rec = {}
+            replay = bool(sampler.sample_replay_decision())
+            rec['replay'] = replay
+            rec['rng_after_decision'] = np.random.get_state()[2]
+            if replay:
+                seeds = [sampler.sample_replay_level() for _ in range(A)]
+                rec['sampled'] = np.array(seeds, dtype=np.int64)
+                rec['staleness_after_sample'] = sampler.seed_staleness.copy()
+            else:
+                levels = []
+                for _ in range(A):
+                    enc = np.zeros((15, 15, 3), np.uint8)
+                    enc[:, :, 0] = 1
+                    enc[0, 0, 0] = 2
+                    # a few duplicates exercise LevelStore's content dedupe
+                    ident = next_level if rs.rand() > 0.15 or next_level == 0 else rs.randint(0, next_level)
+                    enc[1 + ident % 13, 1 + (ident // 13) % 13, :] = (8, 1, 0)
+                    enc[1 + (ident // 169) % 13, 13, :] = (2, 5, 0)
+                    next_level += 1
+                    levels.append(enc.tobytes())
+                seeds = store.insert(levels)
+                rec['inserted'] = np.array(seeds, dtype=np.int64)
+                solv = [bool(s % 3) for s in seeds]
+                sampler.observe_external_unseen_sample(seeds, solvable=solv)
+            st, done = _storage(T, A, rs, mean_len=10)
+            # level_seeds: current seed per actor, re-sampled on done when replaying (adversarial_runner.py:551-588)
+            cur = list(seeds)
+            ls = np.zeros((T, A), np.int32)
+            resampled = []
+            for t in range(T):
+                ls[t] = cur
+                if replay:
+                    for i in range(A):
+                        if done[t, i]:
+                            cur[i] = sampler.sample_replay_level()
+                            resampled.append(cur[i])
+            st.level_seeds.copy_(torch.from_numpy(ls).unsqueeze(-1))
+            rec['resampled'] = np.array(resampled, dtype=np.int64)
+            nv = torch.from_numpy(rs.randn(A, 1).astype(np.float32))
+            st.compute_returns(nv, True, 0.995, 0.95)
+            for k in ('rewards', 'value_preds', 'masks', 'cliffhanger_masks', 'returns'):
+                rec[k] = getattr(st, k).numpy()[:, :, 0].copy()
+            rec['level_seeds'] = ls
+            if replay or True:  # robust PLR also scores the non-replay (exploratory) rollouts
+                sampler.update_with_rollouts(st)
+                sampler.after_update()
+            store.reconcile_seeds(set(int(x) for x in sampler.seeds if x >= 0))
+            rec['seeds'] = sampler.seeds.copy()
+            rec['seed_scores'] = sampler.seed_scores.copy()
+            rec['seed_staleness'] = sampler.seed_staleness.copy()
+            rec['unseen'] = sampler.unseen_seed_weights.copy()
+            rec['weights'] = sampler.sample_weights().copy() if (sampler.unseen_seed_weights < 1).any() else np.zeros(buf)
+            rec['working_size'] = sampler.working_seed_buffer_size
+            rec['staging'] = np.array(sorted(sampler.staging_seed_set), dtype=np.int64)
+            rec['store_seeds'] = np.array(sorted(store.seed2level), dtype=np.int64)
+            rec['solvable_mass'] = float(sampler.solvable_mass) if (sampler.unseen_seed_weights < 1).any() else -1.0
+            rec['running_sample_count'] = sampler.running_sample_count
+            if sampler.grounded_values is not None:
+                rec['grounded_values'] = sampler.grounded_values.copy()
+            rec['rng_pos'] = np.random.get_state()[2]
+            log.append(rec)
+        with gzip.open(os.path.join(GOLDEN, 'plr_session_%s.pkl.gz' % tag), 'wb') as f:
+            pickle.dump({'case': (tag, strategy, buf, temp, sc, rp, rho, A, T), 'transform': transform,
+                         'schedule': 'fixed' if tag == 'pvl_4000' else 'proportionate', 'log': log}, f,
+                        protocol=4)
+        print('plr session', tag, 'replays', sum(r['replay'] for r in log), 'working', log[-1]['working_size'],
+              'max score', float(np.max(log[-1]['seed_scores'])))
+
+
+def gen_weights():
+    """sample_weights / sampling with recorded uniforms on tie-free and tied score vectors."""
+    import numpy as np
+    from level_replay import LevelSampler
+    from gym import spaces
+    rs = np.random.RandomState(3)
+    out = {}
+    for tag, n, temp, sc, ties in (('n4000', 4000, 0.3, 0.3, False), ('n4000_t01', 4000, 0.1, 0.3, False),
+                                   ('n100_ties', 100, 0.3, 0.3, True), ('n37_nostale', 37, 1.0, 0.0, False)):
+        s = LevelSampler([], {'image': spaces.Box(0, 255, (3, 5, 5), 'uint8')}, spaces.Discrete(7), num_actors=4,
+                         strategy='positive_value_loss', score_transform='rank', temperature=temp, rho=0.5,
+                         replay_prob=0.5, staleness_coef=sc, staleness_transform='power', staleness_temperature=1.0,
+                         sample_full_distribution=True, seed_buffer_size=n)
+        scores = rs.rand(n)
+        if ties:
+            scores = np.round(scores * 5) / 5
+        unseen = (rs.rand(n) < 0.2).astype(np.float64)
+        stale = np.floor(rs.rand(n) * 50)
+        s.seed_scores[:] = scores
+        s.unseen_seed_weights[:] = unseen
+        s.seed_staleness[:] = stale
+        s.seeds[:] = np.arange(1, n + 1)
+        s.working_seed_buffer_size = n
+        out['scores_' + tag] = scores
+        out['unseen_' + tag] = unseen
+        out['stale_' + tag] = stale
+        out['weights_' + tag] = s.sample_weights()
+        out['params_' + tag] = np.array([temp, sc, 1.0])
+        np.random.seed(123)
+        st = np.random.get_state()
+        picks = [s.sample_replay_level() for _ in range(40)]
+        np.random.set_state(st)
+        out['u_' + tag] = np.array([np.random.random_sample() for _ in range(40)])
+        out['picks_' + tag] = np.array(picks, dtype=np.int64) - 1  # seed -> index
+        out['stale_after_' + tag] = s.seed_staleness.copy()
+    np.savez_compressed(os.path.join(GOLDEN, 'plr_weights.npz'), **out)
+    print('weights fixtures ok')
+
+
+def gen_plr():
+    rh.activate()
+    gen_gae()
+    gen_weights()
+    gen_sampler()
+
+
+if __name__ == '__main__':
+    gen_plr()

@@ -1,0 +1,102 @@
+"""numpy restatement of the rollout math of the PLR path (TEST INFRASTRUCTURE ONLY -- never imported by
+dcd_isaac_b200).  Pinned by tests/test_plr_oracle.py against fixtures produced by executing the reference
+(oracle/gen_golden_plr.py -> tests/golden/plr_*.npz / .pkl.gz).
+
+  gae             RolloutStorage.compute_gae_returns        algos/storage.py:233-256
+  episode_scores  LevelSampler._update_with_rollouts + score functions   level_replay/level_sampler.py:486-549,307-349
+  sample_weights  LevelSampler.sample_weights / _score_transform          level_sampler.py:726-785
+  sample_replay   _sample_replay_level + _update_staleness                level_sampler.py:664-680,601-604
+"""
+import numpy as np
+
+
+def gae(rewards, values, masks, gamma, gae_lambda):
+    """rewards [T,N], values/masks [T+1,N] float32 -> returns [T,N]; float32 op-by-op like the torch loop."""
+    f = np.float32
+    r, v, m = rewards.astype(f), values.astype(f), masks.astype(f)
+    T = r.shape[0]
+    g32, gl32 = f(gamma), f(gamma * gae_lambda)
+    out = np.zeros_like(r)
+    acc = np.zeros(r.shape[1], dtype=f)
+    for t in reversed(range(T)):
+        delta = (r[t] + (g32 * v[t + 1]) * m[t + 1]) - v[t]
+        acc = delta + (gl32 * m[t + 1]) * acc
+        out[t] = acc + v[t]
+    return out
+
+
+def episode_scores(masks, cliff, returns, values, rewards, seeds, strategy):
+    """Episode records in actor-major / time-minor order: dicts with actor, t_start, t_end, seed, mean, max,
+    reward_sum, value_sum, value_min, cliffhanger."""
+    T, N = rewards.shape
+    recs = []
+    for a in range(N):
+        start = 0
+        for t in range(1, T + 1):
+            if masks[t, a] > 0:
+                continue
+            sl = slice(start, t)
+            adv = returns[sl, a].astype(np.float64) - values[sl, a].astype(np.float64) if returns is not None else None
+            adv32 = (returns[sl, a] - values[sl, a]).astype(np.float32) if returns is not None else None
+            if strategy == 'positive_value_loss':
+                sc = np.maximum(adv32, 0)
+            elif strategy == 'value_l1':
+                sc = np.abs(adv32)
+            else:
+                sc = adv32
+            recs.append(dict(actor=a, t_start=start, t_end=t, seed=int(seeds[start, a]),
+                             mean=float(np.mean(sc.astype(np.float64))), max=float(np.max(sc)),
+                             reward_sum=float(np.sum(rewards[sl, a].astype(np.float64))),
+                             value_sum=float(np.sum(values[sl, a].astype(np.float64))), value_min=float(np.min(values[sl, a])),
+                             cliffhanger=int(not (cliff[t, a] > 0))))
+            start = t
+    return recs
+
+
+def _transform(name, temperature, vals, eps):
+    if name == 'constant':
+        return np.ones_like(vals)
+    if name == 'rank':
+        order = np.flip(np.argsort(vals, kind='stable'))  # ties: higher index first (documented tie rule)
+        ranks = np.empty_like(order)
+        ranks[order] = np.arange(len(order)) + 1
+        return 1 / ranks ** (1. / temperature)
+    if name == 'power':
+        return (np.array(vals).clip(0) + eps) ** (1. / temperature)
+    raise NotImplementedError(name)
+
+
+def sample_weights(scores, staleness, unseen, score_transform='rank', temperature=0.3, staleness_coef=0.3,
+                   staleness_transform='power', staleness_temperature=1.0):
+    eps = 0 if staleness_coef > 0 else 1e-3
+    w = _transform(score_transform, temperature, scores, eps) * (1 - unseen)
+    z = np.sum(w)
+    if z > 0:
+        w = w / z
+    else:
+        w = np.ones_like(w) / len(w) * (1 - unseen)
+        w = w / np.sum(w)
+    if staleness_coef > 0:
+        s = _transform(staleness_transform, staleness_temperature, staleness, 0) * (1 - unseen)
+        z = np.sum(s)
+        s = s / z if z > 0 else 1. / len(s) * (1 - unseen)
+        w = (1 - staleness_coef) * w + staleness_coef * s
+    return w
+
+
+def sample_replay(scores, staleness, unseen, u, **kw):
+    """Sequential draws with recorded uniforms; returns (indices, final staleness)."""
+    staleness = staleness.copy()
+    idx = []
+    coef = kw.get('staleness_coef', 0.3)
+    for uu in u:
+        w = sample_weights(scores, staleness, unseen, **kw)
+        cdf = np.cumsum(w)
+        cdf /= cdf[-1]
+        i = int(np.searchsorted(cdf, uu, side='right'))
+        i = min(i, len(w) - 1)
+        idx.append(i)
+        if coef > 0:
+            staleness = staleness + 1
+            staleness[i] = 0
+    return np.array(idx), staleness

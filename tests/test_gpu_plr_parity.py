@@ -1,0 +1,195 @@
+"""GPU parity of the PLR path: GAE, episode scores, sample weights / replay draws and whole LevelSampler +
+LevelStore sessions, against fixtures produced by EXECUTING the reference and against the numpy oracle.
+Tolerances: GAE bit-exact; scores / weights 1e-5 relative (north_star); sampled indices, seeds, buffer
+membership and staleness exact."""
+import glob
+import gzip
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+RTOL = 1e-5
+
+
+def test_gae_golden_bit_exact():
+    from dcd_isaac_b200.storage import gae_returns
+    g = golden('plr_gae.npz')
+    for tag in 'abc':
+        r = torch.from_numpy(g['rewards_' + tag]).cuda().unsqueeze(-1).contiguous()
+        v = torch.from_numpy(g['values_' + tag]).cuda().unsqueeze(-1).contiguous()
+        m = torch.from_numpy(g['masks_' + tag]).cuda().unsqueeze(-1).contiguous()
+        out = torch.zeros_like(v)
+        gae_returns(r, v, m, out, float(g['gamma']), float(g['gae_lambda']))
+        assert np.array_equal(out.cpu().numpy()[:-1, :, 0], g['returns_' + tag][:-1]), tag
+
+
+def test_gae_vs_oracle_large():
+    from dcd_isaac_b200.storage import gae_returns
+    from oracle import plr_oracle as po
+    rs = np.random.RandomState(0)
+    T, N = 256, 4096
+    r = (rs.rand(T, N) < 0.02).astype(np.float32) * rs.rand(T, N).astype(np.float32)
+    v = rs.randn(T + 1, N).astype(np.float32)
+    m = (rs.rand(T + 1, N) > 0.03).astype(np.float32)
+    out = torch.zeros(T + 1, N, 1, device='cuda')
+    gae_returns(torch.from_numpy(r).cuda().unsqueeze(-1).contiguous(), torch.from_numpy(v).cuda().unsqueeze(-1).contiguous(),
+                torch.from_numpy(m).cuda().unsqueeze(-1).contiguous(), out, 0.995, 0.95)
+    assert np.array_equal(out.cpu().numpy()[:-1, :, 0], po.gae(r, v, m, 0.995, 0.95))
+
+
+class _Rollouts(object):
+    use_popart = False
+
+
+def _rollouts_from(rec):
+    ro = _Rollouts()
+    for k in ('rewards', 'value_preds', 'masks', 'cliffhanger_masks', 'returns'):
+        setattr(ro, k, torch.from_numpy(rec[k]).unsqueeze(-1).contiguous())
+    ro.level_seeds = torch.from_numpy(rec['level_seeds']).unsqueeze(-1).contiguous()
+    return ro
+
+
+@pytest.mark.parametrize('strategy', ['positive_value_loss', 'signed_value_loss', 'value_l1'])
+def test_episode_scores_vs_oracle(strategy):
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    from oracle import plr_oracle as po
+    rs = np.random.RandomState(4)
+    T, N = 256, 512
+    rec = dict(rewards=rs.rand(T, N).astype(np.float32) * (rs.rand(T, N) < 0.05),
+               value_preds=rs.randn(T + 1, N).astype(np.float32), returns=rs.randn(T + 1, N).astype(np.float32),
+               level_seeds=rs.randint(1, 100, size=(T, N)).astype(np.int32))
+    masks = (rs.rand(T + 1, N) > 0.04).astype(np.float32)
+    masks[-1] = 0
+    masks[0, ::7] = 0  # a done at t == 0 must be skipped without moving start_t (level_sampler.py:504-505)
+    rec['masks'] = masks
+    rec['cliffhanger_masks'] = (rs.rand(T + 1, N) > 0.1).astype(np.float32)
+    s = LevelSampler([], None, None, num_actors=N, strategy=strategy, sample_full_distribution=True, seed_buffer_size=64)
+    got = s.episode_records(_rollouts_from(rec))
+    want = po.episode_scores(rec['masks'], rec['cliffhanger_masks'], rec['returns'], rec['value_preds'], rec['rewards'],
+                             rec['level_seeds'], strategy)
+    assert len(got) == len(want)
+    for k in ('actor', 't_start', 't_end', 'seed', 'cliffhanger'):
+        assert np.array_equal(got[k], np.array([w[k] for w in want])), k
+    assert np.allclose(got['mean_score'], [w['mean'] for w in want], rtol=RTOL, atol=1e-7)
+    assert np.allclose(got['max_score'], [w['max'] for w in want], rtol=RTOL, atol=0)
+    assert np.allclose(got['reward_sum'], [w['reward_sum'] for w in want], rtol=RTOL, atol=1e-7)
+    assert np.allclose(got['value_min'], [w['value_min'] for w in want], rtol=0, atol=0)
+
+
+def test_sample_weights_and_replay_golden():
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    g = golden('plr_weights.npz')
+    for tag in ('n4000', 'n4000_t01', 'n37_nostale', 'n100_ties'):
+        temp, sc, st = g['params_' + tag]
+        n = len(g['scores_' + tag])
+        s = LevelSampler([], None, None, num_actors=4, strategy='positive_value_loss', score_transform='rank',
+                         temperature=float(temp), staleness_coef=float(sc), staleness_transform='power',
+                         staleness_temperature=float(st), sample_full_distribution=True, seed_buffer_size=n)
+        s.seed_scores[:] = g['scores_' + tag]
+        s.unseen_seed_weights[:] = g['unseen_' + tag]
+        s.seed_staleness[:] = g['stale_' + tag]
+        s.seeds[:] = np.arange(1, n + 1)
+        s.working_seed_buffer_size = n
+        w = s.sample_weights()
+        ref = g['weights_' + tag]
+        if 'ties' in tag:  # tie order is unspecified in the reference (numpy quicksort): structure only
+            assert abs(w.sum() - 1) < 1e-12 and np.array_equal(w == 0, ref == 0)
+            from oracle import plr_oracle as po
+            want = po.sample_weights(g['scores_' + tag], g['stale_' + tag], g['unseen_' + tag], temperature=float(temp),
+                                     staleness_coef=float(sc), staleness_temperature=float(st))
+            assert np.allclose(w, want, rtol=1e-12)  # our documented tie rule == the oracle's stable argsort
+            continue
+        assert np.allclose(w, ref, rtol=1e-9, atol=0)
+        np.random.seed(123)
+        picks = [s.sample_replay_level() for _ in range(20)]
+        picks += s.sample_replay_levels(20)
+        assert np.array_equal(np.array(picks) - 1, g['picks_' + tag])
+        assert np.array_equal(s.seed_staleness, g['stale_after_' + tag])
+
+
+SESSIONS = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, 'plr_session_*.pkl.gz')))
+
+
+@pytest.mark.parametrize('name', SESSIONS)
+def test_sampler_session_golden(name):
+    """Replays a whole PLR session (decisions, level insertion with dedupe, replay draws incl. the per-done
+    re-sampling inside the rollout, scoring, admission / eviction, reconciliation) recorded from the reference."""
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    from dcd_isaac_b200.level_store import LevelStore
+    with gzip.open(os.path.join(GOLDEN, name), 'rb') as f:
+        sess = pickle.load(f)
+    tag, strategy, buf, temp, sc, rp, rho, A, T = sess['case']
+    np.random.seed(77)
+    rs = np.random.RandomState(5)
+    s = LevelSampler([], None, None, num_actors=A, strategy=strategy, replay_schedule=sess['schedule'],
+                     score_transform=sess['transform'], temperature=temp, eps=0.05, rho=rho, replay_prob=rp, alpha=1.0,
+                     staleness_coef=sc, staleness_transform='power', staleness_temperature=1.0,
+                     sample_full_distribution=True, seed_buffer_size=buf, seed_buffer_priority='replay_support', gamma=0.995)
+    store = LevelStore(data_info={'numpy': True, 'dtype': np.uint8, 'shape': (15, 15, 3)})
+    next_level = 0
+    for cyc, rec in enumerate(sess['log']):
+        replay = s.sample_replay_decision()
+        assert replay == rec['replay'], cyc
+        assert np.random.get_state()[2] == rec['rng_after_decision']
+        if replay:
+            seeds = [s.sample_replay_level() for _ in range(A)]
+            assert np.array_equal(seeds, rec['sampled']), cyc
+            assert np.array_equal(s.seed_staleness, rec['staleness_after_sample'])
+            levels = store.get_levels_device(seeds)
+            assert levels.shape == (A, 15, 15, 3)
+            assert np.array_equal(levels[0].cpu().numpy(), store.get_level(seeds[0]))
+        else:
+            levels = []
+            for _ in range(A):  # same level generator as oracle/gen_golden_plr.py
+                enc = np.zeros((15, 15, 3), np.uint8)
+                enc[:, :, 0] = 1
+                enc[0, 0, 0] = 2
+                ident = next_level if rs.rand() > 0.15 or next_level == 0 else rs.randint(0, next_level)
+                enc[1 + ident % 13, 1 + (ident // 13) % 13, :] = (8, 1, 0)
+                enc[1 + (ident // 169) % 13, 13, :] = (2, 5, 0)
+                next_level += 1
+                levels.append(enc.tobytes())
+            seeds = store.insert(levels)
+            assert np.array_equal(seeds, rec['inserted']), cyc
+            s.observe_external_unseen_sample(seeds, solvable=[bool(x % 3) for x in seeds])
+        # consume the generator's RNG exactly as gen_golden_plr._storage does
+        done = rs.rand(T, A) < (1.0 / 10)
+        done[-1] = True
+        rs.rand(T, A); rs.randint(1, 250, size=(T, A)); rs.rand(A); rs.randn(T + 1, A, 1); rs.randn(T, A, 7)
+        if replay:
+            res = []
+            for t in range(T):
+                for i in range(A):
+                    if done[t, i]:
+                        res.append(s.sample_replay_level())
+            assert np.array_equal(res, rec['resampled']), cyc
+        rs.randn(A, 1)
+        s.update_with_rollouts(_rollouts_from(rec))
+        s.after_update()
+        store.reconcile_seeds(set(int(x) for x in s.seeds if x >= 0))
+        assert np.array_equal(s.seeds, rec['seeds']), cyc
+        assert np.array_equal(s.unseen_seed_weights, rec['unseen'])
+        assert np.allclose(s.seed_scores, rec['seed_scores'], rtol=RTOL, atol=1e-7), cyc
+        assert np.array_equal(s.seed_staleness, rec['seed_staleness'])
+        assert s.working_seed_buffer_size == rec['working_size']
+        assert sorted(s.staging_seed_set) == list(rec['staging'])
+        assert sorted(store.seed2level) == list(rec['store_seeds'])
+        assert s.running_sample_count == rec['running_sample_count']
+        if (s.unseen_seed_weights < 1).any():
+            assert np.allclose(s.sample_weights(), rec['weights'], rtol=RTOL, atol=1e-12), cyc
+            assert np.isclose(float(s.solvable_mass), rec['solvable_mass'], rtol=RTOL)
+        if 'grounded_values' in rec:
+            assert np.allclose(s.grounded_values, rec['grounded_values'], rtol=RTOL)
+        assert np.random.get_state()[2] == rec['rng_pos'], cyc
+    # the objects are checkpointed whole (adversarial_runner.py:214-215)
+    s2, store2 = pickle.loads(pickle.dumps((s, store)))
+    assert np.array_equal(s2.seed_scores, s.seed_scores) and sorted(store2.seed2level) == sorted(store.seed2level)
+    if (s2.unseen_seed_weights < 1).any():
+        assert np.allclose(s2.sample_weights(), s.sample_weights())
