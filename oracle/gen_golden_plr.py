@@ -15,7 +15,7 @@ import ref_harness as rh  # noqa: E402
 GOLDEN = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
 
 
-def _storage(T, N, rs, mean_len=12, handle_timelimits=True, dense_vals=True):
+def _storage(T, N, rs, mean_len=12, handle_timelimits=True, tie_free=False):
     """A reference RolloutStorage filled like adversarial_runner.agent_rollout fills it."""
     import numpy as np
     import torch
@@ -35,7 +35,11 @@ def _storage(T, N, rs, mean_len=12, handle_timelimits=True, dense_vals=True):
     if handle_timelimits:
         cliff[-1] = rs.rand(N) < 0.6  # not-done envs at the rollout end become cliffhangers (:521-528)
     st.cliffhanger_masks[1:].copy_(torch.from_numpy(1.0 - cliff.astype(np.float32)).unsqueeze(-1))
-    st.value_preds.copy_(torch.from_numpy(rs.randn(T + 1, N, 1).astype(np.float32) * 0.3 + 0.4))
+    noise = rs.randn(T + 1, N, 1).astype(np.float32)
+    # tie_free: every advantage is > 0, so no positive_value_loss score is exactly 0.  A seen level whose score ties
+    # with the (score 0) unseen slots gets an arbitrary rank in the reference (numpy's unstable argsort), which no
+    # re-implementation can reproduce; ties are covered separately (plr_weights.npz 'n100_ties').
+    st.value_preds.copy_(torch.from_numpy(noise * 0.001 - 1.0 if tie_free else noise * 0.3 + 0.4))
     st.action_log_dist.copy_(torch.from_numpy(rs.randn(T, N, 7).astype(np.float32)))
     return st, done
 
@@ -113,7 +117,7 @@ def gen_sampler():
                 rec['inserted'] = np.array(seeds, dtype=np.int64)
                 solv = [bool(s % 3) for s in seeds]
                 sampler.observe_external_unseen_sample(seeds, solvable=solv)
-            st, done = _storage(T, A, rs, mean_len=10)
+            st, done = _storage(T, A, rs, mean_len=10, tie_free=tag.startswith('pvl'))
             # level_seeds: current seed per actor, re-sampled on done when replaying (adversarial_runner.py:551-588)
             cur = list(seeds)
             ls = np.zeros((T, A), np.int32)
