@@ -30,7 +30,7 @@ struct Cfg {
 struct Dev {
   int N;
   Cfg c;
-  uint32_t *wall;    // [W][N] wall bit-plane rows (bit x of row y)
+  uint32_t *wall;    // [ceil(N/32)][W][32] wall bit-plane rows (bit x of row y), tile-major: see env_rows()
   uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx5|gy5|hasgoal1|sx5|sy5|hasstart1|sdir2|pending8  z: elapsed16|eplen16  w: ep_ret bits
   uint32_t *adv;     // [N] adversary_step_count12 | adversary_max_steps12 | n_clutter_sampled1
   int4 *metrics;     // [N] n_clutter_placed, distance_to_goal, passable, shortest_path_length
@@ -78,7 +78,9 @@ __device__ __forceinline__ uint4 pack(const Env &e) {
   return h;
 }
 
-// Wall rows of one env: shared memory (stride = tile size) in the hot kernels, HBM (stride = N) elsewhere.
+// Wall rows of one env.  In HBM the bit-plane is tile-major: the W rows of 32 consecutive envs form one contiguous
+// W*128-byte block (row y of env e at wall[((e/32)*W + y)*32 + e%32]), so a warp's tile is ONE bulk copy and a
+// shared-memory image of it is addressed with the same stride (bank index = lane).
 struct Rows {
   uint32_t *p;
   int stride;
@@ -86,42 +88,109 @@ struct Rows {
   __device__ __forceinline__ void set(int r, uint32_t v) const { p[r * stride] = v; }
 };
 
+__device__ __forceinline__ Rows env_rows(const Dev &d, int e) {
+  return Rows{d.wall + ((size_t)(e >> 5) * d.c.W) * 32 + (e & 31), 32};
+}
+
 // ---------------------------------------------------------------------------------------------
 // numpy legacy RandomState == MT19937, generated incrementally: word i of the next generation is
 // x[i+397] ^ twist(x[i], x[i+1]) and only depends on already-updated words when produced in order, so
-// producing one word per draw in place is output-identical to the batch twist and never stalls a
-// lane for 624 dependent iterations.
+// producing words in place, in order, is output-identical to the batch twist and never stalls a lane for 624
+// dependent iterations.
+// Draws are generated SPECULATIVELY IN BATCHES: the words at offsets 0..K-1 from the cursor are mutually
+// independent for K <= 227 (word j reads state[j], state[j+1], state[j+397], none of which is produced inside the
+// batch), so one refill issues ~2K independent loads (one memory round trip instead of one per draw), keeps the
+// tempered outputs and the new state words in thread-local arrays, and store() commits exactly the words that
+// were consumed.  Unconsumed words are simply regenerated by the next refill -- the stream is unchanged.
 struct Rng {
+  static constexpr int kCap = 64;
   uint32_t *mt, *mti_p, *words_p;
   int N, e;
-  uint32_t idx, used;
+  uint32_t idx, used;      // cursor (0..623) and words consumed since seeding, as of the last commit
+  int have, pos, hint;     // batch size, next unread word, size of the next refill
   bool loaded;
-  __device__ Rng(const Dev &dev, int env)
-      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), loaded(false) {}
-  __device__ Rng(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env)
-      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), loaded(false) {}
+  uint32_t out[kCap], nst[kCap];
+  __device__ Rng(const Dev &dev, int env, int hint_ = 8)
+      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), have(0), pos(0),
+        hint(hint_), loaded(false) {}
+  __device__ Rng(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env, int hint_ = 8)
+      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), have(0), pos(0), hint(hint_),
+        loaded(false) {}
   __device__ __forceinline__ void load() {
     if (!loaded) { idx = mti_p[e]; used = words_p[e]; loaded = true; }
   }
-  __device__ __forceinline__ void store() {
-    if (loaded) { mti_p[e] = idx; words_p[e] = used; }
+  // write back the state words of the draws consumed so far and advance the cursor
+  __device__ void commit() {
+    for (int j = 0; j < pos; j++) {
+      uint32_t i = idx + j;
+      if (i >= 624) i -= 624;
+      mt[(size_t)i * N + e] = nst[j];
+    }
+    idx += pos;
+    if (idx >= 624) idx -= 624;
+    used += pos;
+    have = 0; pos = 0;
   }
-  __device__ uint32_t next() {
+  __device__ void refill() {
     load();
-    const uint32_t i = idx;
-    const uint32_t i1 = (i + 1 == 624) ? 0 : i + 1;
-    const uint32_t im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
-    const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
-    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-    y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    mt[(size_t)i * N + e] = y;
-    idx = i1;
-    used++;
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
+    commit();
+    int k = hint < kCap ? hint : kCap;
+    k = (k + 7) & ~7;
+    hint = kCap;  // a caller that came back for more gets a full batch
+    // phase 1: all loads of the batch, in groups of independent loads that share one memory round trip
+    int j0 = 0;
+    for (; j0 + 32 <= k; j0 += 32) {
+      uint32_t tb[32], tc[32];
+#pragma unroll
+      for (int u = 0; u < 32; u++) {
+        uint32_t i1 = idx + j0 + u + 1, im = idx + j0 + u + 397;
+        if (i1 >= 624) i1 -= 624;
+        if (im >= 624) im -= 624;
+        if (im >= 624) im -= 624;
+        tb[u] = mt[(size_t)i1 * N + e];
+        tc[u] = mt[(size_t)im * N + e];
+      }
+#pragma unroll
+      for (int u = 0; u < 32; u++) { out[j0 + u] = tb[u]; nst[j0 + u] = tc[u]; }
+    }
+    for (; j0 < k; j0 += 8) {
+      uint32_t tb[8], tc[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        uint32_t i1 = idx + j0 + u + 1, im = idx + j0 + u + 397;
+        if (i1 >= 624) i1 -= 624;
+        if (im >= 624) im -= 624;
+        if (im >= 624) im -= 624;
+        tb[u] = mt[(size_t)i1 * N + e];
+        tc[u] = mt[(size_t)im * N + e];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { out[j0 + u] = tb[u]; nst[j0 + u] = tc[u]; }
+    }
+    // phase 2: twist + temper in place (out[j] holds state[j+1], nst[j] holds state[j+397])
+    uint32_t a = mt[(size_t)idx * N + e];
+    for (int j = 0; j < k; j++) {
+      const uint32_t b = out[j], c = nst[j];
+      uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      nst[j] = y;
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      out[j] = y;
+      a = b;
+    }
+    have = k;
+  }
+  __device__ __forceinline__ void store() {
+    if (loaded) { commit(); mti_p[e] = idx; words_p[e] = used; }
+  }
+  // forget everything (after a re-seed replaced the stream)
+  __device__ __forceinline__ void reset() { loaded = false; have = 0; pos = 0; }
+  __device__ __forceinline__ uint32_t next() {
+    if (pos >= have) refill();
+    return out[pos++];
   }
   // RandomState.randint(lo, hi): masked rejection on 32-bit words, no draw when hi-lo == 1
   // (gym_minigrid MiniGridEnv._rand_int; call sites multigrid.py:603-606, adversarial.py:205,567).
@@ -207,6 +276,34 @@ __device__ __forceinline__ void flush_pending(const Rows &R, Env &e, Rng &rng, i
   if (e.pending) { replay_respawns(R, e.gx, e.gy, rng, W, e.pending); e.pending = 0; }
 }
 
+// Bit-parallel flood fill with the frontier rows held in registers (ROWS is a compile-time bound >= W, all loops
+// fully unrolled so every array index is a constant).  Synchronous update: row y of step d+1 is computed from
+// rows y-1, y, y+1 of step d (the old row y-1 is carried in `up`).  Returns the hop count to (gx,gy) or -1.
+template <int ROWS>
+__device__ __forceinline__ int flood_fill(const Rows &R, int W, int sx, int sy, int gx, int gy, uint32_t interior, int max_d) {
+  uint32_t reach[ROWS], fr[ROWS];
+#pragma unroll
+  for (int y = 0; y < ROWS; y++) {
+    fr[y] = (y >= 1 && y < W - 1) ? (~R.get(y) & interior) : 0u;
+    reach[y] = (y == sy) ? (1u << sx) : 0u;
+  }
+  for (int d = 1; d <= max_d; d++) {
+    uint32_t up = 0, changed = 0, hit = 0;
+#pragma unroll
+    for (int y = 1; y < ROWS - 1; y++) {
+      const uint32_t r = reach[y];
+      const uint32_t v = (r | (r << 1) | (r >> 1) | up | reach[y + 1]) & fr[y];
+      up = r;
+      reach[y] = v;
+      changed |= v ^ r;
+      hit |= (y == gy) ? ((v >> gx) & 1u) : 0u;
+    }
+    if (hit) return d;
+    if (!changed) return -1;
+  }
+  return -1;
+}
+
 // reset_metrics + compute_metrics (adversarial.py:184-192,407-447): interior wall count, Manhattan
 // distance, and reachability / hop count by a bit-parallel flood fill over the interior rows.
 __device__ __noinline__ int4 compute_metrics(const Rows &R, const Env &e, int W, bool do_reset) {
@@ -219,23 +316,10 @@ __device__ __noinline__ int4 compute_metrics(const Rows &R, const Env &e, int W,
   (void)do_reset;
   if (e.sx == kNone || e.gx == kNone) return m;
   m.y = abs(e.gx - e.sx) + abs(e.gy - e.sy);
-  uint32_t reach[32], nxt[32];
-  for (int y = 0; y < W; y++) reach[y] = 0;
-  reach[e.sy] = 1u << e.sx;
-  m.z = 0;
   if (e.sx == e.gx && e.sy == e.gy) { m.z = 1; m.w = 0; return m; }
-  for (int d = 1; d <= unreachable; d++) {
-    bool grew = false;
-    for (int y = 1; y < W - 1; y++) {
-      const uint32_t r = reach[y];
-      uint32_t v = (r | (r << 1) | (r >> 1) | reach[y - 1] | reach[y + 1]) & ~R.get(y) & interior;
-      nxt[y] = v;
-      grew |= (v != r);
-    }
-    for (int y = 1; y < W - 1; y++) reach[y] = nxt[y];
-    if ((reach[e.gy] >> e.gx) & 1u) { m.z = 1; m.w = d; return m; }
-    if (!grew) break;
-  }
+  const int d = (W <= 16) ? flood_fill<16>(R, W, e.sx, e.sy, e.gx, e.gy, interior, unreachable)
+                          : flood_fill<32>(R, W, e.sx, e.sy, e.gx, e.gy, interior, unreachable);
+  if (d >= 0) { m.z = 1; m.w = d; } else { m.z = 0; }
   return m;
 }
 
@@ -307,7 +391,7 @@ __device__ __noinline__ void reset_random(const Rows &R, Env &e, uint32_t &adv, 
   flush_pending(R, e, rng, W);
   if (c.fixed_env) {  // self.seed(self.seed_value) (adversarial.py:542-543)
     mt_seed(d, env, d.limbs[env], d.limbs[(size_t)d.N + env], (int)d.limbs[2 * (size_t)d.N + env]);
-    rng.loaded = false;
+    rng.reset();
   }
   e.step_count = 0;
   uint32_t adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;

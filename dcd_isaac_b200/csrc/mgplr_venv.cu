@@ -78,7 +78,7 @@ __device__ __noinline__ void emit_direct(const Rows &R, const Env &e, const Cfg 
 __global__ void k_init(Dev d) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   gen_grid(R, d.c.W);
   Env s{};
   s.gx = s.gy = s.sx = s.sy = kNone;
@@ -106,7 +106,7 @@ __global__ void k_seed(Dev d, const uint32_t *scratch, int n, int stride, int ha
 __global__ void k_reset(Dev d) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e];
   int4 met;
@@ -119,7 +119,7 @@ __global__ void k_reset(Dev d) {
 __global__ void k_step_adversary(Dev d, const int64_t *loc, uint8_t *done) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e], err = 0;
   int4 met = d.metrics[e];
@@ -143,7 +143,7 @@ __global__ void k_adv_image(Dev d, float *image, float *time_step) {
   const Env s = unpack(d.hot[e]);
   float t, c, st = 0.f;
   if (s.has_agent && x == s.ax && y == s.ay) { t = 1.0f; c = 0.0f; st = s.adir == 0 ? 0.0f : s.adir == 1 ? 0.1f : s.adir == 2 ? 0.2f : 0.3f; }
-  else if ((d.wall[(size_t)y * d.N + e] >> x) & 1u) { t = 0.2f; c = 0.5f; }
+  else if ((env_rows(d, e).get(y) >> x) & 1u) { t = 0.2f; c = 0.5f; }
   else if (x == s.gx && y == s.gy) { t = 0.8f; c = 0.1f; }
   else { t = 0.1f; c = 0.0f; }
   float *o = image + (size_t)e * 3 * WW + cell;
@@ -154,7 +154,7 @@ __global__ void k_adv_image(Dev d, float *image, float *time_step) {
 __global__ void k_reset_agent(Dev d, OutPtrs o) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   if (s.pending) {  // replay the deferred respawn draws of the last rollout (level unchanged since)
     Rng rng(d, e);
@@ -170,11 +170,11 @@ __global__ void k_reset_agent(Dev d, OutPtrs o) {
 __global__ void k_reset_random(Dev d, const int32_t *n_walls, OutPtrs o) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
-  Rng rng(d, e);
+  Rng rng(d, e, Rng::kCap);
   const int nw = (d.c.resample && n_walls) ? n_walls[e] : -1;
   reset_random(R, s, adv, met, rng, d, e, nw, err);
   rng.store();
@@ -192,7 +192,7 @@ __global__ void k_reset_to_encoding(Dev d, const uint8_t *enc, const int32_t *in
   const int e = index ? index[k] : k;
   if (e < 0 || e >= d.N) return;
   const int W = d.c.W;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e];
   int4 met;
@@ -224,7 +224,7 @@ __global__ void k_reset_to_actions(Dev d, const int32_t *locs, int len, const in
   if (k >= n) return;
   const int e = index ? index[k] : k;
   if (e < 0 || e >= d.N) return;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
@@ -258,7 +258,7 @@ __global__ void k_mutate_edits(Dev d, const int32_t *locs, const int32_t *ops, c
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   const int W = d.c.W, I = W - 2;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   if (s.pending) { Rng rng(d, e); flush_pending(R, s, rng, W); rng.store(); }
   const int k = n_edits[e];
@@ -288,7 +288,7 @@ __global__ void k_mutate_finalize(Dev d, const int32_t *choice, OutPtrs o) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   const int W = d.c.W, I = W - 2;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   int sel;
   if (s.gx == kNone) {
@@ -316,7 +316,7 @@ __global__ void k_encode(Dev d, uint8_t *enc) {
   const Env s = unpack(d.hot[e]);
   uint8_t t, c, st = 0;
   if (s.has_agent && x == s.ax && y == s.ay) { t = 10; c = 0; st = (uint8_t)s.adir; }
-  else if ((d.wall[(size_t)y * d.N + e] >> x) & 1u) { t = 2; c = 5; }
+  else if ((env_rows(d, e).get(y) >> x) & 1u) { t = 2; c = 5; }
   else if (x == s.gx && y == s.gy) { t = 8; c = 1; }
   else { t = 1; c = 0; }
   uint8_t *o = enc + idx * 3;
@@ -329,7 +329,7 @@ __global__ void k_flush(Dev d) {
   if (e >= d.N) return;
   Env s = unpack(d.hot[e]);
   if (!s.pending) return;
-  Rows R{d.wall + e, d.N};
+  const Rows R = env_rows(d, e);
   Rng rng(d, e);
   flush_pending(R, s, rng, d.c.W);
   rng.store();
@@ -393,7 +393,7 @@ __device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int strid
   Env s = unpack(hot);
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
-  Rng rng(d, e);
+  Rng rng(d, e, Rng::kCap);
   reset_random(Rows{rows, stride}, s, adv, met, rng, d, e, n_walls, err);
   rng.store();
   d.adv[e] = adv; d.metrics[e] = met;
@@ -470,6 +470,8 @@ __device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, con
   if (o.cliffhanger_masks) o.cliffhanger_masks[e] = cliff ? 0.f : 1.f;
 }
 
+constexpr int kWarpTile = 32;  // envs per warp tile = lanes
+
 // ---- TMA bulk copies + mbarrier (PTX; SASS: UBLKCP / SYNCS) ----
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -500,26 +502,26 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // wait until the bulk stores have finished READING shared memory (the global writes complete before the grid does)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// Stage the wall rows of envs [base, base+n_tile) into s_rows[r*TILE + i]: W bulk copies of TILE*4 bytes when the
-// tile is full and 16-byte aligned (one elected thread, completion on `bar`), plain coalesced loads otherwise.
+// Stage the wall rows of the CTA's TILE/32 warp-tiles into s_rows[sub][W][32]: one bulk copy of W*128 bytes per
+// sub-tile (one elected thread, completion on `bar`).  The HBM plane is padded to whole tiles, so partial tiles
+// take the same path.
 template <int TILE>
-__device__ __forceinline__ bool stage_rows_begin(const Dev &d, uint32_t *s_rows, uint64_t *bar, int base, int n_tile) {
+__device__ __forceinline__ void stage_rows_begin(const Dev &d, uint32_t *s_rows, uint64_t *bar, int base) {
   const int W = d.c.W;
-  const bool bulk = (n_tile == TILE) && ((d.N & 3) == 0);
-  if (bulk) {
-    if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
-      fence_proxy_async_smem();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, (uint32_t)(W * TILE * 4));
-      for (int r = 0; r < W; r++) bulk_load(s_rows + r * TILE, d.wall + (size_t)r * d.N + base, TILE * 4, bar);
-    }
-  } else if ((int)threadIdx.x < n_tile) {
-    for (int r = 0; r < W; r++) s_rows[r * TILE + threadIdx.x] = d.wall[(size_t)r * d.N + base + threadIdx.x];
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async_smem();
   }
-  return bulk;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)(W * kWarpTile * 4);
+    const int n_tiles = (d.N + kWarpTile - 1) / kWarpTile;
+    int subs = 0;
+    for (int sub = 0; sub < TILE / kWarpTile; sub++) subs += ((base / kWarpTile + sub) < n_tiles);
+    mbar_expect_tx(bar, bytes * subs);
+    for (int sub = 0; sub < subs; sub++)
+      bulk_load(s_rows + sub * W * kWarpTile, d.wall + ((size_t)(base / kWarpTile + sub)) * W * kWarpTile, bytes, bar);
+  }
 }
 
 // Store the CTA's observation tile: n_envs*75 contiguous floats starting at gdst.  All threads must call.
@@ -548,7 +550,6 @@ __device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, 
 //   * the 32x75 float32 observations of tile k leave shared memory as one 9600-byte bulk asynchronous store
 //     that drains while tile k+1 steps and renders; the single obs buffer is only re-acquired
 //     (cp.async.bulk.wait_group.read) right before tile k+1 emits.
-constexpr int kWarpTile = 32;
 __host__ __device__ inline size_t warp_smem_bytes(int W) {
   return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + 127) & ~(size_t)127;
 }
@@ -560,16 +561,12 @@ __device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot,
   emit_obs_u8(v, image_u8 + (size_t)e * kObsFloats);
 }
 
-// rows of one 32-env tile -> shared memory: bulk copies onto `bar` when the tile is full and aligned
-__device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, uint64_t *bar, int base, bool bulk, int lane) {
-  const int W = d.c.W;
-  if (bulk) {
-    if (lane == 0) {
-      mbar_expect_tx(bar, (uint32_t)(W * kWarpTile * 4));
-      for (int r = 0; r < W; r++) bulk_load(s_rows + r * kWarpTile, d.wall + (size_t)r * d.N + base, kWarpTile * 4, bar);
-    }
-  } else if (base + lane < d.N) {
-    for (int r = 0; r < W; r++) s_rows[r * kWarpTile + lane] = d.wall[(size_t)r * d.N + base + lane];
+// rows of one 32-env tile -> shared memory: ONE bulk asynchronous copy of W*128 bytes completing on `bar`
+__device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, uint64_t *bar, int tile, int lane) {
+  if (lane == 0) {
+    const uint32_t bytes = (uint32_t)(d.c.W * kWarpTile * 4);
+    mbar_expect_tx(bar, bytes);
+    bulk_load(s_rows, d.wall + (size_t)tile * d.c.W * kWarpTile, bytes, bar);
   }
 }
 
@@ -585,12 +582,10 @@ __global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles
   const int total = gridDim.x * wpc;
   int tile = blockIdx.x * wpc + warp;
   if (tile >= n_tiles) return;
-  const bool aligned = (N & 3) == 0;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
   __syncwarp();
   // prologue: first tile's rows and scalars
-  bool cur_bulk = aligned && (tile + 1) * kWarpTile <= N;
-  warp_issue_rows(d, s_rows, &bars[0], tile * kWarpTile, cur_bulk, lane);
+  warp_issue_rows(d, s_rows, &bars[0], tile, lane);
   uint4 nh = make_uint4(0, 0, 0, 0);
   int na = 6;
   if (tile * kWarpTile + lane < N) { nh = d.hot[tile * kWarpTile + lane]; na = (int)A.action[tile * kWarpTile + lane]; }
@@ -605,14 +600,12 @@ __global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles
     // prefetch tile k+1 into the other stage (its last readers, tile k-1, are done: __syncwarp)
     const int next = tile + total;
     __syncwarp();
-    bool next_bulk = false;
     if (next < n_tiles) {
-      next_bulk = aligned && (next + 1) * kWarpTile <= N;
-      warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next * kWarpTile, next_bulk, lane);
+      warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane);
       if (next * kWarpTile + lane < N) { nh = d.hot[next * kWarpTile + lane]; na = (int)A.action[next * kWarpTile + lane]; }
     }
-    if (cur_bulk) { mbar_wait(&bars[st], (phase >> st) & 1u); phase ^= 1u << st; }
-    cur_bulk = next_bulk;
+    mbar_wait(&bars[st], (phase >> st) & 1u);
+    phase ^= 1u << st;
 
     Env s = unpack(h);
     const Cfg &c = d.c;
@@ -670,7 +663,7 @@ __global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles
     emit_obs_f32_fast<SEE>(v, s_obs + lane * kObsFloats);
     if (A.o.image) {
       float *gdst = A.o.image + (size_t)base * kObsFloats;
-      if (aligned && n_tile == kWarpTile) {
+      if (n_tile == kWarpTile && (((uintptr_t)gdst) & 15u) == 0) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) { bulk_store(gdst, s_obs, kWarpTile * kObsFloats * 4); bulk_commit(); }
@@ -684,8 +677,10 @@ __global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles
       d.hot[e] = pack(s);
       write_step_scalars(A, e, s, flags, (float)rew);
       if (A.o.image_u8) rare_emit_u8(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.image_u8, e);
-      if (RR && dirty)
-        for (int r = 0; r < W; r++) d.wall[(size_t)r * N + e] = rows[r * kWarpTile + lane];
+      if (RR && dirty) {
+        const Rows G = env_rows(d, e);
+        for (int r = 0; r < W; r++) G.set(r, rows[r * kWarpTile + lane]);
+      }
     }
   }
   if (lane == 0) bulk_wait_read0();
@@ -703,11 +698,11 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
   const int tid = threadIdx.x, base = blockIdx.x * TILE, e = base + tid, W = d.c.W, N = d.N;
   const int n_tile = min(TILE, N - base);
   const bool valid = tid < n_tile;
-  const bool bulk = stage_rows_begin<TILE>(d, s_rows, &bar, base, n_tile);
+  stage_rows_begin<TILE>(d, s_rows, &bar, base);
   Env s{};
   if (valid) s = unpack(d.hot[e]);
-  if (bulk) mbar_wait(&bar, 0);
-  else __syncthreads();
+  mbar_wait(&bar, 0);
+  uint32_t *my_rows = s_rows + (tid >> 5) * W * kWarpTile + (tid & 31);  // [sub][W][32]
   bool dirty = false;
   for (int t = 0; t < T; t++) {
     StepArgs A = A0;
@@ -731,7 +726,7 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
     __syncthreads();
     if (valid) {
       float rew;
-      const uint32_t flags = step_one<SEE, RR, EXT>(d, s_rows + tid, TILE, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats,
+      const uint32_t flags = step_one<SEE, RR, EXT>(d, my_rows, kWarpTile, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats,
                                                     rew, dirty);
       write_step_scalars(A, e, s, flags, rew);
     }
@@ -740,8 +735,10 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
   if (tid == 0) bulk_wait_read0();
   if (valid) {
     d.hot[e] = pack(s);
-    if (RR && dirty)
-      for (int r = 0; r < W; r++) d.wall[(size_t)r * N + e] = s_rows[r * TILE + tid];
+    if (RR && dirty) {
+      const Rows G = env_rows(d, e);
+      for (int r = 0; r < W; r++) G.set(r, my_rows[r * kWarpTile]);
+    }
   }
 }
 
@@ -787,7 +784,9 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
             cfg->resample_n_clutter != 0, cfg->choose_goal_last != 0, cfg->fixed_environment != 0, cfg->n_editor_actions};
   const size_t N = (size_t)num_envs;
   int64_t total = 0;
-  CK(dalloc(&d.wall, (size_t)cfg->width * N, total));
+  const size_t wall_words = (size_t)cfg->width * 32 * ((N + 31) / 32);  // padded to whole 32-env tiles
+  CK(dalloc(&d.wall, wall_words, total));
+  CK(cudaMemset(d.wall, 0, wall_words * sizeof(uint32_t)));
   CK(dalloc(&d.hot, N, total));
   CK(dalloc(&d.adv, N, total));
   CK(dalloc(&d.metrics, N, total));
