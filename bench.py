@@ -226,7 +226,7 @@ def run_ours(a):
                                          T, N, 0, ptr(episodes), max_eps, ptr(n_eps), st))
         if world > 1:
             dist.all_gather_into_tensor(gathered, episodes)
-        launches[0] += 1 + T + 1 + 3
+        launches[0] += 1 + T + 1 + 4
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -253,7 +253,7 @@ def run_ours(a):
             run_roll()
         sync_all()
     else:
-        per_roll = 1 + T + 1 + 3
+        per_roll = 1 + T + 1 + 4
         run_roll, run_steps = rollout, env_steps
     sampler = ClockSampler(local)
     if rank == 0:

@@ -97,104 +97,74 @@ __device__ __forceinline__ Rows env_rows(const Dev &d, int e) {
 // x[i+397] ^ twist(x[i], x[i+1]) and only depends on already-updated words when produced in order, so
 // producing words in place, in order, is output-identical to the batch twist and never stalls a lane for 624
 // dependent iterations.
-// Draws are generated SPECULATIVELY IN BATCHES: the words at offsets 0..K-1 from the cursor are mutually
-// independent for K <= 227 (word j reads state[j], state[j+1], state[j+397], none of which is produced inside the
-// batch), so one refill issues ~2K independent loads (one memory round trip instead of one per draw), keeps the
-// tempered outputs and the new state words in thread-local arrays, and store() commits exactly the words that
-// were consumed.  Unconsumed words are simply regenerated by the next refill -- the stream is unchanged.
+// Draws are generated SPECULATIVELY IN BATCHES of 16: the words at offsets 0..15 from the cursor are mutually
+// independent (word j reads state[j], state[j+1], state[j+397]; none is produced inside a batch shorter than
+// 227), so one refill issues 33 independent loads -- one memory round trip instead of one per draw -- and keeps
+// the tempered outputs and the new state words in REGISTERS (two 16-deep shift registers; every index is a
+// compile-time constant, so nothing lives in local memory as long as the users are inlined into their
+// out-of-line rare path).  A state word is written back when its draw is consumed; unconsumed words are simply
+// regenerated by the next refill, so the stream is exactly numpy's.
 struct Rng {
-  static constexpr int kCap = 64;
+  static constexpr int kBatch = 16;
   uint32_t *mt, *mti_p, *words_p;
   int N, e;
-  uint32_t idx, used;      // cursor (0..623) and words consumed since seeding, as of the last commit
-  int have, pos, hint;     // batch size, next unread word, size of the next refill
+  uint32_t idx, used;  // cursor (0..623), words consumed since seeding
+  int have;            // unread words in the shift registers
   bool loaded;
-  uint32_t out[kCap], nst[kCap];
-  __device__ Rng(const Dev &dev, int env, int hint_ = 8)
-      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), have(0), pos(0),
-        hint(hint_), loaded(false) {}
-  __device__ Rng(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env, int hint_ = 8)
-      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), have(0), pos(0), hint(hint_),
-        loaded(false) {}
+  uint32_t out[kBatch], nst[kBatch];
+  __device__ __forceinline__ Rng(const Dev &dev, int env)
+      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), have(0), loaded(false) {}
+  __device__ __forceinline__ Rng(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env)
+      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), have(0), loaded(false) {}
   __device__ __forceinline__ void load() {
     if (!loaded) { idx = mti_p[e]; used = words_p[e]; loaded = true; }
   }
-  // write back the state words of the draws consumed so far and advance the cursor
-  __device__ void commit() {
-    for (int j = 0; j < pos; j++) {
-      uint32_t i = idx + j;
-      if (i >= 624) i -= 624;
-      mt[(size_t)i * N + e] = nst[j];
-    }
-    idx += pos;
-    if (idx >= 624) idx -= 624;
-    used += pos;
-    have = 0; pos = 0;
-  }
-  __device__ void refill() {
+  __device__ __forceinline__ void refill() {
     load();
-    commit();
-    int k = hint < kCap ? hint : kCap;
-    k = (k + 7) & ~7;
-    hint = kCap;  // a caller that came back for more gets a full batch
-    // phase 1: all loads of the batch, in groups of independent loads that share one memory round trip
-    int j0 = 0;
-    for (; j0 + 32 <= k; j0 += 32) {
-      uint32_t tb[32], tc[32];
-#pragma unroll
-      for (int u = 0; u < 32; u++) {
-        uint32_t i1 = idx + j0 + u + 1, im = idx + j0 + u + 397;
-        if (i1 >= 624) i1 -= 624;
-        if (im >= 624) im -= 624;
-        if (im >= 624) im -= 624;
-        tb[u] = mt[(size_t)i1 * N + e];
-        tc[u] = mt[(size_t)im * N + e];
-      }
-#pragma unroll
-      for (int u = 0; u < 32; u++) { out[j0 + u] = tb[u]; nst[j0 + u] = tc[u]; }
-    }
-    for (; j0 < k; j0 += 8) {
-      uint32_t tb[8], tc[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        uint32_t i1 = idx + j0 + u + 1, im = idx + j0 + u + 397;
-        if (i1 >= 624) i1 -= 624;
-        if (im >= 624) im -= 624;
-        if (im >= 624) im -= 624;
-        tb[u] = mt[(size_t)i1 * N + e];
-        tc[u] = mt[(size_t)im * N + e];
-      }
-#pragma unroll
-      for (int u = 0; u < 8; u++) { out[j0 + u] = tb[u]; nst[j0 + u] = tc[u]; }
-    }
-    // phase 2: twist + temper in place (out[j] holds state[j+1], nst[j] holds state[j+397])
+    uint32_t b[kBatch], c[kBatch];
     uint32_t a = mt[(size_t)idx * N + e];
-    for (int j = 0; j < k; j++) {
-      const uint32_t b = out[j], c = nst[j];
-      uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-      y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      nst[j] = y;
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      uint32_t i1 = idx + u + 1, im = idx + u + 397;
+      if (i1 >= 624) i1 -= 624;
+      if (im >= 624) im -= 624;
+      if (im >= 624) im -= 624;
+      b[u] = mt[(size_t)i1 * N + e];
+      c[u] = mt[(size_t)im * N + e];
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      uint32_t y = (a & 0x80000000u) | (b[u] & 0x7fffffffu);
+      y = c[u] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      nst[u] = y;
       y ^= (y >> 11);
       y ^= (y << 7) & 0x9d2c5680u;
       y ^= (y << 15) & 0xefc60000u;
       y ^= (y >> 18);
-      out[j] = y;
-      a = b;
+      out[u] = y;
+      a = b[u];
     }
-    have = k;
+    have = kBatch;
   }
   __device__ __forceinline__ void store() {
-    if (loaded) { commit(); mti_p[e] = idx; words_p[e] = used; }
+    if (loaded) { mti_p[e] = idx; words_p[e] = used; }
   }
   // forget everything (after a re-seed replaced the stream)
-  __device__ __forceinline__ void reset() { loaded = false; have = 0; pos = 0; }
+  __device__ __forceinline__ void reset() { loaded = false; have = 0; }
   __device__ __forceinline__ uint32_t next() {
-    if (pos >= have) refill();
-    return out[pos++];
+    if (have == 0) refill();
+    const uint32_t v = out[0];
+    mt[(size_t)idx * N + e] = nst[0];  // commit this word's new state
+    idx = (idx + 1 == 624) ? 0 : idx + 1;
+    used++;
+    have--;
+#pragma unroll
+    for (int u = 0; u + 1 < kBatch; u++) { out[u] = out[u + 1]; nst[u] = nst[u + 1]; }
+    return v;
   }
   // RandomState.randint(lo, hi): masked rejection on 32-bit words, no draw when hi-lo == 1
   // (gym_minigrid MiniGridEnv._rand_int; call sites multigrid.py:603-606, adversarial.py:205,567).
-  __device__ int randint(int lo, int hi) {
+  __device__ __forceinline__ int randint(int lo, int hi) {
     const uint32_t rng = (uint32_t)(hi - lo - 1);
     if (rng == 0) return lo;
     const uint32_t mask = 0xffffffffu >> __clz(rng);
@@ -251,7 +221,7 @@ __device__ inline void gen_grid(const Rows &R, int W) {
 
 // place_obj over the whole grid (multigrid.py:565-632): x=_rand_int(0,W), y=_rand_int(0,H); reject
 // non-empty cells; raise after max_tries (max_tries < 0: unbounded).
-__device__ __noinline__ bool place_random(const Rows &R, const Env &e, Rng &rng, int W, int max_tries, int &ox, int &oy) {
+__device__ __forceinline__ bool place_random(const Rows &R, const Env &e, Rng &rng, int W, int max_tries, int &ox, int &oy) {
   int tries = 0;
   for (;;) {
     if (max_tries >= 0 && tries > max_tries) return false;
@@ -265,7 +235,7 @@ __device__ __noinline__ bool place_random(const Rows &R, const Env &e, Rng &rng,
 
 // Replay `count` deferred goal respawns (place_one_agent over the whole grid with the agent off the grid).
 // Returns the last position as x | y<<8.
-__device__ __noinline__ uint32_t replay_respawns(const Rows &R, int gx, int gy, Rng &rng, int W, int count) {
+__device__ __forceinline__ uint32_t replay_respawns(const Rows &R, int gx, int gy, Rng &rng, int W, int count) {
   Env t{};
   t.gx = gx; t.gy = gy; t.has_agent = 0;
   int px = 0, py = 0;
@@ -333,7 +303,7 @@ __device__ __forceinline__ bool reset_agent(Env &e) {
 }
 
 // AdversarialEnv.reset (adversarial.py:194-229).
-__device__ inline void reset_adversary(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Cfg &c) {
+__device__ __forceinline__ void reset_adversary(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Cfg &c) {
   flush_pending(R, e, rng, c.W);
   e.step_count = 0;
   uint32_t adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
@@ -347,7 +317,7 @@ __device__ inline void reset_adversary(const Rows &R, Env &e, uint32_t &adv, int
 }
 
 // step_adversary (adversarial.py:452-539), goal_noise == 0.  Returns done.
-__device__ inline bool step_adversary(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Cfg &c, int loc,
+__device__ __forceinline__ bool step_adversary(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Cfg &c, int loc,
                                       uint32_t &err) {
   const int W = c.W, I = W - 2, A = I * I;
   if (loc < 0 || loc >= A) { err |= kErrBadLoc; return false; }
@@ -384,7 +354,7 @@ __device__ inline bool step_adversary(const Rows &R, Env &e, uint32_t &adv, int4
 }
 
 // reset_random (adversarial.py:541-581).  n_walls < 0 -> int(n_clutter/2).
-__device__ __noinline__ void reset_random(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Dev &d, int env,
+__device__ __forceinline__ void reset_random(const Rows &R, Env &e, uint32_t &adv, int4 &met, Rng &rng, const Dev &d, int env,
                                     int n_walls, uint32_t &err) {
   const Cfg &c = d.c;
   const int W = c.W;

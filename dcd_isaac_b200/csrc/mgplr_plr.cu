@@ -61,47 +61,67 @@ __global__ void k_count_episodes(const float *__restrict__ masks, int T, int N, 
   counts[e] = c;
 }
 
-// single-CTA exclusive scan over actors (canonical actor-major record order)
-__global__ void k_scan_counts(const int32_t *__restrict__ counts, int N, int32_t *__restrict__ offsets, int32_t *__restrict__ total) {
+// Exclusive scan of the per-actor episode counts (canonical actor-major record order), two levels:
+// k_scan_blocks scans 1024 counts per CTA and emits the CTA total, k_scan_tops scans the CTA totals in one CTA;
+// consumers add block_off[actor / 1024].
+__device__ __forceinline__ int32_t block_exclusive_scan_1024(int32_t v, int32_t *warp_sums, int32_t &total) {
+  int32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int32_t w = warp_sums[threadIdx.x];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (threadIdx.x >= o) w += y;
+    }
+    warp_sums[threadIdx.x] = w;
+  }
+  __syncthreads();
+  const int32_t warp_prefix = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+  total = warp_sums[31];
+  return warp_prefix + x - v;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocks(const int32_t *__restrict__ counts, int N, int32_t *__restrict__ offsets,
+                                                      int32_t *__restrict__ block_sums) {
+  __shared__ int32_t warp_sums[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  int32_t total;
+  const int32_t ex = block_exclusive_scan_1024((i < N) ? counts[i] : 0, warp_sums, total);
+  if (i < N) offsets[i] = ex;
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tops(int32_t *__restrict__ block_sums, int n_blocks, int32_t *__restrict__ total_out) {
   __shared__ int32_t warp_sums[32];
   __shared__ int32_t carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < N; base += blockDim.x) {
+  for (int base = 0; base < n_blocks; base += 1024) {
     const int i = base + threadIdx.x;
-    const int32_t v = (i < N) ? counts[i] : 0;
-    int32_t x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) >= o) x += y;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    int32_t total;
+    const int32_t ex = block_exclusive_scan_1024((i < n_blocks) ? block_sums[i] : 0, warp_sums, total);
+    const int32_t c = carry;
     __syncthreads();
-    if (threadIdx.x < 32) {
-      int32_t w = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
-        if (threadIdx.x >= o) w += y;
-      }
-      warp_sums[threadIdx.x] = w;
-    }
-    __syncthreads();
-    const int32_t warp_prefix = (threadIdx.x >> 5) ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
-    if (i < N) offsets[i] = carry + warp_prefix + x - v;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry += warp_prefix + x;
+    if (i < n_blocks) block_sums[i] = c + ex;
+    if (threadIdx.x == 0) carry = c + total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry;
+  if (threadIdx.x == 0) *total_out = carry;
 }
 
 __global__ void k_episode_scores(const float *__restrict__ masks, const float *__restrict__ cliff, const float *__restrict__ returns,
                                  const float *__restrict__ values, const float *__restrict__ rewards,
                                  const int32_t *__restrict__ seeds, int T, int N, int strategy,
-                                 const int32_t *__restrict__ offsets, mgplr_episode *__restrict__ out, int max_out) {
+                                 const int32_t *__restrict__ offsets, const int32_t *__restrict__ block_off,
+                                 mgplr_episode *__restrict__ out, int max_out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
-  int k = offsets[e];
+  int k = offsets[e] + block_off[e >> 10];
   int start = 0;
   double sum = 0.0, vsum = 0.0;
   float mx = -INFINITY, rsum = 0.f, vmin = INFINITY;
@@ -153,18 +173,21 @@ extern "C" int mgplr_plr_episode_scores(const float *masks, const float *cliffha
   if (strategy != MGPLR_SCORE_MAX_MC && !returns) return pfail(MGPLR_E_BADARG, "returns required for this strategy");
   int dev = 0;
   PCK(cudaGetDevice(&dev));
-  if (g_scratch_dev != dev || g_scratch_n < 2 * (size_t)N) {
+  const int n_blocks = (N + 1023) / 1024;
+  const size_t need = 2 * (size_t)N + (size_t)n_blocks;
+  if (g_scratch_dev != dev || g_scratch_n < need) {
     if (g_scratch) cudaFree(g_scratch);
     g_scratch = nullptr;
-    PCK(cudaMalloc((void **)&g_scratch, 2 * (size_t)N * sizeof(int32_t)));
-    g_scratch_n = 2 * (size_t)N; g_scratch_dev = dev;
+    PCK(cudaMalloc((void **)&g_scratch, need * sizeof(int32_t)));
+    g_scratch_n = need; g_scratch_dev = dev;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  int32_t *counts = g_scratch, *offsets = g_scratch + N;
+  int32_t *counts = g_scratch, *offsets = g_scratch + N, *block_off = g_scratch + 2 * (size_t)N;
   k_count_episodes<<<(N + 127) / 128, 128, 0, st>>>(masks, T, N, counts);
-  k_scan_counts<<<1, 1024, 0, st>>>(counts, N, offsets, n_episodes);
+  k_scan_blocks<<<n_blocks, 1024, 0, st>>>(counts, N, offsets, block_off);
+  k_scan_tops<<<1, 1024, 0, st>>>(block_off, n_blocks, n_episodes);
   k_episode_scores<<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, returns, value_preds, rewards, level_seeds, T, N,
-                                                    strategy, offsets, episodes, max_episodes);
+                                                    strategy, offsets, block_off, episodes, max_episodes);
   PCK(cudaGetLastError());
   return 0;
 }

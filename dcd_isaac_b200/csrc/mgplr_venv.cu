@@ -167,17 +167,22 @@ __global__ void k_reset_agent(Dev d, OutPtrs o) {
   emit_direct(R, s, d.c, o, e);
 }
 
-__global__ void k_reset_random(Dev d, const int32_t *n_walls, OutPtrs o) {
+__global__ void __launch_bounds__(128) k_reset_random(Dev d, const int32_t *n_walls, OutPtrs o) {
+  extern __shared__ uint32_t s_rr[];  // [W][128]: the grid is rebuilt in shared memory and written back once
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  const Rows R = env_rows(d, e);
+  const int W = d.c.W;
+  const Rows G = env_rows(d, e);
+  const Rows R{s_rr + threadIdx.x, 128};
   Env s = unpack(d.hot[e]);
+  if (s.pending) for (int r = 0; r < W; r++) R.set(r, G.get(r));  // deferred respawns replay against the old level
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
-  Rng rng(d, e, Rng::kCap);
+  Rng rng(d, e);
   const int nw = (d.c.resample && n_walls) ? n_walls[e] : -1;
   reset_random(R, s, adv, met, rng, d, e, nw, err);
   rng.store();
+  for (int r = 0; r < W; r++) G.set(r, R.get(r));
   s.ep_ret = 0.f; s.ep_len = 0;  // VecMonitor.reset_random (vec_monitor.py:48-52)
   d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
   if (err) d.err[e] |= err;
@@ -393,7 +398,7 @@ __device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int strid
   Env s = unpack(hot);
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
-  Rng rng(d, e, Rng::kCap);
+  Rng rng(d, e);
   reset_random(Rows{rows, stride}, s, adv, met, rng, d, e, n_walls, err);
   rng.store();
   d.adv[e] = adv; d.metrics[e] = met;
@@ -907,7 +912,7 @@ extern "C" int mgplr_reset_agent(mgplr_venv *v, const mgplr_step_out *out, void 
 
 extern "C" int mgplr_reset_random(mgplr_venv *v, const int32_t *n_walls, const mgplr_step_out *out, void *stream) {
   NEED(v);
-  k_reset_random<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, n_walls, outptrs(out));
+  k_reset_random<<<grid_for(v->d.N, 128), 128, (size_t)v->d.c.W * 128 * 4, st>>>(v->d, n_walls, outptrs(out));
   CK(cudaGetLastError());
   return 0;
 }

@@ -12,14 +12,22 @@
 
 int main(int argc, char **argv) {
   int N = argc > 1 ? atoi(argv[1]) : 131072, W = argc > 2 ? atoi(argv[2]) : 15, T = argc > 3 ? atoi(argv[3]) : 64;
-  int reps = argc > 4 ? atoi(argv[4]) : 5, ablate = argc > 5 ? atoi(argv[5]) : 0, see = argc > 6 ? atoi(argv[6]) : 1, amode = argc > 7 ? atoi(argv[7]) : 0;
+  int reps = argc > 4 ? atoi(argv[4]) : 5, ablate = argc > 5 ? atoi(argv[5]) : 0, see = argc > 6 ? atoi(argv[6]) : 1, amode = argc > 7 ? atoi(argv[7]) : 0, rr = argc > 8 ? atoi(argv[8]) : 0;
   mgplr_env_config cfg = {W, 5, 250, 250, see, 50, 0, 1, 0, 4};
   mgplr_venv *v;
   CKM(mgplr_venv_create(&cfg, N, 0, &v));
   std::vector<uint32_t> limbs(2 * N); std::vector<int32_t> cnt(N, 2);
   for (int i = 0; i < N; i++) { limbs[2 * i] = 12345u + 977u * i; limbs[2 * i + 1] = 99u + i; }
   CKM(mgplr_seed(v, limbs.data(), cnt.data(), nullptr, N, 0));
-  CKM(mgplr_reset_random(v, nullptr, nullptr, 0));
+  {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    CKM(mgplr_reset_random(v, nullptr, nullptr, 0)); CKC(cudaDeviceSynchronize());
+    cudaEventRecord(a, 0);
+    CKM(mgplr_reset_random(v, nullptr, nullptr, 0));
+    cudaEventRecord(b, 0); CKC(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    printf("reset_random of %d envs: %.1f us (%.1f ns/env)\n", N, ms * 1e3, ms * 1e6 / N);
+  }
   float *img, *dir, *rew, *mk, *bm, *cm; uint8_t *fl; int64_t *act; float *epr; int32_t *epl;
   CKC(cudaMalloc(&img, (size_t)(T + 1) * N * 300)); CKC(cudaMalloc(&dir, (size_t)(T + 1) * N * 4)); CKC(cudaMalloc(&rew, (size_t)T * N * 4));
   CKC(cudaMalloc(&mk, (size_t)(T + 1) * N * 4)); CKC(cudaMalloc(&bm, (size_t)(T + 1) * N * 4)); CKC(cudaMalloc(&cm, (size_t)(T + 1) * N * 4));
@@ -37,7 +45,7 @@ int main(int argc, char **argv) {
       if (!(ablate & 1)) o.image = img + (size_t)(t + 1) * N * 75;
       if (!(ablate & 2)) { o.direction = dir + (size_t)(t + 1) * N; o.reward = rew + (size_t)t * N; o.flags = fl + (size_t)t * N; o.ep_return = epr; o.ep_length = epl; }
       if (!(ablate & 4)) { o.masks = mk + (size_t)(t + 1) * N; o.bad_masks = bm + (size_t)(t + 1) * N; o.cliffhanger_masks = cm + (size_t)(t + 1) * N; }
-      CKM(mgplr_step_env(v, act + (size_t)t * N, 0, nullptr, 0, &o, st));
+      CKM(mgplr_step_env(v, act + (size_t)t * N, rr, nullptr, 0, &o, st));
     }
   };
   steps(); CKC(cudaStreamSynchronize(st));
@@ -51,7 +59,7 @@ int main(int argc, char **argv) {
   cudaEventRecord(b, st); CKC(cudaStreamSynchronize(st));
   float ms; cudaEventElapsedTime(&ms, a, b);
   double us = ms * 1e3 / (reps * (double)T);  // includes 1/T of the reset_agent launch
-  printf("amode=%d ", amode); printf("N=%d W=%d T=%d see=%d ablate=%d tile=%s: %.2f us/launch  %.3f Gsteps/s  %.0f GB/s@360B\n", N, W, T, see, ablate,
+  printf("amode=%d rr=%d ", amode, rr); printf("N=%d W=%d T=%d see=%d ablate=%d tile=%s: %.2f us/launch  %.3f Gsteps/s  %.0f GB/s@360B\n", N, W, T, see, ablate,
          getenv("MGPLR_TILE") ? getenv("MGPLR_TILE") : "def", us, N / us * 1e-3, N * 360.0 / us * 1e-3);
   mgplr_venv_destroy(v);
   return 0;
