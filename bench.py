@@ -62,6 +62,19 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def traffic_from_profile(N, a):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of k_step_env from the committed `ncu --set full`
+    capture (profiles/traffic.json), when it was taken on this workload; else None."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        t = json.load(open(p))['k_step_env']
+        if t['envs'] == N and t['size'] == a.size and t['opaque'] == a.opaque and not a.reset_random:
+            return t['dram_bytes_per_launch']
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(object):
     """nvidia-smi clocks + throttle reasons during the timed region."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -190,7 +203,7 @@ def run_ours(a):
     flags = torch.zeros(T, N, dtype=torch.uint8, device=dev)
     ep_r = torch.zeros(N, device=dev)
     ep_l = torch.zeros(N, dtype=torch.int32, device=dev)
-    max_eps = N * 16
+    max_eps = N * 4  # ~2.2 episodes per env per rollout here; the kernel drops records beyond the cap
     episodes = torch.zeros(max_eps, 10, dtype=torch.int32, device=dev)
     n_eps = torch.zeros(1, dtype=torch.int32, device=dev)
     gathered = torch.zeros(world * max_eps, 10, dtype=torch.int32, device=dev) if world > 1 else None
@@ -234,6 +247,11 @@ def run_ours(a):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    # nvidia-smi sampling runs from the warm-up to the end of the e2e pass (the K timed steps alone last a few
+    # milliseconds, shorter than one nvidia-smi query), so every sample is taken under load
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(a.warmup, 3)):
         rollout()
     sync_all()
@@ -255,9 +273,6 @@ def run_ours(a):
     else:
         per_roll = 1 + T + 1 + 4
         run_roll, run_steps = rollout, env_steps
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -275,7 +290,6 @@ def run_ours(a):
     sync_all()
     kernel_ms = [k0.elapsed_time(k1) / a.steps]
     launches[0] = per_roll * a.steps
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -330,6 +344,7 @@ def run_ours(a):
                'h2d_bytes_per_step': T * N * 8, 'd2h_bytes_per_step': T * N * 13 + 4,
                'api': 'mgplr_step_env_host (pinned host actions in, reward/flags/episode stats out, obs stay in rollout storage)'}
 
+    clocks = sampler.stop() if rank == 0 else None
     cpu = None
     if rank == 0 and not a.no_cpu:
         cores = os.cpu_count() or 1
@@ -346,14 +361,22 @@ def run_ours(a):
                        (N * T * 410 / 1e9), 'episodes_per_rollout': n_episodes, 'done_steps': n_done, 'goals': n_goal,
                        'state_bytes': venv.state_bytes(), 'launch': 'cuda-graph replay' if use_graph else 'per-kernel launches from Python'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'kernel': 'k_step_env', 'bytes_per_env_step': BYTES_PER_STEP,
+                         'traffic': traffic_from_profile(N, a), 'kernel': 'k_step_env', 'bytes_per_env_step': BYTES_PER_STEP,
                          'avg_launch_us': avg_launch_s * 1e6, 'peak_source': peak_src},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': n_launch, 'clocks': clocks,
         }
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    # teardown: CUDA graphs that captured NCCL work must die before the communicator; never hang the driver on exit
+    if use_graph:
+        del g_roll, g_steps, run_roll, run_steps
+    torch.cuda.synchronize(dev)
     venv.close()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+        finally:
+            os._exit(0)
 
 
 def main():
