@@ -308,17 +308,18 @@ def run_ours(a):
     e2e = None
     if not a.no_e2e:
         h_act = actions.to(torch.int64).cpu().pin_memory()
-        h_rew = torch.zeros(N).pin_memory()
-        h_epr = torch.zeros(N).pin_memory()
-        h_epl = torch.zeros(N, dtype=torch.int32).pin_memory()
         h_flg = torch.zeros(N, dtype=torch.uint8).pin_memory()
+        h_done = torch.zeros(N * 16, dtype=torch.uint8).pin_memory()
+        h_nd = torch.zeros(1, dtype=torch.int32).pin_memory()
         hp = [ptr(h_act[t]) for t in range(T)]
+        done_seen = [0]
 
         def rollout_host():
             check(L.mgplr_reset_agent(venv.h, C.byref(venv._out({'image': obs_img[0], 'direction': obs_dir[0]})), stream))
             for t in range(T):
-                check(L.mgplr_step_env_host(venv.h, hp[t], rr, 3 if t == T - 1 else 0, C.byref(outs[t]), ptr(h_rew), ptr(h_flg),
-                                            ptr(h_epr), ptr(h_epl), stream))
+                check(L.mgplr_step_env_host(venv.h, hp[t], rr, 3 if t == T - 1 else 0, C.byref(outs[t]), ptr(h_flg), ptr(h_done),
+                                            N, ptr(h_nd), stream))
+                done_seen[0] += int(h_nd[0])
             check(L.mgplr_gae(ptr(rewards), ptr(values), ptr(masks), ptr(returns), T, N, 0.995, 0.95, stream))
             check(L.mgplr_plr_episode_scores(ptr(masks), ptr(cliff), ptr(returns), ptr(values), ptr(rewards), ptr(level_seeds),
                                              T, N, 0, ptr(episodes), max_eps, ptr(n_eps), stream))
@@ -341,8 +342,9 @@ def run_ours(a):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ems = float(tt.item())
         e2e = {'value': N * T * ksteps * world / (ems * 1e-3), 'unit': 'env-steps/s',
-               'h2d_bytes_per_step': T * N * 8, 'd2h_bytes_per_step': T * N * 13 + 4,
-               'api': 'mgplr_step_env_host (pinned host actions in, reward/flags/episode stats out, obs stay in rollout storage)'}
+               'h2d_bytes_per_step': T * N * 8, 'd2h_bytes_per_step': T * (N + 16 + 16 * min(N, 2047)) + 4,
+               'api': 'mgplr_step_env_host every vector step: pinned int64 actions H2D, kernel, flags u8[N] + done records D2H, '
+                      'stream sync; observations / rewards / masks stay in rollout storage'}
 
     clocks = sampler.stop() if rank == 0 else None
     cpu = None

@@ -40,6 +40,7 @@ class Episode(C.Structure):
                 ('value_sum', C.c_float), ('value_min', C.c_float), ('cliffhanger', C.c_int32)]
 
 
+DONE_DTYPE = [('env', '<i4'), ('reward', '<f4'), ('ep_return', '<f4'), ('ep_length', '<i4')]
 EPISODE_DTYPE = [('actor', '<i4'), ('t_start', '<i4'), ('t_end', '<i4'), ('seed', '<i4'), ('mean_score', '<f4'),
                  ('max_score', '<f4'), ('reward_sum', '<f4'), ('value_sum', '<f4'), ('value_min', '<f4'),
                  ('cliffhanger', '<i4')]
@@ -92,7 +93,7 @@ def load():
     L.mgplr_mutate_edits.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     L.mgplr_mutate_finalize.argtypes = [vp, vp, C.POINTER(StepOut), vp]
     L.mgplr_step_env.argtypes = [vp, vp, i32, vp, i32, C.POINTER(StepOut), vp]
-    L.mgplr_step_env_host.argtypes = [vp, vp, i32, i32, C.POINTER(StepOut), vp, vp, vp, vp, vp]
+    L.mgplr_step_env_host.argtypes = [vp, vp, i32, i32, C.POINTER(StepOut), vp, vp, i32, vp, vp]
     L.mgplr_rollout.argtypes = [vp, vp, i32, i32, C.POINTER(StepOut), vp]
     L.mgplr_get_encodings.argtypes = [vp, vp, vp]
     L.mgplr_get_metrics.argtypes = [vp, vp, vp]

@@ -44,11 +44,13 @@ struct mgplr_venv {
   // scratch for host->device argument staging
   uint32_t *seed_scratch;  // [4][N]
   int64_t *act_dev;        // [N]   (mgplr_step_env_host)
-  uint8_t *res_dev;        // packed results [N*13]
+  uint8_t *res_dev;        // [16 B: done count][N done records][N flags]
+  uint8_t *res_pin;        // pinned host staging for the count + first kDonePrefix records
   int sm_count;
 };
 
 // dynamic shared memory: `bufs` obs tiles [TILE][75] f32 then wall rows [W][TILE] u32
+constexpr int kDonePrefix = 2047;  // done records fetched together with the count in one D2H copy
 static size_t step_smem_bytes(int W, int tile, int bufs) { return (size_t)bufs * tile * kObsFloats * 4 + (size_t)W * tile * 4; }
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -369,6 +371,8 @@ struct StepArgs {
   const int32_t *n_walls;
   int last_step;  // bit0: last rollout step (adversarial_runner.py:521-530), bit1: use_proper_time_limits
   mgplr_step_out o;
+  uint32_t *done_count;          // host-driven step: append-list of finished episodes (NULL otherwise)
+  mgplr_done_record *done_list;
 };
 
 // ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
@@ -464,8 +468,15 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
   return flags;
 }
 
-__device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, const Env &s, uint32_t flags, float rew) {
+__device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, const Env &s, uint32_t flags, float rew,
+                                                   float ep_ret = 0.f, int ep_len = 0) {
   const mgplr_step_out &o = A.o;
+  if (A.done_count && (flags & MGPLR_F_DONE)) {
+    const uint32_t k = atomicAdd(A.done_count, 1u);
+    mgplr_done_record r;
+    r.env = e; r.reward = rew; r.ep_return = ep_ret; r.ep_length = ep_len;
+    A.done_list[k] = r;
+  }
   if (o.direction) o.direction[e] = (float)s.adir;
   if (o.reward) o.reward[e] = rew;
   if (o.flags) o.flags[e] = (uint8_t)flags;
@@ -618,6 +629,8 @@ __global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles
     uint32_t flags = 0;
     double rew = 0.0;
     bool dirty = false;
+    float fin_ret = 0.f;
+    int fin_len = 0;
     if (valid) {
       const bool want_trunc = A.o.trunc_image || A.o.trunc_direction;
       // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
@@ -650,6 +663,7 @@ __global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles
       s.ep_len += 1;
       if (done) {
         flags |= MGPLR_F_DONE;
+        fin_ret = s.ep_ret; fin_len = s.ep_len;
         if (A.o.ep_return) A.o.ep_return[e] = s.ep_ret;
         if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
         s.ep_ret = 0.f; s.ep_len = 0;
@@ -680,7 +694,7 @@ __global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles
     }
     if (valid) {
       d.hot[e] = pack(s);
-      write_step_scalars(A, e, s, flags, (float)rew);
+      write_step_scalars(A, e, s, flags, (float)rew, fin_ret, fin_len);
       if (A.o.image_u8) rare_emit_u8(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.image_u8, e);
       if (RR && dirty) {
         const Rows G = env_rows(d, e);
@@ -802,7 +816,8 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(dalloc(&d.err, N, total));
   CK(dalloc(&v->seed_scratch, 4 * N, total));
   CK(dalloc(&v->act_dev, N, total));
-  CK(dalloc(&v->res_dev, 16 * N, total));
+  CK(dalloc(&v->res_dev, 16 + 16 * N + N, total));
+  CK(cudaHostAlloc((void **)&v->res_pin, 16 + 16 * (size_t)kDonePrefix, cudaHostAllocDefault));
   v->bytes = total;
   CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device));
   {
@@ -832,7 +847,7 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
   cudaSetDevice(v->device);
   Dev &d = v->d;
   cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
-  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->res_dev);
+  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->res_dev); cudaFreeHost(v->res_pin);
   delete v;
 }
 
@@ -951,12 +966,16 @@ extern "C" int mgplr_mutate_finalize(mgplr_venv *v, const int32_t *choice, const
   return 0;
 }
 
+static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st);
 static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls, int32_t last_step,
                        const mgplr_step_out *out, cudaStream_t st) {
   StepArgs A;
   memset(&A, 0, sizeof(A));
   A.action = action; A.n_walls = n_walls; A.last_step = last_step;
   if (out) A.o = *out;
+  return launch_step_args(v, A, reset_random, st);
+}
+static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st) {
   // persistent grid: as many 4-warp CTAs as fit on the chip (shared-memory bound), capped by the tile count
   const int W = v->d.c.W, wpc = 4;
   const size_t smem = wpc * warp_smem_bytes(W);
@@ -989,33 +1008,39 @@ extern "C" int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t rese
 }
 
 extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
-                                   const mgplr_step_out *out_dev, float *reward_host, uint8_t *flags_host,
-                                   float *ep_return_host, int32_t *ep_length_host, void *stream) {
+                                   const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
+                                   int32_t done_capacity, int32_t *n_done_host, void *stream) {
   NEED(v);
   if (!action_host) return fail(MGPLR_E_BADARG, "action_host is NULL");
   const size_t N = (size_t)v->d.N;
+  uint32_t *count_d = (uint32_t *)v->res_dev;
+  mgplr_done_record *list_d = (mgplr_done_record *)(v->res_dev + 16);
+  uint8_t *flags_d = v->res_dev + 16 + 16 * N;
   CK(cudaMemcpyAsync(v->act_dev, action_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  mgplr_step_out o;
-  memset(&o, 0, sizeof(o));
-  if (out_dev) o = *out_dev;
-  // packed device staging: reward f32 [N] | ep_return f32 [N] | ep_length i32 [N] | flags u8 [N]
-  float *rew_d = (float *)v->res_dev;
-  float *epr_d = rew_d + N;
-  int32_t *epl_d = (int32_t *)(epr_d + N);
-  uint8_t *flg_d = (uint8_t *)(epl_d + N);
-  // the device-side destinations requested by the caller keep working: copy after the kernel
-  mgplr_step_out k = o;
-  k.reward = rew_d; k.ep_return = epr_d; k.ep_length = epl_d; k.flags = flg_d;
-  if (int rc = launch_step(v, v->act_dev, reset_random, nullptr, last_step, &k, st)) return rc;
-  if (o.reward) CK(cudaMemcpyAsync(o.reward, rew_d, N * 4, cudaMemcpyDeviceToDevice, st));
-  if (o.flags) CK(cudaMemcpyAsync(o.flags, flg_d, N, cudaMemcpyDeviceToDevice, st));
-  if (o.ep_return) CK(cudaMemcpyAsync(o.ep_return, epr_d, N * 4, cudaMemcpyDeviceToDevice, st));
-  if (o.ep_length) CK(cudaMemcpyAsync(o.ep_length, epl_d, N * 4, cudaMemcpyDeviceToDevice, st));
-  if (reward_host) CK(cudaMemcpyAsync(reward_host, rew_d, N * 4, cudaMemcpyDeviceToHost, st));
-  if (ep_return_host) CK(cudaMemcpyAsync(ep_return_host, epr_d, N * 4, cudaMemcpyDeviceToHost, st));
-  if (ep_length_host) CK(cudaMemcpyAsync(ep_length_host, epl_d, N * 4, cudaMemcpyDeviceToHost, st));
-  if (flags_host) CK(cudaMemcpyAsync(flags_host, flg_d, N, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(count_d, 0, 16, st));
+  StepArgs A;
+  memset(&A, 0, sizeof(A));
+  if (out_dev) A.o = *out_dev;
+  uint8_t *user_flags = A.o.flags;
+  A.action = v->act_dev; A.last_step = last_step;
+  A.o.flags = flags_d; A.done_count = count_d; A.done_list = list_d;
+  if (int rc = launch_step_args(v, A, reset_random, st)) return rc;
+  if (user_flags) CK(cudaMemcpyAsync(user_flags, flags_d, N, cudaMemcpyDeviceToDevice, st));
+  const size_t prefix = N < (size_t)kDonePrefix ? N : (size_t)kDonePrefix;
+  CK(cudaMemcpyAsync(v->res_pin, v->res_dev, 16 + 16 * prefix, cudaMemcpyDeviceToHost, st));
+  if (flags_host) CK(cudaMemcpyAsync(flags_host, flags_d, N, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  const uint32_t n_done = *(const uint32_t *)v->res_pin;
+  if (n_done_host) *n_done_host = (int32_t)n_done;
+  if (done_host && done_capacity > 0) {
+    const size_t want = n_done < (uint32_t)done_capacity ? n_done : (size_t)done_capacity;
+    const size_t first = want < prefix ? want : prefix;
+    memcpy(done_host, v->res_pin + 16, first * sizeof(mgplr_done_record));
+    if (want > first) {  // a reset storm: fetch the rest directly
+      CK(cudaMemcpyAsync(done_host + first, list_d + first, (want - first) * sizeof(mgplr_done_record), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+  }
   return 0;
 }
 

@@ -83,12 +83,11 @@ class CudaAdversarialVecEnv(object):
         self._ep_l = torch.zeros(N, dtype=torch.int32, device=dev)
         self._done_adv = torch.zeros(N, dtype=torch.uint8, device=dev)
         self._errors = torch.zeros(N, dtype=torch.int32, device=dev)
-        # pinned host staging for the host-driven step (reward f32 | ep_r f32 | ep_l i32 | flags u8)
+        # pinned host staging for the host-driven step (actions in; flags + done records out)
         self._h_action = torch.zeros(N, dtype=torch.int64).pin_memory()
-        self._h_reward = torch.zeros(N, dtype=torch.float32).pin_memory()
-        self._h_ep_r = torch.zeros(N, dtype=torch.float32).pin_memory()
-        self._h_ep_l = torch.zeros(N, dtype=torch.int32).pin_memory()
         self._h_flags = torch.zeros(N, dtype=torch.uint8).pin_memory()
+        self._h_done = torch.zeros(N * 16, dtype=torch.uint8).pin_memory()  # mgplr_done_record [N]
+        self._h_ndone = torch.zeros(1, dtype=torch.int32).pin_memory()
         if seed is not None:
             self.set_seed([seed] * N)
 
@@ -321,11 +320,15 @@ class CudaAdversarialVecEnv(object):
         else:
             self._h_action.copy_(a.reshape(-1))
             check(self.L.mgplr_step_env_host(self.h, ptr(self._h_action), int(bool(reset_random)), 0, C.byref(o),
-                                             ptr(self._h_reward), ptr(self._h_flags), ptr(self._h_ep_r), ptr(self._h_ep_l),
+                                             ptr(self._h_flags), ptr(self._h_done), N, ptr(self._h_ndone),
                                              self._stream()), 'mgplr_step_env_host')
             flags = self._h_flags.numpy().copy()
-            ep_r = self._h_ep_r.numpy().copy()
-            ep_l = self._h_ep_l.numpy().copy()
+            nd = int(self._h_ndone[0])
+            rec = self._h_done.numpy()[:nd * 16].view(np.dtype(_lib.DONE_DTYPE))
+            ep_r = np.zeros(N, np.float32)
+            ep_l = np.zeros(N, np.int32)
+            ep_r[rec['env']] = rec['ep_return']
+            ep_l[rec['env']] = rec['ep_length']
         done = (flags & F_DONE) != 0
         infos = [{} for _ in range(N)]
         if flags.any():

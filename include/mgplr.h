@@ -132,13 +132,22 @@ int mgplr_mutate_finalize(mgplr_venv *v, const int32_t *choice, const mgplr_step
 int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls,
                    int32_t last_step, const mgplr_step_out *out, void *stream);
 
-/* The same transition driven from HOST buffers (the reference's calling convention: actions arrive as a
- * CPU tensor, adversarial_runner.py:512-517; reward / done / info come back to the host).  Observations
- * stay in HBM at out->image (rollout storage).  Copies: action H2D 8 B/env; reward 4 + flags 1 +
- * ep_return 4 + ep_length 4 B/env D2H.  Synchronises `stream` before returning. */
+/* One finished episode, as the host needs it to build info['episode'] (vec_monitor.py:66-74). */
+typedef struct mgplr_done_record {
+  int32_t env;        /* env index */
+  float reward;       /* reward of the terminating step */
+  float ep_return;    /* info['episode']['r'] */
+  int32_t ep_length;  /* info['episode']['l'] */
+} mgplr_done_record;
+
+/* The same transition driven from HOST buffers (the reference's calling convention: actions arrive as a CPU
+ * tensor, adversarial_runner.py:512-517; done / infos go back to the host).  Observations, rewards and masks stay
+ * in HBM at the `out_dev` destinations (rollout storage).  Per call: action i64 [N] H2D; flags u8 [N] and the
+ * (few) done records D2H; one stream synchronisation.  done_host receives min(*n_done_host, done_capacity)
+ * records in unspecified order.  All host pointers should be pinned memory. */
 int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
-                        const mgplr_step_out *out_dev, float *reward_host, uint8_t *flags_host,
-                        float *ep_return_host, int32_t *ep_length_host, void *stream);
+                        const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
+                        int32_t done_capacity, int32_t *n_done_host, void *stream);
 
 /* T consecutive step_env transitions in ONE launch from a recorded action stream u8 [T][N]: env state
  * stays in shared memory / registers across steps (replayed-seed evaluation, random-policy rollouts).
