@@ -5,7 +5,7 @@ from .registry import ENV_SPECS, env_spec  # noqa: F401
 
 
 def __getattr__(name):
-    if name in ('CudaAdversarialVecEnv', 'create_parallel_env'):
+    if name in ('CudaAdversarialVecEnv', 'CudaMazeVecEnv', 'create_parallel_env'):
         from . import vec_env
         return getattr(vec_env, name)
     raise AttributeError(name)

@@ -225,6 +225,36 @@ __global__ void k_reset_to_encoding(Dev d, const uint8_t *enc, const int32_t *in
   emit_direct(R, s, d.c, o, e);
 }
 
+// Fixed-level load (MazeEnv._gen_grid, maze.py:75-94): no env-RNG use, explicit start direction.
+__global__ void k_load_levels(Dev d, const uint8_t *enc, int n_levels, const int32_t *level_index, int start_dir, OutPtrs o) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const int W = d.c.W;
+  const Rows R = env_rows(d, e);
+  Env s = unpack(d.hot[e]);
+  int lv = level_index ? level_index[e] : 0;
+  if (lv < 0 || lv >= n_levels) lv = 0;
+  const uint8_t *src = enc + (size_t)lv * W * W * 3;
+  s.gx = s.gy = s.sx = s.sy = kNone;
+  for (int y = 0; y < W; y++) {
+    uint32_t row = 0;
+    for (int x = 0; x < W; x++) {
+      const uint8_t t = src[((size_t)x * W + y) * 3];
+      if (t == 2) row |= 1u << x;
+      else if (t == 8) { s.gx = x; s.gy = y; }
+      else if (t == 10) { s.sx = x; s.sy = y; }
+    }
+    R.set(y, row);
+  }
+  s.sdir = start_dir & 3;
+  s.pending = 0;  // deferred respawn draws belong to the previous level's stream position: dropped with it
+  s.ep_ret = 0.f; s.ep_len = 0;
+  d.metrics[e] = compute_metrics(R, s, W, true);
+  if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+  d.hot[e] = pack(s);
+  emit_direct(R, s, d.c, o, e);
+}
+
 // reset_to_level, action-string form (adversarial.py:274-283).
 __global__ void k_reset_to_actions(Dev d, const int32_t *locs, int len, const int32_t *index, int n, OutPtrs o) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -937,6 +967,16 @@ extern "C" int mgplr_reset_to_encoding(mgplr_venv *v, const uint8_t *enc, const 
   NEED(v);
   if (!enc || n < 1 || n > v->d.N) return fail(MGPLR_E_BADARG, "mgplr_reset_to_encoding: bad arguments");
   k_reset_to_encoding<<<grid_for(n, 128), 128, 0, st>>>(v->d, enc, index, n, outptrs(out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_load_levels(mgplr_venv *v, const uint8_t *enc, int32_t n_levels, const int32_t *level_index,
+                                 int32_t start_dir, const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  if (!enc || n_levels < 1) return fail(MGPLR_E_BADARG, "mgplr_load_levels: bad arguments");
+  k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d);  // the RNG stream keeps its reference position
+  k_load_levels<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, enc, n_levels, level_index, start_dir, outptrs(out));
   CK(cudaGetLastError());
   return 0;
 }

@@ -37,8 +37,9 @@ def seed_limbs(seed):
 
 
 class CudaAdversarialVecEnv(object):
-    def __init__(self, env_name, num_envs, device='cuda:0', seed=None, fixed_environment=None, **overrides):
-        spec = env_spec(env_name, fixed_environment=fixed_environment, **overrides)
+    def __init__(self, env_name, num_envs, device='cuda:0', seed=None, fixed_environment=None, spec=None, **overrides):
+        if spec is None:
+            spec = env_spec(env_name, fixed_environment=fixed_environment, **overrides)
         self.env_name = env_name
         self.spec = spec
         self.num_envs = int(num_envs)
@@ -447,6 +448,66 @@ class CudaAdversarialVecEnv(object):
             self.close()
         except Exception:
             pass
+
+
+class CudaMazeVecEnv(CudaAdversarialVecEnv):
+    """Zero-shot evaluation mazes (envs/multigrid/maze.py: MazeEnv and subclasses, registered without a TimeLimit) as a
+    vectorised env with the evaluator's API (eval.py:206-329): `reset()` -> agent obs, `step(action)` with the worker's
+    auto-`reset()` on done (parallel_wrappers.py:20-25), VecMonitor episode infos, preprocessed float32 observations.
+    Same step / render kernels as the adversarial env; the level is loaded once with mgplr_load_levels."""
+
+    def __init__(self, env_name, num_envs, device='cuda:0'):
+        from .mazes import MAZES
+        if env_name not in MAZES:
+            raise KeyError('No registered env with id: %s' % env_name)
+        m = MAZES[env_name]
+        spec = dict(n_clutter=0, size=m['size'], choose_goal_last=True, see_through_walls=True, max_steps=m['max_steps'],
+                    max_episode_steps=32767, resample_n_clutter=False, editor_actions='walls_none_agent_goal',
+                    fixed_environment=False)
+        super().__init__(env_name, num_envs, device=device, spec=spec)
+        self.maze = m
+        W = m['size']
+        if 'goal' in m:
+            goals = [tuple(m['goal'])] * num_envs
+        else:  # corridor mazes: row then col drawn per env at construction (maze.py:153-156,180-183)
+            goals = []
+            for _ in range(num_envs):
+                row = np.random.choice(m['goal_rows'])
+                col = np.random.choice(m['goal_cols'])
+                goals.append((int(col), int(row)))
+        distinct = sorted(set(goals))
+        enc = np.zeros((len(distinct), W, W, 3), np.uint8)
+        for k, g in enumerate(distinct):
+            enc[k, :, :, 0] = 1
+            for y in range(W):
+                for x in range(W):
+                    if (m['rows'][y] >> x) & 1:
+                        enc[k, x, y] = (2, 5, 0)
+            enc[k, g[0], g[1]] = (8, 1, 0)
+            enc[k, m['start'][0], m['start'][1]] = (10, 0, 0)
+        self.goal_positions = goals
+        self._levels = torch.from_numpy(enc).to(self.device)
+        self._level_index = torch.tensor([distinct.index(g) for g in goals], dtype=torch.int32, device=self.device)
+        self.set_seed([52] * num_envs)  # MultiGridEnv's default seed (multigrid.py:351)
+        self.reset()
+
+    def reset(self):
+        """MultiGridEnv.reset (multigrid.py:470-502) on every env: regenerate the fixed grid, agent at the start facing 0."""
+        self._assert_not_closed()
+        obs = self._new_obs()
+        o = self._out(obs)
+        check(self.L.mgplr_load_levels(self.h, ptr(self._levels), int(self._levels.shape[0]), ptr(self._level_index), 0,
+                                       C.byref(o), self._stream()), 'mgplr_load_levels')
+        self._raise_errors()
+        return obs
+
+    def step(self, action):
+        """venv.step(action): worker.step auto-reset()s on done (parallel_wrappers.py:20-25); for a fixed maze that is the
+        start state again, i.e. the same transition as step_env."""
+        return self.step_env(action, reset_random=False)
+
+    def get_max_episode_steps(self):
+        return None
 
 
 def create_parallel_env(args, adversary=True, device='cuda:0'):

@@ -110,6 +110,14 @@ int mgplr_reset_random(mgplr_venv *v, const int32_t *n_walls, const mgplr_step_o
 int mgplr_reset_to_encoding(mgplr_venv *v, const uint8_t *enc, const int32_t *index, int32_t n,
                             const mgplr_step_out *out, void *stream);
 
+/* Fixed-level environments (zero-shot evaluation mazes, envs/multigrid/maze.py:23-94 MazeEnv._gen_grid + MultiGridEnv.reset,
+ * multigrid.py:470-502): load byte-encoded levels WITHOUT touching the env RNG and with an explicit start direction
+ * (place_agent_at_pos(rand_dir=True) forces 0, multigrid.py:668-672).  enc u8 [n_levels][W][W][3] (device); env e gets
+ * level level_index[e] (i32 [N] device) or level 0 when level_index is NULL.  Metrics are recomputed, the agent is reset
+ * to the start, step / episode counters are cleared. */
+int mgplr_load_levels(mgplr_venv *v, const uint8_t *enc, int32_t n_levels, const int32_t *level_index, int32_t start_dir,
+                      const mgplr_step_out *out, void *stream);
+
 /* Same, action-string form: locs i32 [n][len] (device), replayed through step_adversary. */
 int mgplr_reset_to_actions(mgplr_venv *v, const int32_t *locs, int32_t len, const int32_t *index, int32_t n,
                            const mgplr_step_out *out, void *stream);
