@@ -616,8 +616,10 @@ __device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, 
   }
 }
 
+// reset_agent mode: the shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids; the DR
+// variant keeps the batched RNG of its in-kernel reset_random in registers instead (2 CTAs/SM).
 template <bool SEE, bool RR, typename EXT>
-__global__ void __launch_bounds__(128) k_step_env(Dev d, StepArgs A, int n_tiles) {
+__global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int n_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = d.c.W, N = d.N;
   const int wpc = blockDim.x >> 5;
