@@ -28,6 +28,8 @@ ENV_CASES = [
     ('sz25', None, dict(size=25, n_clutter=50, choose_goal_last=True, see_through_walls=True, max_steps=250), 250),
     ('sz25_opaque', None, dict(size=25, n_clutter=50, choose_goal_last=True, see_through_walls=False, max_steps=250), 250),
     ('mini6', 'MultiGrid-MiniGoalLastAdversarial-v0', None, 50),
+    # singleton_env: fixed_environment re-seeds on every reset_random (adversarial.py:542-543, util/__init__.py:137-139)
+    ('gl15_fixed', 'MultiGrid-GoalLastFewerBlocksOpaqueWallsAdversarial-v0', {'fixed_environment': True}, 250),
 ]
 
 
@@ -36,7 +38,7 @@ def _make(env_id, kwargs, tl, seed):
     adv = importlib.import_module("envs.multigrid.adversarial")
     from envs.wrappers import TimeLimit
     if env_id is not None:
-        return rh.make_env(env_id, seed=seed)
+        return rh.make_env(env_id, seed=seed, **(kwargs or {}))
     return TimeLimit(adv.AdversarialEnv(seed=seed, **kwargs), max_episode_steps=tl)
 
 
@@ -101,7 +103,7 @@ def gen_env_traces():
             np.savez_compressed(
                 os.path.join(GOLDEN, 'env_trace_%s_%s.npz' % (tag, mode)),
                 W=W, time_limit=tl, max_steps=env.max_steps, see_through=int(env.see_through_walls),
-                n_clutter=env.n_clutter, seeds=np.arange(n_env),
+                n_clutter=env.n_clutter, seeds=np.arange(n_env), fixed=int(bool(env.fixed_environment)),
                 encodings=np.stack(encs), metrics=np.array(met_l), first_obs=np.stack(starts),
                 actions=np.stack(out['actions']), obs=np.array(obs_l, dtype=np.uint8), dirs=np.array(dir_l, dtype=np.int8),
                 rewards=np.array(rew_l, dtype=np.float32), flags=np.array(flag_l, dtype=np.uint8),

@@ -23,7 +23,7 @@ def test_env_trace(name):
     g = golden(name)
     reset_random = name.endswith('_random.npz')
     n_env, T = g['actions'].shape
-    b = mo.OracleBatch(_cfg_from_trace(g), n_env)
+    b = mo.OracleBatch(_cfg_from_trace(g, fixed_environment=bool(g['fixed'])), n_env)
     for i in range(n_env):
         b.seed(i, int(g['seeds'][i]))
         assert b.reset_random(i) == 0
