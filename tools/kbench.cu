@@ -61,6 +61,21 @@ int main(int argc, char **argv) {
   double us = ms * 1e3 / (reps * (double)T);  // includes 1/T of the reset_agent launch
   printf("amode=%d rr=%d ", amode, rr); printf("N=%d W=%d T=%d see=%d ablate=%d tile=%s: %.2f us/launch  %.3f Gsteps/s  %.0f GB/s@360B\n", N, W, T, see, ablate,
          getenv("MGPLR_TILE") ? getenv("MGPLR_TILE") : "def", us, N / us * 1e-3, N * 360.0 / us * 1e-3);
+  {  // the multi-step kernel: T transitions in one launch from a recorded u8 action stream
+    std::vector<uint8_t> h8((size_t)T * N);
+    for (size_t i = 0; i < h8.size(); i++) h8[i] = (uint8_t)h[i];
+    uint8_t *act8; CKC(cudaMalloc(&act8, h8.size())); CKC(cudaMemcpy(act8, h8.data(), h8.size(), cudaMemcpyHostToDevice));
+    mgplr_step_out o = {};
+    o.image = img + (size_t)N * 75; o.direction = dir + N; o.reward = rew; o.flags = fl; o.masks = mk + N; o.bad_masks = bm + N;
+    o.cliffhanger_masks = cm + N;
+    CKM(mgplr_rollout(v, act8, T, rr, &o, st)); CKC(cudaStreamSynchronize(st));
+    cudaEventRecord(a, st);
+    for (int r = 0; r < reps; r++) CKM(mgplr_rollout(v, act8, T, rr, &o, st));
+    cudaEventRecord(b, st); CKC(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ms, a, b);
+    double us2 = ms * 1e3 / (reps * (double)T);
+    printf("  mgplr_rollout (T steps per launch): %.2f us/step  %.3f Gsteps/s  %.0f GB/s@360B\n", us2, N / us2 * 1e-3, N * 360.0 / us2 * 1e-3);
+  }
   mgplr_venv_destroy(v);
   return 0;
 }
