@@ -230,7 +230,7 @@ def gen_mutate():
                         ('empty', 'MultiGrid-GoalLastEmptyAdversarialEnv-Edit-v0'),
                         ('wn25', 'MultiGrid-GoalLastFewerBlocksAdversarial-EditWN-v0')):
         rec = {k: [] for k in ('base_enc', 'locs', 'ops', 'n_edits', 'goal_choice', 'agent_choice', 'need', 'out_enc',
-                               'metrics', 'obs', 'dirs')}
+                               'metrics', 'obs', 'dirs', 'np_seed', 'num_edits')}
         np.random.seed(2024)
         n_cases = 48
         for i in range(n_cases):
@@ -254,6 +254,8 @@ def gen_mutate():
                     log['randint'].clear(); log['choice'].clear()
                     if c > 0:
                         base = env.encoding.copy()
+                    last_seed = 5000 + i * 10 + c
+                    np.random.seed(last_seed)
                     o = env.mutate_level(num_edits=num_edits)
             finally:
                 np.random.randint, np.random.choice = o_randint, o_choice
@@ -282,6 +284,7 @@ def gen_mutate():
             rec['out_enc'].append(env.encoding.copy())
             rec['metrics'].append([env.n_clutter_placed, env.distance_to_goal, int(env.passable), env.shortest_path_length])
             rec['obs'].append(np.array(o['image'], dtype=np.uint8)); rec['dirs'].append(int(o['direction'][0]))
+            rec['np_seed'].append(last_seed); rec['num_edits'].append(num_edits)
         np.savez_compressed(os.path.join(GOLDEN, 'mutate_%s.npz' % tag), env_name=env_id,
                             n_editor_actions=len(env.editor_actions), **{k: np.array(v) for k, v in rec.items()})
         print('mutate', tag, 'fallbacks', np.array(rec['need']).sum(0))
