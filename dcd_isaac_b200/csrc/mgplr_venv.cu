@@ -135,22 +135,63 @@ __global__ void k_step_adversary(Dev d, const int64_t *loc, uint8_t *done) {
 }
 
 // Adversary observation image f32 [N][3][W][W] = Grid.encode()/10 with channels first
-// (adversarial.py:222-227,532-537; obs_wrappers.py:104-110).  One thread per (env, cell): for a fixed
-// channel consecutive threads write consecutive floats, so all three stores are coalesced.
-__global__ void k_adv_image(Dev d, float *image, float *time_step) {
-  const int W = d.c.W, WW = W * W;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)d.N * WW) return;
-  const int e = (int)(idx / WW), cell = (int)(idx % WW), x = cell / W, y = cell % W;
-  const Env s = unpack(d.hot[e]);
-  float t, c, st = 0.f;
-  if (s.has_agent && x == s.ax && y == s.ay) { t = 1.0f; c = 0.0f; st = s.adir == 0 ? 0.0f : s.adir == 1 ? 0.1f : s.adir == 2 ? 0.2f : 0.3f; }
-  else if ((env_rows(d, e).get(y) >> x) & 1u) { t = 0.2f; c = 0.5f; }
-  else if (x == s.gx && y == s.gy) { t = 0.8f; c = 0.1f; }
-  else { t = 0.1f; c = 0.0f; }
-  float *o = image + (size_t)e * 3 * WW + cell;
-  o[0] = t; o[WW] = c; o[2 * WW] = st;
-  if (time_step && cell == 0) time_step[e] = (float)(d.adv[e] & 0xfff);
+// (adversarial.py:222-227,532-537; obs_wrappers.py:104-110).  A CTA assembles the images of kAdvGroup consecutive
+// envs in shared memory (one thread per cell: type, colour, state planes) and writes them with ONE bulk asynchronous
+// store (kAdvGroup * 3*W*W*4 bytes, contiguous in the output and 16-byte aligned for groups of 4 envs); a ragged or
+// misaligned last group falls back to plain coalesced stores.
+constexpr int kAdvGroup = 4;
+constexpr int kFuseAdvMaxEnvs = 16384;
+// mode 0: image only; 1: AdversarialEnv.reset first; 2: step_adversary(loc) first -- the state update of the group's
+// envs runs on the first n_env threads of the same CTA, so reset()/step_adversary() + observation is ONE launch.
+__global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *time_step, int mode, const int64_t *loc,
+                                                   uint8_t *done) {
+  extern __shared__ __align__(128) float s_img[];
+  const int W = d.c.W, WW = W * W, per_env = 3 * WW;
+  const int e0 = blockIdx.x * kAdvGroup, n_env = min(kAdvGroup, d.N - e0);
+  if (mode && (int)threadIdx.x < n_env) {
+    const int e = e0 + threadIdx.x;
+    const Rows R = env_rows(d, e);
+    Env s = unpack(d.hot[e]);
+    uint32_t adv = d.adv[e], err = 0;
+    int4 met = d.metrics[e];
+    Rng rng(d, e);
+    if (mode == 1) reset_adversary(R, s, adv, met, rng, d.c);
+    else {
+      const long long l = loc[e];
+      const bool dn = step_adversary(R, s, adv, met, rng, d.c, (l < 0 || l > 0x7fffffff) ? -1 : (int)l, err);
+      if (done) done[e] = dn ? 1 : 0;
+    }
+    rng.store();
+    d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
+    if (err) d.err[e] |= err;
+  }
+  if (mode) __syncthreads();
+  for (int i = threadIdx.x; i < n_env * WW; i += blockDim.x) {
+    const int k = i / WW, cell = i - k * WW, x = cell / W, y = cell - x * W, e = e0 + k;
+    const Env s = unpack(d.hot[e]);
+    float t, c, st = 0.f;
+    if (s.has_agent && x == s.ax && y == s.ay) { t = 1.0f; c = 0.0f; st = s.adir == 0 ? 0.0f : s.adir == 1 ? 0.1f : s.adir == 2 ? 0.2f : 0.3f; }
+    else if ((env_rows(d, e).get(y) >> x) & 1u) { t = 0.2f; c = 0.5f; }
+    else if (x == s.gx && y == s.gy) { t = 0.8f; c = 0.1f; }
+    else { t = 0.1f; c = 0.0f; }
+    float *o = s_img + k * per_env + cell;
+    o[0] = t; o[WW] = c; o[2 * WW] = st;
+  }
+  if (time_step && (int)threadIdx.x < n_env) time_step[e0 + threadIdx.x] = (float)(d.adv[e0 + threadIdx.x] & 0xfff);
+  float *gdst = image + (size_t)e0 * per_env;
+  const uint32_t bytes = (uint32_t)(n_env * per_env * 4);
+  if ((bytes & 15u) == 0 && (((uintptr_t)gdst) & 15u) == 0) {
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_store(gdst, s_img, bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_env * per_env; i += blockDim.x) gdst[i] = s_img[i];
+  }
 }
 
 __global__ void k_reset_agent(Dev d, OutPtrs o) {
@@ -920,28 +961,34 @@ extern "C" int mgplr_seed(mgplr_venv *v, const uint32_t *limbs_host, const int32
   return 0;
 }
 
-static int launch_adv_image(mgplr_venv *v, float *adv_image, float *time_step, cudaStream_t st) {
-  if (!adv_image) return 0;
-  const size_t total = (size_t)v->d.N * v->d.c.W * v->d.c.W;
-  k_adv_image<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v->d, adv_image, time_step);
+static int launch_adv_image(mgplr_venv *v, float *adv_image, float *time_step, int mode, const int64_t *loc, uint8_t *done,
+                            cudaStream_t st) {
+  const size_t smem = (size_t)kAdvGroup * 3 * v->d.c.W * v->d.c.W * sizeof(float);
+  k_adv_image<<<(v->d.N + kAdvGroup - 1) / kAdvGroup, 128, smem, st>>>(v->d, adv_image, time_step, mode, loc, done);
   CK(cudaGetLastError());
   return 0;
 }
 
 extern "C" int mgplr_reset(mgplr_venv *v, float *adv_image, float *time_step, void *stream) {
   NEED(v);
+  // small batches are launch-bound: one fused launch; large batches are bandwidth-bound: a dense state-update kernel
+  // (one thread per env) followed by the image kernel beats 4 busy threads per CTA
+  if (adv_image && v->d.N <= kFuseAdvMaxEnvs) return launch_adv_image(v, adv_image, time_step, 1, nullptr, nullptr, st);
   k_reset<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d);
   CK(cudaGetLastError());
-  return launch_adv_image(v, adv_image, time_step, st);
+  if (adv_image) return launch_adv_image(v, adv_image, time_step, 0, nullptr, nullptr, st);
+  return 0;
 }
 
 extern "C" int mgplr_step_adversary(mgplr_venv *v, const int64_t *loc, float *adv_image, float *time_step, uint8_t *done,
                                     void *stream) {
   NEED(v);
   if (!loc) return fail(MGPLR_E_BADARG, "loc is NULL");
+  if (adv_image && v->d.N <= kFuseAdvMaxEnvs) return launch_adv_image(v, adv_image, time_step, 2, loc, done, st);
   k_step_adversary<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, loc, done);
   CK(cudaGetLastError());
-  return launch_adv_image(v, adv_image, time_step, st);
+  if (adv_image) return launch_adv_image(v, adv_image, time_step, 0, nullptr, nullptr, st);
+  return 0;
 }
 
 static OutPtrs outptrs(const mgplr_step_out *o) {
