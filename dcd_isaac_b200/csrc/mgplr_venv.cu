@@ -143,12 +143,14 @@ constexpr int kAdvGroup = 4;
 constexpr int kFuseAdvMaxEnvs = 16384;
 // mode 0: image only; 1: AdversarialEnv.reset first; 2: step_adversary(loc) first -- the state update of the group's
 // envs runs on the first n_env threads of the same CTA, so reset()/step_adversary() + observation is ONE launch.
+// FUSED is a template parameter so that the image-only instance keeps its small register footprint (occupancy).
+template <bool FUSED>
 __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *time_step, int mode, const int64_t *loc,
                                                    uint8_t *done) {
   extern __shared__ __align__(128) float s_img[];
   const int W = d.c.W, WW = W * W, per_env = 3 * WW;
   const int e0 = blockIdx.x * kAdvGroup, n_env = min(kAdvGroup, d.N - e0);
-  if (mode && (int)threadIdx.x < n_env) {
+  if (FUSED && mode && (int)threadIdx.x < n_env) {
     const int e = e0 + threadIdx.x;
     const Rows R = env_rows(d, e);
     Env s = unpack(d.hot[e]);
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *t
     d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
     if (err) d.err[e] |= err;
   }
-  if (mode) __syncthreads();
+  if (FUSED && mode) __syncthreads();
   for (int i = threadIdx.x; i < n_env * WW; i += blockDim.x) {
     const int k = i / WW, cell = i - k * WW, x = cell / W, y = cell - x * W, e = e0 + k;
     const Env s = unpack(d.hot[e]);
@@ -964,7 +966,9 @@ extern "C" int mgplr_seed(mgplr_venv *v, const uint32_t *limbs_host, const int32
 static int launch_adv_image(mgplr_venv *v, float *adv_image, float *time_step, int mode, const int64_t *loc, uint8_t *done,
                             cudaStream_t st) {
   const size_t smem = (size_t)kAdvGroup * 3 * v->d.c.W * v->d.c.W * sizeof(float);
-  k_adv_image<<<(v->d.N + kAdvGroup - 1) / kAdvGroup, 128, smem, st>>>(v->d, adv_image, time_step, mode, loc, done);
+  const int grid = (v->d.N + kAdvGroup - 1) / kAdvGroup;
+  if (mode) k_adv_image<true><<<grid, 128, smem, st>>>(v->d, adv_image, time_step, mode, loc, done);
+  else k_adv_image<false><<<grid, 128, smem, st>>>(v->d, adv_image, time_step, 0, nullptr, nullptr);
   CK(cudaGetLastError());
   return 0;
 }
