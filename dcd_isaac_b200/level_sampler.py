@@ -71,9 +71,11 @@ class LevelSampler(object):
         self._init_seed_index(seeds)
         self.unseen_seed_weights = np.array([1.] * N)
         self.seed_scores = np.array([0.] * N, dtype=float)
-        self.partial_seed_scores = np.zeros((num_actors, N), dtype=float)
-        self.partial_seed_max_scores = np.ones((num_actors, N), dtype=float) * float('-inf')
-        self.partial_seed_steps = np.zeros((num_actors, N), dtype=np.int32)
+        # The reference's dense [num_actors, N] partial-score arrays (level_sampler.py:80-82) are only ever non-zero for a
+        # rollout that does not end in `done`, which the runner never produces (adversarial_runner.py:530).  They are
+        # allocated on first use so that 10^5 actors x 4000 slots does not cost gigabytes of host memory.
+        self._partials = None
+        self._partials_dirty = False
         self.seed_staleness = np.array([0.] * N, dtype=float)
         self.running_sample_count = 0
         self.next_seed_index = 0
@@ -93,6 +95,26 @@ class LevelSampler(object):
             self.partial_seed_max_scores_buffer = [{} for _ in range(num_actors)]
             self.partial_seed_steps_buffer = [{} for _ in range(num_actors)]
         self._dev = None  # lazily created device mirrors (not pickled)
+
+    # ------------------------------------------------------------------ lazily allocated partial-score arrays
+    def _alloc_partials(self):
+        if self._partials is None:
+            A, N = self.num_actors, self.seed_buffer_size
+            self._partials = (np.zeros((A, N), dtype=float), np.ones((A, N), dtype=float) * float('-inf'),
+                              np.zeros((A, N), dtype=np.int32))
+        return self._partials
+
+    @property
+    def partial_seed_scores(self):
+        return self._alloc_partials()[0]
+
+    @property
+    def partial_seed_max_scores(self):
+        return self._alloc_partials()[1]
+
+    @property
+    def partial_seed_steps(self):
+        return self._alloc_partials()[2]
 
     # ------------------------------------------------------------------ pickling (adversarial_runner.py:214-215)
     def __getstate__(self):
@@ -188,16 +210,20 @@ class LevelSampler(object):
         seed_idx = self.seed2index.get(seed, -1)
         if seed_idx < 0:
             return 0, None
-        partial_score = self.partial_seed_scores[actor_index][seed_idx]
-        partial_max_score = self.partial_seed_max_scores[actor_index][seed_idx]
-        partial_num_steps = self.partial_seed_steps[actor_index][seed_idx]
+        if self._partials is None and done:
+            partial_score, partial_max_score, partial_num_steps = np.float64(0.), float('-inf'), np.int32(0)
+        else:
+            partial_score = self.partial_seed_scores[actor_index][seed_idx]
+            partial_max_score = self.partial_seed_max_scores[actor_index][seed_idx]
+            partial_num_steps = self.partial_seed_steps[actor_index][seed_idx]
         running_num_steps = partial_num_steps + num_steps
         merged_score = partial_score + (score - partial_score) * num_steps / float(running_num_steps)
         merged_max_score = max(partial_max_score, max_score)
         if done:
-            self.partial_seed_scores[actor_index][seed_idx] = 0.
-            self.partial_seed_max_scores[actor_index][seed_idx] = float('-inf')
-            self.partial_seed_steps[actor_index][seed_idx] = 0
+            if self._partials is not None:
+                self.partial_seed_scores[actor_index][seed_idx] = 0.
+                self.partial_seed_max_scores[actor_index][seed_idx] = float('-inf')
+                self.partial_seed_steps[actor_index][seed_idx] = 0
             self.unseen_seed_weights[seed_idx] = 0.
             old_score = self.seed_scores[seed_idx]
             total_score = self.max_score_coef * merged_max_score + (1 - self.max_score_coef) * merged_score
@@ -206,6 +232,7 @@ class LevelSampler(object):
             self.partial_seed_scores[actor_index][seed_idx] = merged_score
             self.partial_seed_max_scores[actor_index][seed_idx] = merged_max_score
             self.partial_seed_steps[actor_index][seed_idx] = running_num_steps
+            self._partials_dirty = True
         return merged_score, seed_idx
 
     @property
@@ -232,8 +259,9 @@ class LevelSampler(object):
                 self.seeds[seed_idx] = seed
                 self.seed2index[seed] = seed_idx
                 self.seed_scores[seed_idx] = merged_score
-                self.partial_seed_scores[:, seed_idx] = 0.
-                self.partial_seed_steps[:, seed_idx] = 0
+                if self._partials is not None:
+                    self.partial_seed_scores[:, seed_idx] = 0.
+                    self.partial_seed_steps[:, seed_idx] = 0
                 self.seed_staleness[seed_idx] = self.running_sample_count - self.seed2timestamp_buffer[seed]
                 self.working_seed_buffer_size = min(self.working_seed_buffer_size + 1, self.seed_buffer_size)
                 if self.track_solvable:
@@ -299,13 +327,90 @@ class LevelSampler(object):
         rec = self.episode_records(rollouts)
         self._apply_episode_records(rec)
 
-    def _apply_episode_records(self, rec):
+    def _apply_episode_records(self, rec, vectorize=None):
+        """Apply episode records in the reference's order.  Records of seeds in the staging set take the order-dependent
+        admission path one by one; the runs between them are independent per buffer slot and are applied with numpy
+        (occurrence by occurrence for a slot that appears several times), which is what makes 10^5 actors practical.
+        Bit-identical to the sequential walk (tests/test_level_sampler_host.py)."""
+        if vectorize is None:
+            vectorize = len(rec) >= 256
+        if (not vectorize) or self._partials_dirty or len(rec) == 0:
+            for r in rec:
+                self._apply_one_record(r)
+            return
+        if (rec['cliffhanger'] == 2).any():  # a not-done tail: partial bookkeeping, sequential
+            for r in rec:
+                self._apply_one_record(r)
+            return
+        n = len(rec)
+        seeds = rec['seed']
+        lo = 0
+        if self.sample_full_distribution and self.staging_seed_set:
+            cand = np.nonzero(np.isin(seeds, np.fromiter(self.staging_seed_set, dtype=np.int64)) & (rec['cliffhanger'] != 1))[0]
+        else:
+            cand = ()
+        for pos in cand:
+            if int(seeds[pos]) not in self.staging_seed_set:
+                continue  # already admitted / rejected by an earlier record of this rollout
+            self._apply_batch(rec[lo:pos])
+            self._apply_one_record(rec[pos])
+            lo = pos + 1
+        self._apply_batch(rec[lo:n])
+
+    def _apply_batch(self, rec):
+        """Vectorised application of records none of whose seeds is in the staging set (all `done`)."""
+        rec = rec[rec['cliffhanger'] == 0]
+        if len(rec) == 0:
+            return
+        if len(self.seed2index) == 0:
+            return
+        keys = np.fromiter(self.seed2index.keys(), dtype=np.int64, count=len(self.seed2index))
+        vals = np.fromiter(self.seed2index.values(), dtype=np.int64, count=len(self.seed2index))
+        order = np.argsort(keys)
+        keys, vals = keys[order], vals[order]
+        s = rec['seed'].astype(np.int64)
+        pos = np.searchsorted(keys, s)
+        pos[pos >= len(keys)] = len(keys) - 1
+        known = keys[pos] == s
+        rec = rec[known]
+        if len(rec) == 0:
+            return
+        idx = vals[pos[known]]
+        # occurrence number of every record within its slot, in record order
+        o = np.argsort(idx, kind='stable')
+        sorted_idx = idx[o]
+        first = np.r_[True, sorted_idx[1:] != sorted_idx[:-1]]
+        start = np.maximum.accumulate(np.where(first, np.arange(len(o)), 0))
+        occ = np.empty(len(o), dtype=np.int64)
+        occ[o] = np.arange(len(o)) - start
+        nsteps = (rec['t_end'] - rec['t_start']).astype(np.float64)
+        mean_s, max_s = rec['mean_score'].astype(np.float64), rec['max_score'].astype(np.float64)
         grounded = self.grounded_values is not None
-        for r in rec:
+        if self.strategy == 'uniform':
+            mean_s, max_s = np.ones_like(mean_s), np.ones_like(max_s)
+        for k in range(int(occ.max()) + 1):
+            m = occ == k
+            i_k, n_k = idx[m], nsteps[m]
+            if grounded:
+                gv = np.maximum(self.grounded_values[i_k], rec['reward_sum'][m].astype(np.float64))
+                score = ((0 + n_k) / n_k) * (gv - rec['value_sum'][m].astype(np.float64) / n_k)
+                mx = gv - rec['value_min'][m].astype(np.float64)
+            else:
+                score, mx = mean_s[m], max_s[m]
+            merged = 0.0 + (score - 0.0) * n_k / n_k
+            total = self.max_score_coef * mx + (1 - self.max_score_coef) * merged
+            self.unseen_seed_weights[i_k] = 0.
+            self.seed_scores[i_k] = (1 - self.alpha) * self.seed_scores[i_k] + self.alpha * total
+            if grounded:
+                self.grounded_values[i_k] = gv
+
+    def _apply_one_record(self, r):
+        grounded = self.grounded_values is not None
+        if True:
             actor, seed_t, n = int(r['actor']), int(r['seed']), int(r['t_end'] - r['t_start'])
             cl = int(r['cliffhanger'])
             if cl == 1:  # cliffhanger episodes are skipped (level_sampler.py:527-528)
-                continue
+                return
             done = cl != 2
             score, max_score, grounded_value = float(r['mean_score']), float(r['max_score']), None
             if self.strategy == 'uniform':
@@ -318,7 +423,7 @@ class LevelSampler(object):
                     grounded_value = max(self.grounded_values[seed_idx], gv_) if seed_idx is not None else gv_
                 if self.sample_full_distribution and seed_t in self.partial_seed_steps_buffer[actor]:
                     partial_steps = self.partial_seed_steps_buffer[actor][seed_t]
-                elif seed_idx is not None:
+                elif seed_idx is not None and self._partials is not None:
                     partial_steps = self.partial_seed_steps[actor][seed_idx]
                 else:
                     partial_steps = 0
@@ -340,11 +445,13 @@ class LevelSampler(object):
         """level_sampler.py:580-599: flush non-zero partial scores as finished episodes with score 0."""
         if not self._has_working_seed_buffer:
             return
-        for actor_index, seed_idx in zip(*np.nonzero(self.partial_seed_scores)):
-            if self.partial_seed_scores[actor_index][seed_idx] != 0:
-                self.update_seed_score(actor_index, self.seeds[seed_idx], 0, float('-inf'), 0)
-        self.partial_seed_scores.fill(0)
-        self.partial_seed_steps.fill(0)
+        if self._partials is not None:
+            for actor_index, seed_idx in zip(*np.nonzero(self.partial_seed_scores)):
+                if self.partial_seed_scores[actor_index][seed_idx] != 0:
+                    self.update_seed_score(actor_index, self.seeds[seed_idx], 0, float('-inf'), 0)
+            self.partial_seed_scores.fill(0)
+            self.partial_seed_steps.fill(0)
+        self._partials_dirty = False
         if self.sample_full_distribution:
             for actor_index in range(self.num_actors):
                 for seed in list(self.partial_seed_scores_buffer[actor_index].keys()):
