@@ -304,13 +304,24 @@ __device__ void mix_staleness(const double *w_score, const double *staleness, co
   __syncthreads();
 }
 
+// `cached` != NULL: the normalised score weights were computed before (mgplr_plr_score_weights) and are reused --
+// scores do not change between the draws of a rollout, only staleness does, so the sort is paid once per update.
 __global__ void __launch_bounds__(1024) k_sample_weights(const double *scores, const double *staleness, const double *unseen, int n,
-                                                         WeightArgs a, double *weights, double *w_score) {
+                                                         WeightArgs a, double *weights, double *w_score, const double *cached) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  Key *keys = reinterpret_cast<Key *>(sm);
+  __shared__ double red[33];
+  if (cached) w_score = const_cast<double *>(cached);
+  else score_weights(scores, unseen, n, a, w_score, keys, red);
+  mix_staleness(w_score, staleness, unseen, n, a, weights, keys, red);
+}
+
+__global__ void __launch_bounds__(1024) k_score_weights(const double *scores, const double *unseen, int n, WeightArgs a,
+                                                        double *w_score) {
   extern __shared__ __align__(16) uint8_t sm[];
   Key *keys = reinterpret_cast<Key *>(sm);
   __shared__ double red[33];
   score_weights(scores, unseen, n, a, w_score, keys, red);
-  mix_staleness(w_score, staleness, unseen, n, a, weights, keys, red);
 }
 
 static double *g_dscratch = nullptr;
@@ -333,12 +344,29 @@ static size_t sort_smem(int n) {
   return (size_t)n2 * sizeof(Key);
 }
 
+static int check_transform(int t);
+static size_t sort_smem(int n);
+static int ensure_dscratch(size_t n);
+
+extern "C" int mgplr_plr_score_weights(const double *scores, const double *unseen, int32_t n, int32_t score_transform,
+                                       double temperature, double eps, double *score_weights, void *stream) {
+  if (!scores || !unseen || !score_weights || n < 1 || n > kMaxBuf)
+    return pfail(MGPLR_E_BADARG, "mgplr_plr_score_weights: bad arguments (n must be in [1, 8192])");
+  if (int rc = check_transform(score_transform)) return rc;
+  const size_t smem = sort_smem(n);
+  PCK(cudaFuncSetAttribute(k_score_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const WeightArgs a{score_transform, 0, temperature, eps, 0.0, 1.0};
+  k_score_weights<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, unseen, n, a, score_weights);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
 static int check_transform(int t) { return (t >= 0 && t <= 2) ? 0 : pfail(MGPLR_E_UNSUPPORTED, "transform must be 0 constant, 1 rank or 2 power"); }
 
 extern "C" int mgplr_plr_sample_weights(const double *scores, const double *staleness, const double *unseen, int32_t n,
                                         int32_t score_transform, double temperature, double eps, double staleness_coef,
-                                        int32_t staleness_transform, double staleness_temperature, double *weights,
-                                        void *stream) {
+                                        int32_t staleness_transform, double staleness_temperature, const double *score_weights_in,
+                                        double *weights, void *stream) {
   if (!scores || !staleness || !unseen || !weights || n < 1 || n > kMaxBuf)
     return pfail(MGPLR_E_BADARG, "mgplr_plr_sample_weights: bad arguments (n must be in [1, 8192])");
   if (int rc = check_transform(score_transform)) return rc;
@@ -347,7 +375,7 @@ extern "C" int mgplr_plr_sample_weights(const double *scores, const double *stal
   const size_t smem = sort_smem(n);
   PCK(cudaFuncSetAttribute(k_sample_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const WeightArgs a{score_transform, staleness_transform, temperature, eps, staleness_coef, staleness_temperature};
-  k_sample_weights<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, a, weights, g_dscratch);
+  k_sample_weights<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, a, weights, g_dscratch, score_weights_in);
   PCK(cudaGetLastError());
   return 0;
 }
@@ -357,13 +385,14 @@ extern "C" int mgplr_plr_sample_weights(const double *scores, const double *stal
 // cumsum -> /cdf[-1] -> searchsorted(u, side='right') = #{cdf <= u}.
 __global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, double *staleness, const double *unseen, int n,
                                                         WeightArgs a, const double *u, int n_draws, int32_t *out_index,
-                                                        double *w_rank, double *weights) {
+                                                        double *w_rank, double *weights, const double *cached) {
   extern __shared__ __align__(16) uint8_t sm[];
   Key *keys = reinterpret_cast<Key *>(sm);
   __shared__ double red[33];
   __shared__ double wsum[32];
   __shared__ int s_pick;
-  score_weights(scores, unseen, n, a, w_rank, keys, red);
+  if (cached) w_rank = const_cast<double *>(cached);
+  else score_weights(scores, unseen, n, a, w_rank, keys, red);
   const double coef = a.coef;
   // contiguous chunk per thread so the scan is a per-thread serial cumsum + a block scan of chunk sums
   const int per = (n + blockDim.x - 1) / blockDim.x;
@@ -410,8 +439,8 @@ __global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, do
 
 extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, const double *unseen, int32_t n,
                                        int32_t score_transform, double temperature, double eps, double staleness_coef,
-                                       int32_t staleness_transform, double staleness_temperature, const double *u,
-                                       int32_t n_draws, int32_t *out_index, void *stream) {
+                                       int32_t staleness_transform, double staleness_temperature, const double *score_weights_in,
+                                       const double *u, int32_t n_draws, int32_t *out_index, void *stream) {
   if (!scores || !staleness || !unseen || !u || !out_index || n < 1 || n > kMaxBuf || n_draws < 1)
     return pfail(MGPLR_E_BADARG, "mgplr_plr_sample_replay: bad arguments (n must be in [1, 8192])");
   if (int rc = check_transform(score_transform)) return rc;
@@ -421,7 +450,7 @@ extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, 
   PCK(cudaFuncSetAttribute(k_sample_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const WeightArgs a{score_transform, staleness_transform, temperature, eps, staleness_coef, staleness_temperature};
   k_sample_replay<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, a, u, n_draws, out_index, g_dscratch,
-                                                          g_dscratch + kMaxBuf);
+                                                          g_dscratch + kMaxBuf, score_weights_in);
   PCK(cudaGetLastError());
   return 0;
 }

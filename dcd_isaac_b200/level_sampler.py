@@ -143,15 +143,27 @@ class LevelSampler(object):
                 'stale': torch.zeros(N, dtype=torch.float64, device=dev),
                 'unseen': torch.zeros(N, dtype=torch.float64, device=dev),
                 'weights': torch.zeros(N, dtype=torch.float64, device=dev),
+                'w_score': torch.zeros(N, dtype=torch.float64, device=dev),
+                'w_key': None,   # (scores, unseen) the cached score weights were computed from
             }
         return self._dev
 
     def _upload(self):
+        """Host arrays -> device mirrors.  Scores / unseen flags only change in update paths, so their upload and the score
+        half of the weights (the sort) are skipped while they are unchanged; staleness is uploaded every time."""
+        from . import _lib
         d = self._device_ctx()
         t = d['torch']
-        d['scores'].copy_(t.from_numpy(np.ascontiguousarray(self.seed_scores, dtype=np.float64)))
         d['stale'].copy_(t.from_numpy(np.ascontiguousarray(self.seed_staleness, dtype=np.float64)))
-        d['unseen'].copy_(t.from_numpy(np.ascontiguousarray(self.unseen_seed_weights, dtype=np.float64)))
+        key = d['w_key']
+        if key is None or not (np.array_equal(key[0], self.seed_scores) and np.array_equal(key[1], self.unseen_seed_weights)):
+            d['scores'].copy_(t.from_numpy(np.ascontiguousarray(self.seed_scores, dtype=np.float64)))
+            d['unseen'].copy_(t.from_numpy(np.ascontiguousarray(self.unseen_seed_weights, dtype=np.float64)))
+            st, temp, eps, _, _, _ = self._weight_args()
+            _lib.check(d['lib'].mgplr_plr_score_weights(_lib.ptr(d['scores']), _lib.ptr(d['unseen']), self.seed_buffer_size, st,
+                                                        temp, eps, _lib.ptr(d['w_score']),
+                                                        t.cuda.current_stream(d['dev']).cuda_stream), 'mgplr_plr_score_weights')
+            d['w_key'] = (self.seed_scores.copy(), self.unseen_seed_weights.copy())
         return d
 
     def _transform_code(self, name):
@@ -512,7 +524,8 @@ class LevelSampler(object):
         st, temp, eps, coef, stt, stemp = self._weight_args()
         _lib.check(d['lib'].mgplr_plr_sample_weights(_lib.ptr(d['scores']), _lib.ptr(d['stale']), _lib.ptr(d['unseen']),
                                                      self.seed_buffer_size, st, temp, eps, coef, stt, stemp,
-                                                     _lib.ptr(d['weights']), t.cuda.current_stream(d['dev']).cuda_stream),
+                                                     _lib.ptr(d['w_score']), _lib.ptr(d['weights']),
+                                                     t.cuda.current_stream(d['dev']).cuda_stream),
                    'mgplr_plr_sample_weights')
         return d['weights'].cpu().numpy().copy()
 
@@ -528,8 +541,8 @@ class LevelSampler(object):
         out = t.zeros(n, dtype=t.int32, device=d['dev'])
         st, temp, eps, coef, stt, stemp = self._weight_args()
         _lib.check(d['lib'].mgplr_plr_sample_replay(_lib.ptr(d['scores']), _lib.ptr(d['stale']), _lib.ptr(d['unseen']),
-                                                    self.seed_buffer_size, st, temp, eps, coef, stt, stemp, _lib.ptr(du), n,
-                                                    _lib.ptr(out), t.cuda.current_stream(d['dev']).cuda_stream),
+                                                    self.seed_buffer_size, st, temp, eps, coef, stt, stemp, _lib.ptr(d['w_score']),
+                                                    _lib.ptr(du), n, _lib.ptr(out), t.cuda.current_stream(d['dev']).cuda_stream),
                    'mgplr_plr_sample_replay')
         idx = out.cpu().numpy()
         if self.staleness_coef > 0:

@@ -223,15 +223,22 @@ int mgplr_plr_episode_scores(const float *masks, const float *cliffhanger_masks,
  * rank transform are broken by index (higher index = better rank): np.flip(np.argsort(scores, kind='stable')). */
 int mgplr_plr_sample_weights(const double *scores, const double *staleness, const double *unseen, int32_t n,
                              int32_t score_transform, double temperature, double eps, double staleness_coef,
-                             int32_t staleness_transform, double staleness_temperature, double *weights, void *stream);
+                             int32_t staleness_transform, double staleness_temperature, const double *score_weights,
+                             double *weights, void *stream);
+
+/* The score half of sample_weights alone: normalise(transform(scores) * seen) -> score_weights f64 [n].  Scores only
+ * change in update_with_rollouts, so callers compute this once per update and pass it as `score_weights` to the two
+ * functions around it (NULL there = recompute); only the staleness half is then redone per draw. */
+int mgplr_plr_score_weights(const double *scores, const double *unseen, int32_t n, int32_t score_transform,
+                            double temperature, double eps, double *score_weights, void *stream);
 
 /* n_draws sequential _sample_replay_level draws (level_sampler.py:664-680 + 601-604) with recorded uniforms
  * u f64 [n_draws] (np.random.choice's single random_sample each): staleness is updated between draws
  * exactly as the reference does.  out_index i32 [n_draws]; staleness f64 [n] updated in place. */
 int mgplr_plr_sample_replay(const double *scores, double *staleness, const double *unseen, int32_t n,
                             int32_t score_transform, double temperature, double eps, double staleness_coef,
-                            int32_t staleness_transform, double staleness_temperature, const double *u, int32_t n_draws,
-                            int32_t *out_index, void *stream);
+                            int32_t staleness_transform, double staleness_temperature, const double *score_weights,
+                            const double *u, int32_t n_draws, int32_t *out_index, void *stream);
 
 #ifdef __cplusplus
 }

@@ -129,11 +129,11 @@ def main():
     stl = torch.floor(torch.rand(nb, dtype=torch.float64, device='cuda') * 50)
     un = (torch.rand(nb, device='cuda') < 0.1).double()
     wt = torch.zeros(nb, dtype=torch.float64, device='cuda')
-    t = timeit(lambda: check(L.mgplr_plr_sample_weights(ptr(sc), ptr(stl), ptr(un), nb, 1, 0.3, 0.0, 0.3, 2, 1.0, ptr(wt), st())))
+    t = timeit(lambda: check(L.mgplr_plr_sample_weights(ptr(sc), ptr(stl), ptr(un), nb, 1, 0.3, 0.0, 0.3, 2, 1.0, None, ptr(wt), st())))
     rec('sample_weights (buffer 4000, rank + staleness)', t, 1, nb * 8 * 4, 'one CTA, fp64; latency-bound (bitonic sort of 4096 keys)')
     u = torch.rand(32, dtype=torch.float64, device='cuda')
     oi = torch.zeros(32, dtype=torch.int32, device='cuda')
-    t = timeit(lambda: check(L.mgplr_plr_sample_replay(ptr(sc), ptr(stl), ptr(un), nb, 1, 0.3, 0.0, 0.3, 2, 1.0, ptr(u), 32, ptr(oi), st())))
+    t = timeit(lambda: check(L.mgplr_plr_sample_replay(ptr(sc), ptr(stl), ptr(un), nb, 1, 0.3, 0.0, 0.3, 2, 1.0, None, ptr(u), 32, ptr(oi), st())))
     rec('32 sequential sample_replay_level draws (buffer 4000)', t, 32, nb * 8 * 3, 'reference: 20.7 ms on CPU (BASELINE.md)')
     for o_ in out:
         print(json.dumps(o_))
