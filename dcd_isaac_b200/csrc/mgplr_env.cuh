@@ -98,24 +98,25 @@ __device__ __forceinline__ Rows env_rows(const Dev &d, int e) {
 // producing words in place, in order, is output-identical to the batch twist and never stalls a lane for 624
 // dependent iterations.
 // Draws are generated SPECULATIVELY IN BATCHES of 16: the words at offsets 0..15 from the cursor are mutually
-// independent (word j reads state[j], state[j+1], state[j+397]; none is produced inside a batch shorter than
-// 227), so one refill issues 33 independent loads -- one memory round trip instead of one per draw -- and keeps
-// the tempered outputs and the new state words in REGISTERS (two 16-deep shift registers; every index is a
-// compile-time constant, so nothing lives in local memory as long as the users are inlined into their
-// out-of-line rare path).  A state word is written back when its draw is consumed; unconsumed words are simply
-// regenerated by the next refill, so the stream is exactly numpy's.
+// independent (word j reads state[j], state[j+1], state[j+397]; none is produced inside a batch shorter than 227), so
+// one refill issues 33 independent loads -- one memory round trip instead of one per draw.  Tempered outputs and new
+// state words of the batch live in a per-thread column of SHARED memory ([32][threads]: rows 0..15 outputs, 16..31
+// state words; bank = thread), so a draw is two conflict-free LDS and one STG committing that word's state.
+// Unconsumed words are simply regenerated by the next refill, so the stream is exactly numpy's.  Refills are
+// WARP-UNIFORM: when any converged lane runs dry every converged lane refills from its own cursor, which keeps the
+// refill code from being replayed once per lane under divergence (it was 75 % of reset_random's instructions).
 struct Rng {
   static constexpr int kBatch = 16;
   uint32_t *mt, *mti_p, *words_p;
   int N, e;
   uint32_t idx, used;  // cursor (0..623), words consumed since seeding
-  int have;            // unread words in the shift registers
+  int have, pos;       // words in the batch, next unread word
   bool loaded;
-  uint32_t out[kBatch], nst[kBatch];
-  __device__ __forceinline__ Rng(const Dev &dev, int env)
-      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), have(0), loaded(false) {}
-  __device__ __forceinline__ Rng(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env)
-      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), have(0), loaded(false) {}
+  uint32_t *buf;       // this thread's column of the shared scratch
+  int stride;          // threads per row of the scratch
+  __device__ __forceinline__ Rng(const Dev &dev, int env, uint32_t *buf_, int stride_)
+      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), have(0), pos(0), loaded(false),
+        buf(buf_), stride(stride_) {}
   __device__ __forceinline__ void load() {
     if (!loaded) { idx = mti_p[e]; used = words_p[e]; loaded = true; }
   }
@@ -136,34 +137,69 @@ struct Rng {
     for (int u = 0; u < kBatch; u++) {
       uint32_t y = (a & 0x80000000u) | (b[u] & 0x7fffffffu);
       y = c[u] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      nst[u] = y;
+      buf[(kBatch + u) * stride] = y;
       y ^= (y >> 11);
       y ^= (y << 7) & 0x9d2c5680u;
       y ^= (y << 15) & 0xefc60000u;
       y ^= (y >> 18);
-      out[u] = y;
+      buf[u * stride] = y;
       a = b[u];
     }
-    have = kBatch;
+    have = kBatch; pos = 0;
   }
   __device__ __forceinline__ void store() {
     if (loaded) { mti_p[e] = idx; words_p[e] = used; }
   }
   // forget everything (after a re-seed replaced the stream)
-  __device__ __forceinline__ void reset() { loaded = false; have = 0; }
+  __device__ __forceinline__ void reset() { loaded = false; have = 0; pos = 0; }
   __device__ __forceinline__ uint32_t next() {
-    if (have == 0) refill();
-    const uint32_t v = out[0];
-    mt[(size_t)idx * N + e] = nst[0];  // commit this word's new state
+    if (__any_sync(__activemask(), pos >= have)) refill();
+    const uint32_t v = buf[pos * stride];
+    mt[(size_t)idx * N + e] = buf[(kBatch + pos) * stride];  // commit this word's new state
     idx = (idx + 1 == 624) ? 0 : idx + 1;
     used++;
-    have--;
-#pragma unroll
-    for (int u = 0; u + 1 < kBatch; u++) { out[u] = out[u + 1]; nst[u] = nst[u + 1]; }
+    pos++;
     return v;
   }
-  // RandomState.randint(lo, hi): masked rejection on 32-bit words, no draw when hi-lo == 1
-  // (gym_minigrid MiniGridEnv._rand_int; call sites multigrid.py:603-606, adversarial.py:205,567).
+  __device__ __forceinline__ int randint(int lo, int hi) {
+    const uint32_t rng = (uint32_t)(hi - lo - 1);
+    if (rng == 0) return lo;
+    const uint32_t mask = 0xffffffffu >> __clz(rng);
+    uint32_t v;
+    do { v = next() & mask; } while (v > rng);
+    return lo + (int)v;
+  }
+};
+
+// One word per draw, no scratch: for the rare paths of the hot kernel that cannot spare shared memory.
+struct RngSlow {
+  uint32_t *mt, *mti_p, *words_p;
+  int N, e;
+  uint32_t idx, used;
+  bool loaded;
+  __device__ __forceinline__ RngSlow(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env)
+      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), loaded(false) {}
+  __device__ __forceinline__ void load() {
+    if (!loaded) { idx = mti_p[e]; used = words_p[e]; loaded = true; }
+  }
+  __device__ __forceinline__ void store() {
+    if (loaded) { mti_p[e] = idx; words_p[e] = used; }
+  }
+  __device__ __forceinline__ void reset() { loaded = false; }
+  __device__ __forceinline__ uint32_t next() {
+    load();
+    const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
+    const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    mt[(size_t)i * N + e] = y;
+    idx = i1; used++;
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
   __device__ __forceinline__ int randint(int lo, int hi) {
     const uint32_t rng = (uint32_t)(hi - lo - 1);
     if (rng == 0) return lo;
@@ -221,7 +257,8 @@ __device__ inline void gen_grid(const Rows &R, int W) {
 
 // place_obj over the whole grid (multigrid.py:565-632): x=_rand_int(0,W), y=_rand_int(0,H); reject
 // non-empty cells; raise after max_tries (max_tries < 0: unbounded).
-__device__ __forceinline__ bool place_random(const Rows &R, const Env &e, Rng &rng, int W, int max_tries, int &ox, int &oy) {
+template <typename RNG>
+__device__ __forceinline__ bool place_random(const Rows &R, const Env &e, RNG &rng, int W, int max_tries, int &ox, int &oy) {
   int tries = 0;
   for (;;) {
     if (max_tries >= 0 && tries > max_tries) return false;
@@ -235,14 +272,16 @@ __device__ __forceinline__ bool place_random(const Rows &R, const Env &e, Rng &r
 
 // Replay `count` deferred goal respawns (place_one_agent over the whole grid with the agent off the grid).
 // Returns the last position as x | y<<8.
-__device__ __forceinline__ uint32_t replay_respawns(const Rows &R, int gx, int gy, Rng &rng, int W, int count) {
+template <typename RNG>
+__device__ __forceinline__ uint32_t replay_respawns(const Rows &R, int gx, int gy, RNG &rng, int W, int count) {
   Env t{};
   t.gx = gx; t.gy = gy; t.has_agent = 0;
   int px = 0, py = 0;
   for (int i = 0; i < count; i++) place_random(R, t, rng, W, -1, px, py);
   return (uint32_t)px | ((uint32_t)py << 8);
 }
-__device__ __forceinline__ void flush_pending(const Rows &R, Env &e, Rng &rng, int W) {
+template <typename RNG>
+__device__ __forceinline__ void flush_pending(const Rows &R, Env &e, RNG &rng, int W) {
   if (e.pending) { replay_respawns(R, e.gx, e.gy, rng, W, e.pending); e.pending = 0; }
 }
 

@@ -51,7 +51,10 @@ struct mgplr_venv {
 
 // dynamic shared memory: `bufs` obs tiles [TILE][75] f32 then wall rows [W][TILE] u32
 constexpr int kDonePrefix = 2047;  // done records fetched together with the count in one D2H copy
-static size_t step_smem_bytes(int W, int tile, int bufs) { return (size_t)bufs * tile * kObsFloats * 4 + (size_t)W * tile * 4; }
+// (+ the batched-RNG scratch [32][tile] of the in-kernel reset_random)
+static size_t step_smem_bytes(int W, int tile, int bufs, bool rr = true) {
+  return (size_t)bufs * tile * kObsFloats * 4 + (size_t)W * tile * 4 + (rr ? (size_t)32 * tile * 4 : 0);
+}
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +80,10 @@ __device__ __noinline__ void emit_direct(const Rows &R, const Env &e, const Cfg 
 }
 
 // ------------------------------------------------------------------------------------------ kernels: level ops
+// shared scratch of the batched RNG for 128-thread level kernels: [32][128] words, one column per thread
+#define RNG_SCRATCH() __shared__ uint32_t s_rng_[32 * 128]
+#define RNG_OF(d, e) Rng((d), (e), s_rng_ + threadIdx.x, 128)
+
 __global__ void k_init(Dev d) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
@@ -106,26 +113,28 @@ __global__ void k_seed(Dev d, const uint32_t *scratch, int n, int stride, int ha
 }
 
 __global__ void k_reset(Dev d) {
+  RNG_SCRATCH();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e];
   int4 met;
-  Rng rng(d, e);
+  Rng rng = RNG_OF(d, e);
   reset_adversary(R, s, adv, met, rng, d.c);
   rng.store();
   d.hot[e] = pack(s); d.adv[e] = adv; d.metrics[e] = met;
 }
 
 __global__ void k_step_adversary(Dev d, const int64_t *loc, uint8_t *done) {
+  RNG_SCRATCH();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e], err = 0;
   int4 met = d.metrics[e];
-  Rng rng(d, e);
+  Rng rng = RNG_OF(d, e);
   const long long l = loc[e];
   const bool dn = step_adversary(R, s, adv, met, rng, d.c, (l < 0 || l > 0x7fffffff) ? -1 : (int)l, err);
   rng.store();
@@ -147,6 +156,7 @@ constexpr int kFuseAdvMaxEnvs = 16384;
 template <bool FUSED>
 __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *time_step, int mode, const int64_t *loc,
                                                    uint8_t *done) {
+  RNG_SCRATCH();
   extern __shared__ __align__(128) float s_img[];
   const int W = d.c.W, WW = W * W, per_env = 3 * WW;
   const int e0 = blockIdx.x * kAdvGroup, n_env = min(kAdvGroup, d.N - e0);
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *t
     Env s = unpack(d.hot[e]);
     uint32_t adv = d.adv[e], err = 0;
     int4 met = d.metrics[e];
-    Rng rng(d, e);
+    Rng rng = RNG_OF(d, e);
     if (mode == 1) reset_adversary(R, s, adv, met, rng, d.c);
     else {
       const long long l = loc[e];
@@ -197,12 +207,13 @@ __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *t
 }
 
 __global__ void k_reset_agent(Dev d, OutPtrs o) {
+  RNG_SCRATCH();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   if (s.pending) {  // replay the deferred respawn draws of the last rollout (level unchanged since)
-    Rng rng(d, e);
+    Rng rng = RNG_OF(d, e);
     flush_pending(R, s, rng, d.c.W);
     rng.store();
   }
@@ -213,6 +224,7 @@ __global__ void k_reset_agent(Dev d, OutPtrs o) {
 }
 
 __global__ void __launch_bounds__(128) k_reset_random(Dev d, const int32_t *n_walls, OutPtrs o) {
+  RNG_SCRATCH();
   extern __shared__ uint32_t s_rr[];  // [W][128]: the grid is rebuilt in shared memory and written back once
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
@@ -223,7 +235,7 @@ __global__ void __launch_bounds__(128) k_reset_random(Dev d, const int32_t *n_wa
   if (s.pending) for (int r = 0; r < W; r++) R.set(r, G.get(r));  // deferred respawns replay against the old level
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
-  Rng rng(d, e);
+  Rng rng = RNG_OF(d, e);
   const int nw = (d.c.resample && n_walls) ? n_walls[e] : -1;
   reset_random(R, s, adv, met, rng, d, e, nw, err);
   rng.store();
@@ -237,6 +249,7 @@ __global__ void __launch_bounds__(128) k_reset_random(Dev d, const int32_t *n_wa
 // reset_to_level, byte form (adversarial.py:271-294, multigrid.py:264-280): reset() draws a FRESH start
 // direction; the encoding's agent dir byte is not restored.
 __global__ void k_reset_to_encoding(Dev d, const uint8_t *enc, const int32_t *index, int n, OutPtrs o) {
+  RNG_SCRATCH();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int e = index ? index[k] : k;
@@ -246,7 +259,7 @@ __global__ void k_reset_to_encoding(Dev d, const uint8_t *enc, const int32_t *in
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e];
   int4 met;
-  Rng rng(d, e);
+  Rng rng = RNG_OF(d, e);
   reset_adversary(R, s, adv, met, rng, d.c);
   rng.store();
   const uint8_t *src = enc + (size_t)k * W * W * 3;
@@ -300,6 +313,7 @@ __global__ void k_load_levels(Dev d, const uint8_t *enc, int n_levels, const int
 
 // reset_to_level, action-string form (adversarial.py:274-283).
 __global__ void k_reset_to_actions(Dev d, const int32_t *locs, int len, const int32_t *index, int n, OutPtrs o) {
+  RNG_SCRATCH();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int e = index ? index[k] : k;
@@ -308,7 +322,7 @@ __global__ void k_reset_to_actions(Dev d, const int32_t *locs, int len, const in
   Env s = unpack(d.hot[e]);
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
-  Rng rng(d, e);
+  Rng rng = RNG_OF(d, e);
   reset_adversary(R, s, adv, met, rng, d.c);
   if (d.c.resample) adv = (adv & ~(0xfffu << 12)) | ((uint32_t)len << 12);
   for (int i = 0; i < len; i++) {
@@ -335,12 +349,13 @@ __device__ __forceinline__ int count_free(const Rows &R, const Env &s, int W, in
 // mutate_level, edit phase (adversarial.py:317-368).
 __global__ void k_mutate_edits(Dev d, const int32_t *locs, const int32_t *ops, const int32_t *n_edits, int max_edits,
                                uint8_t *need, int32_t *n_free) {
+  RNG_SCRATCH();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   const int W = d.c.W, I = W - 2;
   const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
-  if (s.pending) { Rng rng(d, e); flush_pending(R, s, rng, W); rng.store(); }
+  if (s.pending) { Rng rng = RNG_OF(d, e); flush_pending(R, s, rng, W); rng.store(); }
   const int k = n_edits[e];
   for (int n = 0; n < k && n < max_edits; n++) {
     const int loc = locs[(size_t)e * max_edits + n], op = ops[(size_t)e * max_edits + n];
@@ -405,12 +420,13 @@ __global__ void k_encode(Dev d, uint8_t *enc) {
 
 // replay deferred respawn draws so that the RNG state seen by the host is the reference's
 __global__ void k_flush(Dev d) {
+  RNG_SCRATCH();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   Env s = unpack(d.hot[e]);
   if (!s.pending) return;
   const Rows R = env_rows(d, e);
-  Rng rng(d, e);
+  Rng rng = RNG_OF(d, e);
   flush_pending(R, s, rng, d.c.W);
   rng.store();
   d.hot[e] = pack(s);
@@ -454,7 +470,7 @@ struct StepArgs {
 // ones first, see Env::pending).  Returns the last one as x | y<<8.
 __device__ __noinline__ uint32_t rare_respawn(uint32_t *mt, uint32_t *mti, uint32_t *words, int N, int e, uint32_t *rows,
                                               int stride, int W, int gx, int gy, int count) {
-  Rng rng(mt, mti, words, N, e);
+  RngSlow rng(mt, mti, words, N, e);
   const uint32_t p = replay_respawns(Rows{rows, stride}, gx, gy, rng, W, count);
   rng.store();
   return p;
@@ -471,11 +487,12 @@ __device__ __noinline__ void rare_emit_trunc(uint32_t *rows, int stride, uint4 h
 }
 
 // worker.step_env's reset_random branch (parallel_wrappers.py:30-33)
-__device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int stride, uint4 hot, int e, int n_walls) {
+__device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int stride, uint4 hot, int e, int n_walls, uint32_t *rng_col,
+                                                int rng_stride) {
   Env s = unpack(hot);
   uint32_t adv = d.adv[e], err = 0;
   int4 met;
-  Rng rng(d, e);
+  Rng rng(d, e, rng_col, rng_stride);
   reset_random(Rows{rows, stride}, s, adv, met, rng, d, e, n_walls, err);
   rng.store();
   d.adv[e] = adv; d.metrics[e] = met;
@@ -487,7 +504,7 @@ __device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int strid
 // In reset_agent mode a goal's respawn draw is DEFERRED (Env::pending, mgplr_env.cuh).
 template <bool SEE, bool RR, typename EXT>
 __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int stride, Env &s, int e, int a, const StepArgs &A,
-                                             float *s_obs, float &rew_out, bool &rows_dirty) {
+                                             float *s_obs, float &rew_out, bool &rows_dirty, uint32_t *rng_col, int rng_stride) {
   const Cfg &c = d.c;
   const Rows R{rows, stride};
   uint32_t flags = 0;
@@ -528,7 +545,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
     s.ep_ret = 0.f; s.ep_len = 0;
     // worker.step_env (parallel_wrappers.py:27-37)
     if (RR) {
-      s = unpack(rare_reset_random(d, rows, stride, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1));
+      s = unpack(rare_reset_random(d, rows, stride, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1, rng_col, rng_stride));
       rows_dirty = true;
     } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
   } else if ((A.last_step & 3) == 3 && want_trunc) {
@@ -639,8 +656,9 @@ __device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, 
 //   * the 32x75 float32 observations of tile k leave shared memory as one 9600-byte bulk asynchronous store
 //     that drains while tile k+1 steps and renders; the single obs buffer is only re-acquired
 //     (cp.async.bulk.wait_group.read) right before tile k+1 emits.
-__host__ __device__ inline size_t warp_smem_bytes(int W) {
-  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + 127) & ~(size_t)127;
+// per warp: obs tile | two row buffers | two mbarriers | (DR variant) batched-RNG scratch [32][32]
+__host__ __device__ inline size_t warp_smem_bytes(int W, bool rr) {
+  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + (rr ? 32 * kWarpTile * 4 : 0) + 127) & ~(size_t)127;
 }
 
 __device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot, int W, int see, uint8_t *image_u8, int e) {
@@ -666,10 +684,11 @@ __global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = d.c.W, N = d.N;
   const int wpc = blockDim.x >> 5;
-  uint8_t *wbase = smem + (size_t)warp * warp_smem_bytes(W);
+  uint8_t *wbase = smem + (size_t)warp * warp_smem_bytes(W, RR);
   float *s_obs = reinterpret_cast<float *>(wbase);
   uint32_t *s_rows = reinterpret_cast<uint32_t *>(wbase + (size_t)kWarpTile * kObsFloats * 4);
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 2 * W * kWarpTile);
+  uint32_t *s_rng = reinterpret_cast<uint32_t *>(bars + 2);  // only present (and used) when RR
   const int total = gridDim.x * wpc;
   int tile = blockIdx.x * wpc + warp;
   if (tile >= n_tiles) return;
@@ -743,7 +762,8 @@ __global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
         s.ep_ret = 0.f; s.ep_len = 0;
         if (RR) {  // worker.step_env (parallel_wrappers.py:27-37)
-          s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1));
+          s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1,
+                                       s_rng + lane, kWarpTile));
           dirty = true;
         } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
       } else if ((A.last_step & 3) == 3 && want_trunc) {
@@ -797,6 +817,7 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
   if (valid) s = unpack(d.hot[e]);
   mbar_wait(&bar, 0);
   uint32_t *my_rows = s_rows + (tid >> 5) * W * kWarpTile + (tid & 31);  // [sub][W][32]
+  uint32_t *s_rng = s_rows + (TILE / kWarpTile) * W * kWarpTile;           // [32][TILE]
   bool dirty = false;
   for (int t = 0; t < T; t++) {
     StepArgs A = A0;
@@ -821,7 +842,7 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
     if (valid) {
       float rew;
       const uint32_t flags = step_one<SEE, RR, EXT>(d, my_rows, kWarpTile, s, e, (int)actions[off + e], A, s_obs + tid * kObsFloats,
-                                                    rew, dirty);
+                                                    rew, dirty, s_rng + tid, TILE);
       write_step_scalars(A, e, s, flags, rew);
     }
     if (A.o.image) store_obs_tile(A.o.image + (size_t)base * kObsFloats, s_obs, n_tile, false);
@@ -897,8 +918,9 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device));
   {
     const int W = cfg->width;
-    const int step_smem = (int)(4 * warp_smem_bytes(W));
-#define SET_STEP(SEE, RR, EXT) CK(cudaFuncSetAttribute(k_step_env<SEE, RR, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, step_smem));
+#define SET_STEP(SEE, RR, EXT)                                                                          \
+  CK(cudaFuncSetAttribute(k_step_env<SEE, RR, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                          (int)(4 * warp_smem_bytes(W, RR))));
 #define SET_ROLL(SEE, RR, TL, EXT) \
   CK(cudaFuncSetAttribute(k_rollout<SEE, RR, TL, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes(W, TL, 2)));
 #define SET_ALL(EXT)                                                                                  \
@@ -1071,7 +1093,7 @@ static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_rando
 static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st) {
   // persistent grid: as many 4-warp CTAs as fit on the chip (shared-memory bound), capped by the tile count
   const int W = v->d.c.W, wpc = 4;
-  const size_t smem = wpc * warp_smem_bytes(W);
+  const size_t smem = wpc * warp_smem_bytes(W, reset_random != 0);
   const int n_tiles = (v->d.N + kWarpTile - 1) / kWarpTile;
   const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
   int grid = v->sm_count * per_sm;
@@ -1146,7 +1168,7 @@ extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, i
   if (out_t0) A.o = *out_t0;
   const int tile = 64;
   const int grid = grid_for(v->d.N, tile);
-  const size_t smem = step_smem_bytes(v->d.c.W, tile, 2);
+  const size_t smem = step_smem_bytes(v->d.c.W, tile, 2, reset_random != 0);
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = v->d.c.W <= 24;
 #define LAUNCH(SEE, RR, EXT) k_rollout<SEE, RR, 64, EXT><<<grid, 64, smem, st>>>(v->d, actions, T, A)
 #define BY_MODE(EXT)                                  \

@@ -49,6 +49,27 @@ int main(int argc, char **argv) {
     }
   };
   steps(); CKC(cudaStreamSynchronize(st));
+  if (getenv("KB_TRACE")) {  // per-launch timing of one rollout (no graph): print the slow launches
+    std::vector<cudaEvent_t> ev(T + 2);
+    for (auto &e : ev) cudaEventCreate(&e);
+    mgplr_step_out ro = {}; ro.image = img; ro.direction = dir;
+    cudaEventRecord(ev[0], st);
+    CKM(mgplr_reset_agent(v, &ro, st));
+    cudaEventRecord(ev[1], st);
+    for (int t = 0; t < T; t++) {
+      mgplr_step_out o = {};
+      o.image = img + (size_t)(t + 1) * N * 75; o.reward = rew + (size_t)t * N; o.flags = fl + (size_t)t * N;
+      CKM(mgplr_step_env(v, act + (size_t)t * N, rr, nullptr, 0, &o, st));
+      cudaEventRecord(ev[t + 2], st);
+    }
+    CKC(cudaStreamSynchronize(st));
+    float ms0; cudaEventElapsedTime(&ms0, ev[0], ev[1]);
+    printf("trace: reset_agent %.1f us\n", ms0 * 1e3);
+    for (int t = 0; t < T; t++) {
+      float msx; cudaEventElapsedTime(&msx, ev[t + 1], ev[t + 2]);
+      if (msx * 1e3 > 80.0 || t < 2) printf("trace: step %d  %.1f us\n", t, msx * 1e3);
+    }
+  }
   cudaGraph_t g; cudaGraphExec_t ge;
   CKC(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal)); steps(); CKC(cudaStreamEndCapture(st, &g));
   CKC(cudaGraphInstantiate(&ge, g, 0));
