@@ -931,6 +931,12 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
 #undef SET_ROLL
 #undef SET_STEP
   }
+  {  // kernels whose dynamic shared memory can exceed the 48 KB default at the widest grids
+    const int adv_smem = (int)((size_t)kAdvGroup * 3 * cfg->width * cfg->width * sizeof(float));
+    CK(cudaFuncSetAttribute(k_adv_image<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem));
+    CK(cudaFuncSetAttribute(k_adv_image<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem));
+    CK(cudaFuncSetAttribute(k_reset_random, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->width * 128 * 4));
+  }
   CK(cudaMemset(d.mt, 0, 624 * N * sizeof(uint32_t)));
   k_init<<<grid_for(num_envs, 256), 256>>>(d);
   CK(cudaGetLastError());
