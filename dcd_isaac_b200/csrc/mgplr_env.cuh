@@ -39,6 +39,7 @@ struct Dev {
   uint32_t *limbs;   // [3][N] seed limbs lo, hi, count (re-seed of fixed_environment)
   uint32_t *words;   // [N] MT words consumed since seeding
   uint32_t *err;     // [N] sticky error bits
+  uint32_t *sched;   // [2] dynamic tile scheduler of the step kernel: next tile, warps finished (self-resetting)
 };
 
 // `pending` = goal respawns (multigrid.py:821-838) whose env-RNG draws have not been made yet.  A respawn draw
@@ -422,6 +423,162 @@ __device__ __forceinline__ void reset_random(const Rows &R, Env &e, uint32_t &ad
   adv = 0u | (adv_max << 12) | (sampled << 24);
   met = compute_metrics(R, e, W, true);
   if (!reset_agent(e)) err |= kErrNoStart;
+}
+
+// ---------------------------------------------------------------------------------------------
+// WARP-COOPERATIVE reset_random: all 32 lanes rebuild ONE env's level.  Inside the step kernel a tile usually has
+// zero or one finished env; running the lane-serial reset_random there costs the whole ~25 k-instruction generation
+// for 1/32 of the lanes.  Here the 32 lanes share the work of one env instead: lane j generates MT19937 word j of a
+// 32-word batch (one memory round trip per 32 draws), lane y owns row y of the grid (gen_grid, wall count and the
+// flood fill become a handful of shuffles per iteration), and the (inherently serial) rejection sampling runs
+// warp-uniformly on broadcast values.  Draw order and count are exactly reset_random()'s.
+struct CoopRng {
+  uint32_t *mt, *mti_p, *words_p;
+  int N, e, lane;
+  uint32_t idx, used;
+  int have, pos;
+  uint32_t w_out, w_nst;
+  __device__ __forceinline__ CoopRng(const Dev &dev, int env, int lane_)
+      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), lane(lane_), have(0), pos(0), w_out(0), w_nst(0) {
+    idx = mti_p[e]; used = words_p[e];
+  }
+  __device__ __forceinline__ void commit() {  // write back the state words of the consumed draws
+    if (lane < pos) {
+      uint32_t i = idx + lane;
+      if (i >= 624) i -= 624;
+      mt[(size_t)i * N + e] = w_nst;
+    }
+    idx += pos;
+    if (idx >= 624) idx -= 624;
+    used += pos;
+    pos = 0; have = 0;
+  }
+  __device__ __forceinline__ void refill() {
+    commit();
+    __syncwarp();
+    uint32_t i = idx + lane, i1 = i + 1, im = i + 397;
+    if (i >= 624) i -= 624;
+    if (i1 >= 624) i1 -= 624;
+    if (im >= 624) im -= 624;
+    if (im >= 624) im -= 624;
+    const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
+    uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    w_nst = y;
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    w_out = y;
+    have = 32;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    if (pos >= have) refill();
+    const uint32_t v = __shfl_sync(0xffffffffu, w_out, pos);
+    pos++;
+    return v;
+  }
+  __device__ __forceinline__ int randint(int lo, int hi) {
+    const uint32_t rng = (uint32_t)(hi - lo - 1);
+    if (rng == 0) return lo;
+    const uint32_t mask = 0xffffffffu >> __clz(rng);
+    uint32_t v;
+    do { v = next() & mask; } while (v > rng);
+    return lo + (int)v;
+  }
+  __device__ __forceinline__ void store() {
+    commit();
+    if (lane == 0) { mti_p[e] = idx; words_p[e] = used; }
+    __syncwarp();
+  }
+};
+
+// place_obj over the whole grid, warp-uniform (all lanes see the same draws and the same shared-memory rows)
+__device__ __forceinline__ bool coop_place_random(const Rows &R, int gx, int gy, bool has_agent, int ax, int ay, CoopRng &rng, int W,
+                                                  int max_tries, int &ox, int &oy) {
+  int tries = 0;
+  for (;;) {
+    if (max_tries >= 0 && tries > max_tries) return false;
+    tries++;
+    const int x = rng.randint(0, W), y = rng.randint(0, W);
+    const bool empty = !((R.get(y) >> x) & 1u) && !(x == gx && y == gy) && !(has_agent && x == ax && y == ay);
+    if (!empty) continue;
+    ox = x; oy = y;
+    return true;
+  }
+}
+
+// All 32 lanes call this with warp-uniform arguments; `R` is env `env`'s row column in shared memory.  Returns the
+// new hot record (uniform) and writes adv / metrics / error flags of the env from lane 0.
+__device__ __noinline__ uint4 coop_reset_random(Dev d, uint32_t *col, int stride, uint4 hot, int env, int n_walls, int lane) {
+  const Cfg &c = d.c;
+  const int W = c.W;
+  const Rows R{col, stride};
+  Env e = unpack(hot);
+  uint32_t err = 0;
+  if (c.fixed_env) {  // self.seed(self.seed_value) (adversarial.py:542-543); deferred respawns of the old stream are moot
+    if (lane == 0) mt_seed(d, env, d.limbs[env], d.limbs[(size_t)d.N + env], (int)d.limbs[2 * (size_t)d.N + env]);
+    __syncwarp();
+    e.pending = 0;
+  }
+  CoopRng rng(d, env, lane);
+  int x = 0, y = 0;
+  for (int i = 0; i < e.pending; i++) coop_place_random(R, e.gx, e.gy, false, 0, 0, rng, W, -1, x, y);  // flush_pending
+  e.pending = 0;
+  e.step_count = 0;
+  uint32_t adv = d.adv[env];
+  uint32_t adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
+  e.has_agent = 0; e.adir = e.sdir; e.done_flag = 0;
+  e.sx = e.sy = kNone; e.gx = e.gy = kNone;
+  // gen_grid: lane y writes row y
+  __syncwarp();
+  if (lane < W) {
+    const uint32_t full = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
+    R.set(lane, (lane == 0 || lane == W - 1) ? full : (1u | (1u << (W - 1))));
+  }
+  __syncwarp();
+  if (!coop_place_random(R, kNone, kNone, false, 0, 0, rng, W, 100, x, y)) err |= kErrRetries;
+  e.gx = x; e.gy = y;
+  e.sdir = rng.randint(0, 4);
+  coop_place_random(R, e.gx, e.gy, false, 0, 0, rng, W, -1, x, y);
+  e.sx = x; e.sy = y; e.has_agent = 1; e.ax = x; e.ay = y;
+  if (n_walls < 0) n_walls = c.n_clutter / 2;
+  else { adv_max = (uint32_t)n_walls + 2; sampled = 1; }
+  for (int i = 0; i < n_walls; i++) {
+    if (!coop_place_random(R, e.gx, e.gy, true, e.ax, e.ay, rng, W, 100, x, y)) { err |= kErrRetries; break; }
+    __syncwarp();
+    if (lane == 0) R.set(y, R.get(y) | (1u << x));
+    __syncwarp();
+  }
+  rng.store();
+  adv = 0u | (adv_max << 12) | (sampled << 24);
+  // compute_metrics: lane y owns row y
+  const int unreachable = (W - 2) * (W - 2) + 1;
+  const uint32_t interior = ((W >= 32) ? 0xffffffffu : ((1u << W) - 1u)) & ~1u & ~(1u << (W - 1));
+  const bool inner = lane >= 1 && lane < W - 1;
+  const uint32_t row = (lane < W) ? R.get(lane) : 0u;
+  int n = inner ? __popc(row & interior) : 0;
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  int4 met = make_int4(n, abs(e.gx - e.sx) + abs(e.gy - e.sy), 0, unreachable);
+  {
+    const uint32_t fr = inner ? (~row & interior) : 0u;
+    uint32_t reach = (lane == e.sy) ? (1u << e.sx) : 0u;
+    for (int dd = 1; dd <= unreachable; dd++) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, reach, 1), dn = __shfl_down_sync(0xffffffffu, reach, 1);
+      const uint32_t v = (reach | (reach << 1) | (reach >> 1) | (lane > 0 ? up : 0u) | (lane < 31 ? dn : 0u)) & fr;
+      const bool changed = __any_sync(0xffffffffu, v != reach);
+      reach = v;
+      const uint32_t grow = __shfl_sync(0xffffffffu, reach, e.gy);
+      if ((grow >> e.gx) & 1u) { met.z = 1; met.w = dd; break; }
+      if (!changed) break;
+    }
+  }
+  if (!reset_agent(e)) err |= kErrNoStart;
+  if (lane == 0) {
+    d.adv[env] = adv; d.metrics[env] = met;
+    if (err) d.err[env] |= err;
+  }
+  return pack(e);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -680,7 +680,7 @@ __device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, 
 // reset_agent mode: the shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids; the DR
 // variant keeps the batched RNG of its in-kernel reset_random in registers instead (2 CTAs/SM).
 template <bool SEE, bool RR, typename EXT>
-__global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int n_tiles) {
+__global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int n_tiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = d.c.W, N = d.N;
   const int wpc = blockDim.x >> 5;
@@ -690,6 +690,8 @@ __global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 2 * W * kWarpTile);
   uint32_t *s_rng = reinterpret_cast<uint32_t *>(bars + 2);  // only present (and used) when RR
   const int total = gridDim.x * wpc;
+  // Static round-robin tile assignment (tile = global_warp + k * total_warps).  A dynamic scheduler on one global
+  // atomic counter was measured: ~9 k same-address atomics per launch doubled the launch time (10 -> 20 us).
   int tile = blockIdx.x * wpc + warp;
   if (tile >= n_tiles) return;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     const uint4 h = nh;
     const int a = na;
     uint32_t *rows = s_rows + st * W * kWarpTile;
-    // prefetch tile k+1 into the other stage (its last readers, tile k-1, are done: __syncwarp)
+    // prefetch the next tile into the other stage (its last readers, the previous tile, are done: __syncwarp)
     const int next = tile + total;
     __syncwarp();
     if (next < n_tiles) {
@@ -722,7 +724,7 @@ __global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     const Rows R{rows + lane, kWarpTile};
     uint32_t flags = 0;
     double rew = 0.0;
-    bool dirty = false;
+    bool dirty = false, need_rr = false;
     float fin_ret = 0.f;
     int fin_len = 0;
     if (valid) {
@@ -761,13 +763,35 @@ __global__ void __launch_bounds__(128, RR ? 2 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         if (A.o.ep_return) A.o.ep_return[e] = s.ep_ret;
         if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
         s.ep_ret = 0.f; s.ep_len = 0;
-        if (RR) {  // worker.step_env (parallel_wrappers.py:27-37)
-          s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1,
-                                       s_rng + lane, kWarpTile));
-          dirty = true;
-        } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+        if (RR) need_rr = true;  // worker.step_env (parallel_wrappers.py:27-37): reset_random below, warp-converged
+        else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
       } else if ((A.last_step & 3) == 3 && want_trunc) {
         rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+      }
+    }
+    if (RR) {
+      // Finished envs get a fresh random level.  Few per tile (the common case): the warp rebuilds them one at a time
+      // cooperatively; many (a synchronized time-limit storm): every lane rebuilds its own (lane-parallel).
+      const unsigned m = __ballot_sync(0xffffffffu, need_rr);
+      if (m) {
+        dirty = need_rr;
+        if (__popc(m) > 10) {
+          if (need_rr)
+            s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1,
+                                         s_rng + lane, kWarpTile));
+        } else {
+          const uint4 mine = pack(s);
+          for (unsigned rest = m; rest; rest &= rest - 1) {
+            const int le = __ffs(rest) - 1;
+            uint4 h2;
+            h2.x = __shfl_sync(0xffffffffu, mine.x, le); h2.y = __shfl_sync(0xffffffffu, mine.y, le);
+            h2.z = __shfl_sync(0xffffffffu, mine.z, le); h2.w = __shfl_sync(0xffffffffu, mine.w, le);
+            const int env = base + le;
+            const int nw = (c.resample && A.n_walls) ? A.n_walls[env] : -1;
+            const uint4 r = coop_reset_random(d, rows + le, kWarpTile, h2, env, nw, lane);
+            if (lane == le) s = unpack(r);
+          }
+        }
       }
     }
     const View v = render_view_t<SEE, EXT>(R, s, W);
@@ -910,6 +934,8 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(dalloc(&d.limbs, 3 * N, total));
   CK(dalloc(&d.words, N, total));
   CK(dalloc(&d.err, N, total));
+  CK(dalloc(&d.sched, 2, total));
+  CK(cudaMemset(d.sched, 0, 2 * sizeof(uint32_t)));
   CK(dalloc(&v->seed_scratch, 4 * N, total));
   CK(dalloc(&v->act_dev, N, total));
   CK(dalloc(&v->res_dev, 16 + 16 * N + N, total));
@@ -950,7 +976,7 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
   cudaSetDevice(v->device);
   Dev &d = v->d;
   cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
-  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->res_dev); cudaFreeHost(v->res_pin);
+  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->res_dev); cudaFreeHost(v->res_pin);
   delete v;
 }
 
