@@ -6,8 +6,8 @@ environments per GPU (15x15, 25 blocks: BASELINE.json configs[1]) -- T launches 
 float32 observations, rewards and masks straight into rollout storage -- followed by GAE and the PLR
 positive-value-loss episode-score reduction (and, for N>1 GPUs, the NCCL all-gather of the episode records).
 Actions/values are synthetic and resident in HBM before the timed region.  `value` = env-steps/s over all
-GPUs; `e2e` drives the same rollout through the host-buffer C-ABI call (mgplr_step_env_host: pinned action
-H2D + kernel + reward/flags/episode D2H every vector step).
+GPUs; `e2e` drives the same rollout through the host-buffer C-ABI call (mgplr_step_env_host every vector step: the
+kernel reads the pinned int64 actions over PCIe and writes flags + done records back to pinned host memory).
 
   python bench.py [--gpus N --steps K --warmup W] [--impl reference]
   torchrun --nproc-per-node N ... bench.py --gpus N ...
@@ -355,10 +355,12 @@ def run_ours(a):
             tt = torch.tensor([ems], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ems = float(tt.item())
+        dones_per_rollout = done_seen[0] // (ksteps + 1)
         e2e = {'value': N * T * ksteps * world / (ems * 1e-3), 'unit': 'env-steps/s',
-               'h2d_bytes_per_step': T * N * 8, 'd2h_bytes_per_step': T * (N + 16 + 16 * min(N, 2047)) + 4,
-               'api': 'mgplr_step_env_host every vector step: pinned int64 actions H2D, kernel, flags u8[N] + done records D2H, '
-                      'stream sync; observations / rewards / masks stay in rollout storage'}
+               'h2d_bytes_per_step': T * N * 8, 'd2h_bytes_per_step': T * N + 16 * dones_per_rollout + 4,
+               'api': 'mgplr_step_env_host every vector step (T calls per rollout): the kernel reads the pinned int64 actions over PCIe '
+                      '(zero-copy), writes flags u8[N] and the done records into pinned host memory, one stream sync per vector step; '
+                      'observations / rewards / masks stay in rollout storage'}
 
     clocks = sampler.stop() if rank == 0 else None
     cpu = None

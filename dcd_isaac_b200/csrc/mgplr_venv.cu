@@ -44,13 +44,14 @@ struct mgplr_venv {
   // scratch for host->device argument staging
   uint32_t *seed_scratch;  // [4][N]
   int64_t *act_dev;        // [N]   (mgplr_step_env_host)
-  uint8_t *res_dev;        // [16 B: done count][N done records][N flags]
-  uint8_t *res_pin;        // pinned host staging for the count + first kDonePrefix records
+  uint32_t *cnt_dev;       // [2] ping-pong append counters of the host-driven step (each launch zeroes the other one)
+  uint8_t *res_pin;        // pinned + device-mapped: [N done records (env = -1: empty slot)][N flags]
+  uint8_t *res_pin_dev;    // the same allocation as the device sees it
+  uint32_t host_steps;     // host-driven steps issued (selects the ping-pong counter)
   int sm_count;
 };
 
 // dynamic shared memory: `bufs` obs tiles [TILE][75] f32 then wall rows [W][TILE] u32
-constexpr int kDonePrefix = 2047;  // done records fetched together with the count in one D2H copy
 // (+ the batched-RNG scratch [32][tile] of the in-kernel reset_random)
 static size_t step_smem_bytes(int W, int tile, int bufs, bool rr = true) {
   return (size_t)bufs * tile * kObsFloats * 4 + (size_t)W * tile * 4 + (rr ? (size_t)32 * tile * 4 : 0);
@@ -461,7 +462,9 @@ struct StepArgs {
   int last_step;  // bit0: last rollout step (adversarial_runner.py:521-530), bit1: use_proper_time_limits
   mgplr_step_out o;
   uint32_t *done_count;          // host-driven step: append-list of finished episodes (NULL otherwise)
-  mgplr_done_record *done_list;
+  uint32_t *done_count_next;     // the counter of the NEXT host-driven step, zeroed by this launch
+  mgplr_done_record *done_list;  // device view of pinned host memory: records cross PCIe as posted writes
+  uint8_t *flags_host;           // second flags destination (mapped pinned host memory) or NULL
 };
 
 // ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
@@ -570,6 +573,7 @@ __device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, con
   if (o.direction) o.direction[e] = (float)s.adir;
   if (o.reward) o.reward[e] = rew;
   if (o.flags) o.flags[e] = (uint8_t)flags;
+  if (A.flags_host) A.flags_host[e] = (uint8_t)flags;
   const bool done = flags & MGPLR_F_DONE, last = A.last_step & 1, cliff = last && (A.last_step & 2) && !done;
   if (o.masks) o.masks[e] = (done || last) ? 0.f : 1.f;
   if (o.bad_masks) o.bad_masks[e] = ((flags & MGPLR_F_TRUNC_KEY) || cliff) ? 0.f : 1.f;
@@ -694,6 +698,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   // atomic counter was measured: ~9 k same-address atomics per launch doubled the launch time (10 -> 20 us).
   int tile = blockIdx.x * wpc + warp;
   if (tile >= n_tiles) return;
+  if (A.done_count_next && blockIdx.x == 0 && threadIdx.x == 0) *A.done_count_next = 0;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
   __syncwarp();
   // prologue: first tile's rows and scalars
@@ -938,8 +943,11 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(cudaMemset(d.sched, 0, 2 * sizeof(uint32_t)));
   CK(dalloc(&v->seed_scratch, 4 * N, total));
   CK(dalloc(&v->act_dev, N, total));
-  CK(dalloc(&v->res_dev, 16 + 16 * N + N, total));
-  CK(cudaHostAlloc((void **)&v->res_pin, 16 + 16 * (size_t)kDonePrefix, cudaHostAllocDefault));
+  CK(dalloc(&v->cnt_dev, 2, total));
+  CK(cudaMemset(v->cnt_dev, 0, 2 * sizeof(uint32_t)));
+  CK(cudaHostAlloc((void **)&v->res_pin, 16 * N + N, cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void **)&v->res_pin_dev, v->res_pin, 0));
+  memset(v->res_pin, 0xff, 16 * N);  // env = -1 in every record slot
   v->bytes = total;
   CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device));
   {
@@ -976,7 +984,7 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
   cudaSetDevice(v->device);
   Dev &d = v->d;
   cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
-  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->res_dev); cudaFreeHost(v->res_pin);
+  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->cnt_dev); cudaFreeHost(v->res_pin);
   delete v;
 }
 
@@ -1154,40 +1162,55 @@ extern "C" int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t rese
   return launch_step(v, action, reset_random, n_walls, last_step, out, st);
 }
 
+// Device view of a host pointer when it is pinned (cudaHostAlloc / cudaHostRegister) memory, else NULL.
+static void *mapped_view(const void *host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+// Host-driven transition.  With pinned buffers the whole call is ONE kernel launch and one stream synchronisation:
+// the kernel reads the actions straight from the caller's pinned memory (zero-copy over PCIe, prefetched one tile ahead),
+// writes the flags straight into the caller's pinned flags buffer and appends the done records to a device-mapped pinned
+// list (dense prefix of an env = -1 sentinel-filled array, so no count has to come back).  Pageable buffers take staged
+// copies around the same launch.
 extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
                                    const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
                                    int32_t done_capacity, int32_t *n_done_host, void *stream) {
   NEED(v);
   if (!action_host) return fail(MGPLR_E_BADARG, "action_host is NULL");
   const size_t N = (size_t)v->d.N;
-  uint32_t *count_d = (uint32_t *)v->res_dev;
-  mgplr_done_record *list_d = (mgplr_done_record *)(v->res_dev + 16);
-  uint8_t *flags_d = v->res_dev + 16 + 16 * N;
-  CK(cudaMemcpyAsync(v->act_dev, action_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(count_d, 0, 16, st));
+  mgplr_done_record *list_h = (mgplr_done_record *)v->res_pin;
+  uint8_t *flags_pin = v->res_pin + 16 * N;
+  const int64_t *act = (const int64_t *)mapped_view(action_host);
+  if (!act) {
+    CK(cudaMemcpyAsync(v->act_dev, action_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    act = v->act_dev;
+  }
+  uint8_t *flags_map = flags_host ? (uint8_t *)mapped_view(flags_host) : nullptr;
+  const bool stage_flags = flags_host && !flags_map;
   StepArgs A;
   memset(&A, 0, sizeof(A));
   if (out_dev) A.o = *out_dev;
-  uint8_t *user_flags = A.o.flags;
-  A.action = v->act_dev; A.last_step = last_step;
-  A.o.flags = flags_d; A.done_count = count_d; A.done_list = list_d;
+  A.action = act; A.last_step = last_step;
+  A.done_count = v->cnt_dev + (v->host_steps & 1u);
+  A.done_count_next = v->cnt_dev + ((v->host_steps + 1u) & 1u);
+  A.done_list = (mgplr_done_record *)v->res_pin_dev;
+  A.flags_host = stage_flags ? v->res_pin_dev + 16 * N : flags_map;
+  v->host_steps++;
   if (int rc = launch_step_args(v, A, reset_random, st)) return rc;
-  if (user_flags) CK(cudaMemcpyAsync(user_flags, flags_d, N, cudaMemcpyDeviceToDevice, st));
-  const size_t prefix = N < (size_t)kDonePrefix ? N : (size_t)kDonePrefix;
-  CK(cudaMemcpyAsync(v->res_pin, v->res_dev, 16 + 16 * prefix, cudaMemcpyDeviceToHost, st));
-  if (flags_host) CK(cudaMemcpyAsync(flags_host, flags_d, N, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const uint32_t n_done = *(const uint32_t *)v->res_pin;
+  if (stage_flags) memcpy(flags_host, flags_pin, N);
+  // the records are a dense prefix of the sentinel-filled list
+  size_t n_done = 0;
+  while (n_done < N && list_h[n_done].env >= 0) n_done++;
   if (n_done_host) *n_done_host = (int32_t)n_done;
   if (done_host && done_capacity > 0) {
-    const size_t want = n_done < (uint32_t)done_capacity ? n_done : (size_t)done_capacity;
-    const size_t first = want < prefix ? want : prefix;
-    memcpy(done_host, v->res_pin + 16, first * sizeof(mgplr_done_record));
-    if (want > first) {  // a reset storm: fetch the rest directly
-      CK(cudaMemcpyAsync(done_host + first, list_d + first, (want - first) * sizeof(mgplr_done_record), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-    }
+    const size_t want = n_done < (size_t)done_capacity ? n_done : (size_t)done_capacity;
+    memcpy(done_host, list_h, want * sizeof(mgplr_done_record));
   }
+  for (size_t k = 0; k < n_done; k++) list_h[k].env = -1;
   return 0;
 }
 

@@ -150,9 +150,12 @@ typedef struct mgplr_done_record {
 
 /* The same transition driven from HOST buffers (the reference's calling convention: actions arrive as a CPU
  * tensor, adversarial_runner.py:512-517; done / infos go back to the host).  Observations, rewards and masks stay
- * in HBM at the `out_dev` destinations (rollout storage).  Per call: action i64 [N] H2D; flags u8 [N] and the
- * (few) done records D2H; one stream synchronisation.  done_host receives min(*n_done_host, done_capacity)
- * records in unspecified order.  All host pointers should be pinned memory. */
+ * in HBM at the `out_dev` destinations (rollout storage).  With PINNED host buffers (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory) the call is one kernel launch + one stream synchronisation: the kernel reads
+ * action i64 [N] straight from the caller's memory over PCIe, writes flags u8 [N] straight into flags_host and appends
+ * the (few) done records to a device-mapped pinned list owned by the handle.  Pageable buffers work too (staged
+ * copies).  done_host receives min(*n_done_host, done_capacity) records in unspecified order.  Use one stream per
+ * handle for these calls. */
 int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
                         const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
                         int32_t done_capacity, int32_t *n_done_host, void *stream);
