@@ -29,6 +29,7 @@ struct Cfg {
 // Device view of one venv (all pointers are HBM).
 struct Dev {
   int N;
+  int l2_hints;      // 1: L2 eviction-priority hints in the step kernel (level + hot records evict_last, observations evict_first)
   Cfg c;
   uint32_t *wall;    // [ceil(N/32)][W][32] wall bit-plane rows (bit x of row y), tile-major: see env_rows()
   uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx5|gy5|hasgoal1|sx5|sy5|hasstart1|sdir2|pending8  z: elapsed16|eplen16  w: ep_ret bits
@@ -667,6 +668,113 @@ __device__ __forceinline__ View render_view_t(const Rows &R, const Env &e, int W
 template <bool SEE_THROUGH>
 __device__ __forceinline__ View render_view(const Rows &R, const Env &e, int W) {
   return render_view_t<SEE_THROUGH, uint64_t>(R, e, W);
+}
+
+// ---- packed, branch-free variant used by the hot kernels -------------------------------------------------------
+// The 5x5 view is ONE 25-bit word Z with bit (vy*5 + vx) = wall at view cell (vx, vy).  All four directions share one
+// instruction stream (a warp holds agents facing every way, so a per-direction branch executes every side):
+//   * five world rows are fetched in a per-direction order (k-th row = base + step*k) and 5 bits are cut out of each
+//     at a per-direction column offset -> X, bit (k*5 + j) = wall at (off + j, base + step*k);
+//   * facing right / down the cut is mirrored in both axes: brev(X) >> 7 (a 25-bit reversal);
+//   * facing right / left the view rows are world columns: a 5x5 bit-matrix transpose (8 shifted masks).
+// dir 3 (up):    cell(vx,vy) = (ax-2+vx,   ay-4+vy)   rows ay-4.. step +1, off ax-2            -> Z = X
+// dir 1 (down):  cell(vx,vy) = (ax+2-vx,   ay+4-vy)   rows ay..   step +1, off ax-2, mirrored  -> Z = rev25(X)
+// dir 2 (left):  cell(vx,vy) = (ax-4+vy,   ay+2-vx)   rows ay+2.. step -1, off ax-4            -> Z = X^T
+// dir 0 (right): cell(vx,vy) = (ax+4-vy,   ay-2+vx)   rows ay+2.. step -1, off ax,   mirrored  -> Z = rev25(X)^T
+__device__ __forceinline__ uint32_t transpose5(uint32_t x) {  // bit (r*5+c) -> bit (c*5+r)
+  uint32_t y = x & 0x1041041u;
+  y |= (x >> 4) & 0x0082082u;
+  y |= (x >> 8) & 0x0004104u;
+  y |= (x >> 12) & 0x0000208u;
+  y |= (x >> 16) & 0x0000010u;
+  y |= (x << 4) & 0x0820820u;
+  y |= (x << 8) & 0x0410400u;
+  y |= (x << 12) & 0x0208000u;
+  y |= (x << 16) & 0x0100000u;
+  return y;
+}
+
+struct PackedView {
+  uint32_t wall;  // bit (vy*5+vx): wall, already masked by `vis`
+  uint32_t vis;   // bit (vy*5+vx): visible (all ones when see_through_walls)
+  int goal;       // vx*5+vy of the goal if it is in view and visible, else -1
+};
+
+template <bool SEE_THROUGH, typename EXT>
+__device__ __forceinline__ PackedView render_packed(const Rows &R, const Env &e, int W) {
+  constexpr int PAD = 4;
+  const int d = e.adir;
+  const bool vertical = d & 1, mirrored = d < 2;
+  const int base = (d == 3) ? e.ay - 4 : (d == 1) ? e.ay : e.ay + 2;
+  const int step = vertical ? 1 : -1;
+  const int off = ((d == 0) ? e.ax : (d == 2) ? e.ax - 4 : e.ax - 2) + PAD;
+  const EXT ones = ~(EXT)0;
+  const EXT border = ((EXT)15) | (ones << (W + PAD));
+  uint32_t X = 0;
+#pragma unroll
+  for (int k = 0; k < kV; k++) {
+    const int wy = base + step * k;
+    EXT row = ones;  // outside the grid = wall
+    if (wy >= 0 && wy < W) row = ((EXT)R.get(wy) << PAD) | border;
+    X |= ((uint32_t)(row >> off) & 31u) << (5 * k);
+  }
+  if (mirrored) X = __brev(X) >> 7;
+  if (!vertical) X = transpose5(X);
+  PackedView v;
+  // goal in view coordinates: fd = (g-a).f, lt = (g-a).r
+  const int dx = e.gx - e.ax, dy = e.gy - e.ay;
+  const int p = vertical ? dy : dx, q = vertical ? dx : dy;  // d=0: fd=dx, lt=dy; 1: dy,-dx; 2: -dx,-dy; 3: -dy,dx
+  const int fd = (d == 0 || d == 1) ? p : -p;
+  const int lt = (d == 0 || d == 3) ? q : -q;
+  const int gvy = kV - 1 - fd, gvx = lt + kV / 2;
+  const bool in = (e.gx != kNone) && (unsigned)gvx < (unsigned)kV && (unsigned)gvy < (unsigned)kV;
+  if (SEE_THROUGH) {
+    v.wall = X; v.vis = 0x1ffffffu;
+    v.goal = in ? gvx * kV + gvy : -1;
+  } else {
+    // gym_minigrid Grid.process_vis(agent_pos=(V/2, V-1)), the two sweeps per row as bit closures
+    uint32_t m = 1u << (kV / 2), V = 0;
+#pragma unroll
+    for (int j = kV - 1; j >= 0; j--) {
+      const uint32_t open = ~(X >> (5 * j)) & 31u;
+      uint32_t P = m;
+#pragma unroll
+      for (int it = 0; it < kV - 1; it++) P |= ((P & open) << 1) & 31u;   // left -> right, i = 0..V-2
+      const uint32_t srcL = P & open & 15u;
+      uint32_t nxt = srcL | (srcL << 1);
+      uint32_t Q = P;
+#pragma unroll
+      for (int it = 0; it < kV - 1; it++) Q |= (Q & open) >> 1;           // right -> left, i = V-1..1
+      const uint32_t srcR = Q & open & 30u;
+      nxt |= srcR | (srcR >> 1);
+      V |= Q << (5 * j);
+      m = nxt;
+    }
+    v.vis = V; v.wall = X & V;
+    v.goal = (in && ((V >> (gvy * kV + gvx)) & 1u)) ? gvx * kV + gvy : -1;
+  }
+  return v;
+}
+
+// preprocessed observation [3][5][5] (c, vx, vy) from the packed view: type = unseen 0 | wall 0.2 | goal 0.8 | empty
+// 0.1, colour = wall 0.5 | goal 0.1 | 0, state = 0.  One bit test per cell; the goal (at most one cell, never a wall)
+// is patched in afterwards; the agent's own cell (V/2, V-1) never holds a wall or the goal and renders as empty.
+// ZERO_STATE = false leaves the all-zero state plane alone (the caller zeroed it once and nothing else writes it).
+template <bool SEE_THROUGH, bool ZERO_STATE>
+__device__ __forceinline__ void emit_packed_f32(const PackedView &v, float *o) {
+#pragma unroll
+  for (int vx = 0; vx < kV; vx++)
+#pragma unroll
+    for (int vy = 0; vy < kV; vy++) {
+      const uint32_t bit = 1u << (vy * kV + vx);
+      const bool bw = v.wall & bit;
+      float t = bw ? 0.2f : 0.1f;
+      if (!SEE_THROUGH) t = (v.vis & bit) ? t : 0.0f;
+      o[vx * kV + vy] = t;
+      o[kV * kV + vx * kV + vy] = bw ? 0.5f : 0.0f;
+      if (ZERO_STATE) o[2 * kV * kV + vx * kV + vy] = 0.0f;
+    }
+  if (v.goal >= 0) { o[v.goal] = 0.8f; o[kV * kV + v.goal] = 0.1f; }
 }
 
 // cell code of view cell (vx,vy): 0 unseen, 1 empty, 2 wall, 3 goal

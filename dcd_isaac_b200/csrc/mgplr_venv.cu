@@ -48,6 +48,7 @@ struct mgplr_venv {
   uint8_t *res_pin;        // pinned + device-mapped: [N done records (env = -1: empty slot)][N flags]
   uint8_t *res_pin_dev;    // the same allocation as the device sees it
   uint32_t host_steps;     // host-driven steps issued (selects the ping-pong counter)
+  int pdl;                 // launch the step kernel with programmatic stream serialization
   int sm_count;
 };
 
@@ -503,6 +504,8 @@ __device__ __noinline__ uint4 rare_reset_random(Dev d, uint32_t *rows, int strid
   return pack(s);
 }
 
+__device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot, int W, int see, uint8_t *image_u8, int e);
+
 // One env transition for the thread's env; `rows` = this env's wall rows in shared memory.  Returns flags.
 // In reset_agent mode a goal's respawn draw is DEFERRED (Env::pending, mgplr_env.cuh).
 template <bool SEE, bool RR, typename EXT>
@@ -554,9 +557,9 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
   } else if ((A.last_step & 3) == 3 && want_trunc) {
     rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
   }
-  const View v = render_view_t<SEE, EXT>(R, s, c.W);
-  emit_obs_f32_fast<SEE>(v, s_obs);
-  if (A.o.image_u8) emit_obs_u8(v, A.o.image_u8 + (size_t)e * kObsFloats);
+  const PackedView v = render_packed<SEE, EXT>(R, s, c.W);
+  emit_packed_f32<SEE, false>(v, s_obs);
+  if (A.o.image_u8) rare_emit_u8(rows, stride, pack(s), c.W, c.see_through, A.o.image_u8, e);
   rew_out = (float)rew;
   return flags;
 }
@@ -607,6 +610,36 @@ __device__ __forceinline__ void bulk_load(void *sdst, const void *gsrc, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// L2 eviction-priority policies (createpolicy) and hinted variants of the copies.  The level (wall bit-plane) and the
+// hot records are re-read by every step launch of a rollout and are small (a few MB): they are kept in the 126 MB L2
+// (evict_last) while the observation stream, written once and read much later, is marked evict_first so that it does
+// not push them out.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 normal, 1 evict_last, 2 evict_first
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_load_hint(void *sdst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+               "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_hint_u4(const uint4 *p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint_u4(uint4 *p, const uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk stores have finished READING shared memory (the global writes complete before the grid does)
@@ -673,11 +706,11 @@ __device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot,
 }
 
 // rows of one 32-env tile -> shared memory: ONE bulk asynchronous copy of W*128 bytes completing on `bar`
-__device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, uint64_t *bar, int tile, int lane) {
+__device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, uint64_t *bar, int tile, int lane, uint64_t pol) {
   if (lane == 0) {
     const uint32_t bytes = (uint32_t)(d.c.W * kWarpTile * 4);
     mbar_expect_tx(bar, bytes);
-    bulk_load(s_rows, d.wall + (size_t)tile * d.c.W * kWarpTile, bytes, bar);
+    bulk_load_hint(s_rows, d.wall + (size_t)tile * d.c.W * kWarpTile, bytes, bar, pol);
   }
 }
 
@@ -697,15 +730,24 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   // Static round-robin tile assignment (tile = global_warp + k * total_warps).  A dynamic scheduler on one global
   // atomic counter was measured: ~9 k same-address atomics per launch doubled the launch time (10 -> 20 us).
   int tile = blockIdx.x * wpc + warp;
+  // Programmatic dependent launch: consecutive step launches of a rollout are serially dependent through the hot
+  // records, so the NEXT launch is allowed to become resident as this one's CTAs retire and to run its on-chip
+  // prologue; it blocks at griddepcontrol.wait (below) until this grid has completed and its writes are visible.
+  asm volatile("griddepcontrol.launch_dependents;");
   if (tile >= n_tiles) return;
-  if (A.done_count_next && blockIdx.x == 0 && threadIdx.x == 0) *A.done_count_next = 0;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
+  // the state plane of every observation is all zero: written once here, never touched by emit_packed_f32
+#pragma unroll
+  for (int i = 0; i < kV * kV; i++) s_obs[lane * kObsFloats + 2 * kV * kV + i] = 0.0f;
   __syncwarp();
+  const uint64_t pol_keep = l2_policy(d.l2_hints ? 1 : 0), pol_stream = l2_policy(d.l2_hints ? 2 : 0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
+  if (A.done_count_next && blockIdx.x == 0 && threadIdx.x == 0) *A.done_count_next = 0;
   // prologue: first tile's rows and scalars
-  warp_issue_rows(d, s_rows, &bars[0], tile, lane);
+  warp_issue_rows(d, s_rows, &bars[0], tile, lane, pol_keep);
   uint4 nh = make_uint4(0, 0, 0, 0);
   int na = 6;
-  if (tile * kWarpTile + lane < N) { nh = d.hot[tile * kWarpTile + lane]; na = (int)A.action[tile * kWarpTile + lane]; }
+  if (tile * kWarpTile + lane < N) { nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep); na = (int)A.action[tile * kWarpTile + lane]; }
   uint32_t phase = 0;  // bit s = parity to wait for on bars[s]
   for (int k = 0; tile < n_tiles; tile += total, k++) {
     const int st = k & 1, base = tile * kWarpTile, e = base + lane;
@@ -718,8 +760,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     const int next = tile + total;
     __syncwarp();
     if (next < n_tiles) {
-      warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane);
-      if (next * kWarpTile + lane < N) { nh = d.hot[next * kWarpTile + lane]; na = (int)A.action[next * kWarpTile + lane]; }
+      warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane, pol_keep);
+      if (next * kWarpTile + lane < N) { nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_keep); na = (int)A.action[next * kWarpTile + lane]; }
     }
     mbar_wait(&bars[st], (phase >> st) & 1u);
     phase ^= 1u << st;
@@ -799,17 +841,17 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         }
       }
     }
-    const View v = render_view_t<SEE, EXT>(R, s, W);
+    const PackedView v = render_packed<SEE, EXT>(R, s, W);
     // re-acquire the observation buffer: the previous tile's bulk store must have finished reading it
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
-    emit_obs_f32_fast<SEE>(v, s_obs + lane * kObsFloats);
+    emit_packed_f32<SEE, false>(v, s_obs + lane * kObsFloats);
     if (A.o.image) {
       float *gdst = A.o.image + (size_t)base * kObsFloats;
       if (n_tile == kWarpTile && (((uintptr_t)gdst) & 15u) == 0) {
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) { bulk_store(gdst, s_obs, kWarpTile * kObsFloats * 4); bulk_commit(); }
+        if (lane == 0) { bulk_store_hint(gdst, s_obs, kWarpTile * kObsFloats * 4, pol_stream); bulk_commit(); }
       } else {
         __syncwarp();
         for (int i = lane; i < n_tile * kObsFloats; i += 32) gdst[i] = s_obs[i];
@@ -817,7 +859,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
       }
     }
     if (valid) {
-      d.hot[e] = pack(s);
+      st_hint_u4(&d.hot[e], pack(s), pol_keep);
       write_step_scalars(A, e, s, flags, (float)rew, fin_ret, fin_len);
       if (A.o.image_u8) rare_emit_u8(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.image_u8, e);
       if (RR && dirty) {
@@ -842,6 +884,9 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
   const int n_tile = min(TILE, N - base);
   const bool valid = tid < n_tile;
   stage_rows_begin<TILE>(d, s_rows, &bar, base);
+  // the all-zero state plane of both observation buffers is written once (emit_packed_f32 leaves it alone)
+#pragma unroll
+  for (int i = 0; i < kV * kV; i++) { s_obs0[tid * kObsFloats + 2 * kV * kV + i] = 0.0f; s_obs1[tid * kObsFloats + 2 * kV * kV + i] = 0.0f; }
   Env s{};
   if (valid) s = unpack(d.hot[e]);
   mbar_wait(&bar, 0);
@@ -924,6 +969,8 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   v->device = device;
   Dev &d = v->d;
   d.N = num_envs;
+  d.l2_hints = getenv("MGPLR_L2_HINTS") ? atoi(getenv("MGPLR_L2_HINTS")) : 1;
+  v->pdl = getenv("MGPLR_PDL") ? atoi(getenv("MGPLR_PDL")) : 0;  // measured: no gain at 131 072 envs, slower at 4 096
   d.c = Cfg{cfg->width, cfg->max_steps, cfg->max_episode_steps, cfg->see_through_walls != 0, cfg->n_clutter,
             cfg->resample_n_clutter != 0, cfg->choose_goal_last != 0, cfg->fixed_environment != 0, cfg->n_editor_actions};
   const size_t N = (size_t)num_envs;
@@ -1140,7 +1187,14 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   const int need = (n_tiles + wpc - 1) / wpc;
   if (grid > need) grid = need;
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
-#define LAUNCH(SEE, RR, EXT) k_step_env<SEE, RR, EXT><<<grid, wpc * 32, smem, st>>>(v->d, A, n_tiles)
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(wpc * 32); lc.dynamicSmemBytes = smem; lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr; lc.numAttrs = v->pdl ? 1 : 0;
+#define LAUNCH(SEE, RR, EXT) CK(cudaLaunchKernelEx(&lc, k_step_env<SEE, RR, EXT>, v->d, A, n_tiles))
 #define BY_MODE(EXT)                                  \
   do {                                                \
     if (see && rr) LAUNCH(true, true, EXT);           \
