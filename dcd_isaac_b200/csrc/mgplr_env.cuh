@@ -40,8 +40,19 @@ struct Dev {
   uint32_t *limbs;   // [3][N] seed limbs lo, hi, count (re-seed of fixed_environment)
   uint32_t *words;   // [N] MT words consumed since seeding
   uint32_t *err;     // [N] sticky error bits
-  uint32_t *sched;   // [2] dynamic tile scheduler of the step kernel: next tile, warps finished (self-resetting)
+  // speculative next-level generation of the DR auto-reset (step_env(reset_random=True)), see the "speculation" block
+  uint32_t *spec;    // [N] bits 0-15: MT words logically consumed but not yet applied to mt / mti / words; bit 16 / 17:
+                     //     candidate 0 (episode ended without a goal) / 1 (ended at the goal) is valid
+  uint32_t *cand;    // [N][2][W + 8] candidate records: wall rows, packed goal/start, metrics[4], words consumed, error bits
+  int32_t *rr_list;  // [2N + slack] regeneration jobs 2*env + candidate (-1 = empty slot)
+  unsigned long long *prof;  // debug counters (MGPLR_RR_PROF), else NULL
+  uint32_t *sched;   // [4] regeneration phase of the step kernel: jobs appended, warps past their tiles, next ticket, warps exited
 };
+constexpr int kMetricsDirty = -2;  // metrics.z of an env whose level came from a candidate record: recomputed by the getter
+constexpr uint32_t kSpecAdvMask = 0xffffu, kSpecValid0 = 1u << 16, kSpecValid1 = 1u << 17;
+constexpr int kSpecWindow = 224;   // MT words one regeneration job can look ahead (< 227: all computable from the present state)
+constexpr int kRrListSlack = 32768;
+__host__ __device__ inline int cand_words(int W) { return W + 8; }
 
 // `pending` = goal respawns (multigrid.py:821-838) whose env-RNG draws have not been made yet.  A respawn draw
 // depends only on the level (walls + goal; the agent is off the grid while it is drawn) and its result is
@@ -109,7 +120,7 @@ __device__ __forceinline__ Rows env_rows(const Dev &d, int e) {
 // refill code from being replayed once per lane under divergence (it was 75 % of reset_random's instructions).
 struct Rng {
   static constexpr int kBatch = 16;
-  uint32_t *mt, *mti_p, *words_p;
+  uint32_t *mt, *mti_p, *words_p, *spec_p;
   int N, e;
   uint32_t idx, used;  // cursor (0..623), words consumed since seeding
   int have, pos;       // words in the batch, next unread word
@@ -117,10 +128,27 @@ struct Rng {
   uint32_t *buf;       // this thread's column of the shared scratch
   int stride;          // threads per row of the scratch
   __device__ __forceinline__ Rng(const Dev &dev, int env, uint32_t *buf_, int stride_)
-      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), idx(0), used(0), have(0), pos(0), loaded(false),
-        buf(buf_), stride(stride_) {}
+      : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), spec_p(dev.spec), N(dev.N), e(env), idx(0), used(0), have(0), pos(0),
+        loaded(false), buf(buf_), stride(stride_) {}
+  // Any consumer of the env RNG other than the speculation itself first applies the words a committed candidate consumed
+  // logically (one word at a time: rare) and drops the candidates, whose stream position is about to become stale.
+  __device__ __noinline__ void settle(uint32_t sp) {
+    for (uint32_t k = sp & kSpecAdvMask; k; k--) {
+      const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
+      const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
+      uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      mt[(size_t)i * N + e] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      idx = i1; used++;
+    }
+    spec_p[e] = 0;
+    mti_p[e] = idx; words_p[e] = used;
+  }
   __device__ __forceinline__ void load() {
-    if (!loaded) { idx = mti_p[e]; used = words_p[e]; loaded = true; }
+    if (!loaded) {
+      idx = mti_p[e]; used = words_p[e]; loaded = true;
+      const uint32_t sp = spec_p[e];
+      if (sp) settle(sp);
+    }
   }
   __device__ __forceinline__ void refill() {
     load();
@@ -154,6 +182,7 @@ struct Rng {
   }
   // forget everything (after a re-seed replaced the stream)
   __device__ __forceinline__ void reset() { loaded = false; have = 0; pos = 0; }
+  __device__ __forceinline__ bool ok() const { return true; }
   __device__ __forceinline__ uint32_t next() {
     if (__any_sync(__activemask(), pos >= have)) refill();
     const uint32_t v = buf[pos * stride];
@@ -175,27 +204,39 @@ struct Rng {
 
 // One word per draw, no scratch: for the rare paths of the hot kernel that cannot spare shared memory.
 struct RngSlow {
-  uint32_t *mt, *mti_p, *words_p;
+  uint32_t *mt, *mti_p, *words_p, *spec_p;
   int N, e;
   uint32_t idx, used;
   bool loaded;
-  __device__ __forceinline__ RngSlow(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, int N_, int env)
-      : mt(mt_), mti_p(mti_), words_p(words_), N(N_), e(env), idx(0), used(0), loaded(false) {}
+  __device__ __forceinline__ RngSlow(uint32_t *mt_, uint32_t *mti_, uint32_t *words_, uint32_t *spec_, int N_, int env)
+      : mt(mt_), mti_p(mti_), words_p(words_), spec_p(spec_), N(N_), e(env), idx(0), used(0), loaded(false) {}
   __device__ __forceinline__ void load() {
-    if (!loaded) { idx = mti_p[e]; used = words_p[e]; loaded = true; }
+    if (!loaded) {
+      idx = mti_p[e]; used = words_p[e]; loaded = true;
+      const uint32_t sp = spec_p[e];
+      if (sp) {  // see Rng::settle
+        for (uint32_t k = sp & kSpecAdvMask; k; k--) next_raw();
+        spec_p[e] = 0;
+      }
+    }
   }
-  __device__ __forceinline__ void store() {
-    if (loaded) { mti_p[e] = idx; words_p[e] = used; }
-  }
-  __device__ __forceinline__ void reset() { loaded = false; }
-  __device__ __forceinline__ uint32_t next() {
-    load();
+  __device__ __forceinline__ uint32_t next_raw() {
     const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
     const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
     uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
     mt[(size_t)i * N + e] = y;
     idx = i1; used++;
+    return y;
+  }
+  __device__ __forceinline__ void store() {
+    if (loaded) { mti_p[e] = idx; words_p[e] = used; }
+  }
+  __device__ __forceinline__ void reset() { loaded = false; }
+  __device__ __forceinline__ bool ok() const { return true; }
+  __device__ __forceinline__ uint32_t next() {
+    load();
+    uint32_t y = next_raw();
     y ^= (y >> 11);
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
@@ -238,6 +279,13 @@ __device__ __noinline__ void mt_seed(const Dev &d, int e, uint32_t k0, uint32_t 
   mt[e] = 0x80000000u;
   d.mti[e] = 0;  // numpy's mti = 624 ("regenerate everything") == incremental index 0
   d.words[e] = 0;
+  d.spec[e] = 0;  // a new stream: pending logical advance and candidates are moot
+}
+
+// level edits that do not draw from the env RNG: the candidates' respawn draws depended on the old level
+__device__ __forceinline__ void spec_invalidate(const Dev &d, int e) {
+  const uint32_t sp = d.spec[e];
+  if (sp & ~kSpecAdvMask) d.spec[e] = sp & kSpecAdvMask;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,6 +312,7 @@ __device__ __forceinline__ bool place_random(const Rows &R, const Env &e, RNG &r
   int tries = 0;
   for (;;) {
     if (max_tries >= 0 && tries > max_tries) return false;
+    if (!rng.ok()) return false;  // look-ahead window exhausted (speculation only)
     tries++;
     const int x = rng.randint(0, W), y = rng.randint(0, W);
     if (!is_empty(R, e, x, y)) continue;
@@ -433,6 +482,43 @@ __device__ __forceinline__ void reset_random(const Rows &R, Env &e, uint32_t &ad
 // 32-word batch (one memory round trip per 32 draws), lane y owns row y of the grid (gen_grid, wall count and the
 // flood fill become a handful of shuffles per iteration), and the (inherently serial) rejection sampling runs
 // warp-uniformly on broadcast values.  Draw order and count are exactly reset_random()'s.
+// Apply `a` (<= kSpecWindow < 227) logically consumed words to env e's MT state, all lanes of the warp together: every new
+// state word of the span only depends on PRESENT state words (j, j+1, j+397 mod 624), so all are loaded first, then stored.
+__device__ __forceinline__ void coop_mt_advance(const Dev &d, int e, int lane, uint32_t &idx, uint32_t &used, int a) {
+  constexpr int kPer = (kSpecWindow + 31) / 32;
+  uint32_t ns[kPer];
+  const size_t N = d.N;
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    const int j = lane + 32 * i;
+    ns[i] = 0;
+    if (j < a) {
+      uint32_t p = idx + j, p1 = p + 1, pm = p + 397;
+      if (p >= 624) p -= 624;
+      if (p1 >= 624) p1 -= 624;
+      if (pm >= 624) pm -= 624;
+      if (pm >= 624) pm -= 624;
+      const uint32_t x = d.mt[p * N + e], b = d.mt[p1 * N + e], c = d.mt[pm * N + e];
+      const uint32_t y = (x & 0x80000000u) | (b & 0x7fffffffu);
+      ns[i] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    const int j = lane + 32 * i;
+    if (j < a) {
+      uint32_t p = idx + j;
+      if (p >= 624) p -= 624;
+      d.mt[p * N + e] = ns[i];
+    }
+  }
+  __syncwarp();
+  idx += a;
+  if (idx >= 624) idx -= 624;
+  used += a;
+}
+
 struct CoopRng {
   uint32_t *mt, *mti_p, *words_p;
   int N, e, lane;
@@ -442,6 +528,12 @@ struct CoopRng {
   __device__ __forceinline__ CoopRng(const Dev &dev, int env, int lane_)
       : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), lane(lane_), have(0), pos(0), w_out(0), w_nst(0) {
     idx = mti_p[e]; used = words_p[e];
+    const uint32_t sp = dev.spec[e];  // see Rng::settle
+    if (sp) {
+      coop_mt_advance(dev, e, lane, idx, used, (int)(sp & kSpecAdvMask));
+      if (lane == 0) dev.spec[e] = 0;
+      __syncwarp();
+    }
   }
   __device__ __forceinline__ void commit() {  // write back the state words of the consumed draws
     if (lane < pos) {
@@ -492,14 +584,88 @@ struct CoopRng {
     if (lane == 0) { mti_p[e] = idx; words_p[e] = used; }
     __syncwarp();
   }
+  __device__ __forceinline__ bool ok() const { return true; }
 };
 
+// Warp-uniform draws from a precomputed look-ahead window of tempered MT outputs in shared memory (speculation).
+struct WinRng {
+  const uint32_t *win;
+  int pos, n;
+  bool overflow;
+  __device__ __forceinline__ uint32_t next() {
+    if (pos >= n) { overflow = true; return 0u; }
+    return win[pos++];
+  }
+  __device__ __forceinline__ int randint(int lo, int hi) {
+    const uint32_t rng = (uint32_t)(hi - lo - 1);
+    if (rng == 0) return lo;
+    const uint32_t mask = 0xffffffffu >> __clz(rng);
+    uint32_t v;
+    do { v = next() & mask; } while (v > rng && !overflow);
+    return lo + (int)(v > rng ? 0u : v);
+  }
+  __device__ __forceinline__ bool ok() const { return !overflow; }
+};
+
+// The level-building core of reset_random (adversarial.py:546-581), all 32 lanes on warp-uniform values; `R` = W rows in
+// shared memory that this warp owns.  Draw order and count are exactly reset_random()'s.
+struct LevelOut {
+  int gx, gy, sx, sy, sdir;
+  int4 met;
+  uint32_t err;
+};
+template <typename RNG>
+__device__ __forceinline__ LevelOut coop_level_core(const Rows &R, RNG &rng, int W, int n_walls, int lane) {
+  LevelOut o;
+  o.err = 0;
+  int x = 0, y = 0;
+  __syncwarp();
+  if (lane < W) {  // gen_grid: lane y writes row y
+    const uint32_t full = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
+    R.set(lane, (lane == 0 || lane == W - 1) ? full : (1u | (1u << (W - 1))));
+  }
+  __syncwarp();
+  if (!coop_place_random(R, kNone, kNone, false, 0, 0, rng, W, 100, x, y)) o.err |= kErrRetries;
+  o.gx = x; o.gy = y;
+  o.sdir = rng.randint(0, 4);
+  coop_place_random(R, o.gx, o.gy, false, 0, 0, rng, W, -1, x, y);
+  o.sx = x; o.sy = y;
+  for (int i = 0; i < n_walls; i++) {
+    if (!coop_place_random(R, o.gx, o.gy, true, o.sx, o.sy, rng, W, 100, x, y)) { o.err |= kErrRetries; break; }
+    __syncwarp();
+    if (lane == 0) R.set(y, R.get(y) | (1u << x));
+    __syncwarp();
+  }
+  // compute_metrics: lane y owns row y
+  const int unreachable = (W - 2) * (W - 2) + 1;
+  const uint32_t interior = ((W >= 32) ? 0xffffffffu : ((1u << W) - 1u)) & ~1u & ~(1u << (W - 1));
+  const bool inner = lane >= 1 && lane < W - 1;
+  const uint32_t row = (lane < W) ? R.get(lane) : 0u;
+  int n = inner ? __popc(row & interior) : 0;
+  for (int s = 16; s > 0; s >>= 1) n += __shfl_xor_sync(0xffffffffu, n, s);
+  o.met = make_int4(n, abs(o.gx - o.sx) + abs(o.gy - o.sy), 0, unreachable);
+  const uint32_t fr = inner ? (~row & interior) : 0u;
+  uint32_t reach = (lane == o.sy) ? (1u << o.sx) : 0u;
+  for (int dd = 1; dd <= unreachable; dd++) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, reach, 1), dn = __shfl_down_sync(0xffffffffu, reach, 1);
+    const uint32_t v = (reach | (reach << 1) | (reach >> 1) | (lane > 0 ? up : 0u) | (lane < 31 ? dn : 0u)) & fr;
+    const bool changed = __any_sync(0xffffffffu, v != reach);
+    reach = v;
+    const uint32_t grow = __shfl_sync(0xffffffffu, reach, o.gy);
+    if ((grow >> o.gx) & 1u) { o.met.z = 1; o.met.w = dd; break; }
+    if (!changed) break;
+  }
+  return o;
+}
+
 // place_obj over the whole grid, warp-uniform (all lanes see the same draws and the same shared-memory rows)
-__device__ __forceinline__ bool coop_place_random(const Rows &R, int gx, int gy, bool has_agent, int ax, int ay, CoopRng &rng, int W,
+template <typename RNG>
+__device__ __forceinline__ bool coop_place_random(const Rows &R, int gx, int gy, bool has_agent, int ax, int ay, RNG &rng, int W,
                                                   int max_tries, int &ox, int &oy) {
   int tries = 0;
   for (;;) {
     if (max_tries >= 0 && tries > max_tries) return false;
+    if (!rng.ok()) return false;  // look-ahead window exhausted (speculation only)
     tries++;
     const int x = rng.randint(0, W), y = rng.randint(0, W);
     const bool empty = !((R.get(y) >> x) & 1u) && !(x == gx && y == gy) && !(has_agent && x == ax && y == ay);
@@ -516,7 +682,6 @@ __device__ __noinline__ uint4 coop_reset_random(Dev d, uint32_t *col, int stride
   const int W = c.W;
   const Rows R{col, stride};
   Env e = unpack(hot);
-  uint32_t err = 0;
   if (c.fixed_env) {  // self.seed(self.seed_value) (adversarial.py:542-543); deferred respawns of the old stream are moot
     if (lane == 0) mt_seed(d, env, d.limbs[env], d.limbs[(size_t)d.N + env], (int)d.limbs[2 * (size_t)d.N + env]);
     __syncwarp();
@@ -529,57 +694,253 @@ __device__ __noinline__ uint4 coop_reset_random(Dev d, uint32_t *col, int stride
   e.step_count = 0;
   uint32_t adv = d.adv[env];
   uint32_t adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
-  e.has_agent = 0; e.adir = e.sdir; e.done_flag = 0;
-  e.sx = e.sy = kNone; e.gx = e.gy = kNone;
-  // gen_grid: lane y writes row y
-  __syncwarp();
-  if (lane < W) {
-    const uint32_t full = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
-    R.set(lane, (lane == 0 || lane == W - 1) ? full : (1u | (1u << (W - 1))));
-  }
-  __syncwarp();
-  if (!coop_place_random(R, kNone, kNone, false, 0, 0, rng, W, 100, x, y)) err |= kErrRetries;
-  e.gx = x; e.gy = y;
-  e.sdir = rng.randint(0, 4);
-  coop_place_random(R, e.gx, e.gy, false, 0, 0, rng, W, -1, x, y);
-  e.sx = x; e.sy = y; e.has_agent = 1; e.ax = x; e.ay = y;
   if (n_walls < 0) n_walls = c.n_clutter / 2;
   else { adv_max = (uint32_t)n_walls + 2; sampled = 1; }
-  for (int i = 0; i < n_walls; i++) {
-    if (!coop_place_random(R, e.gx, e.gy, true, e.ax, e.ay, rng, W, 100, x, y)) { err |= kErrRetries; break; }
-    __syncwarp();
-    if (lane == 0) R.set(y, R.get(y) | (1u << x));
-    __syncwarp();
-  }
+  const LevelOut o = coop_level_core(R, rng, W, n_walls, lane);
   rng.store();
   adv = 0u | (adv_max << 12) | (sampled << 24);
-  // compute_metrics: lane y owns row y
-  const int unreachable = (W - 2) * (W - 2) + 1;
-  const uint32_t interior = ((W >= 32) ? 0xffffffffu : ((1u << W) - 1u)) & ~1u & ~(1u << (W - 1));
-  const bool inner = lane >= 1 && lane < W - 1;
-  const uint32_t row = (lane < W) ? R.get(lane) : 0u;
-  int n = inner ? __popc(row & interior) : 0;
-  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-  int4 met = make_int4(n, abs(e.gx - e.sx) + abs(e.gy - e.sy), 0, unreachable);
-  {
-    const uint32_t fr = inner ? (~row & interior) : 0u;
-    uint32_t reach = (lane == e.sy) ? (1u << e.sx) : 0u;
-    for (int dd = 1; dd <= unreachable; dd++) {
-      const uint32_t up = __shfl_up_sync(0xffffffffu, reach, 1), dn = __shfl_down_sync(0xffffffffu, reach, 1);
-      const uint32_t v = (reach | (reach << 1) | (reach >> 1) | (lane > 0 ? up : 0u) | (lane < 31 ? dn : 0u)) & fr;
-      const bool changed = __any_sync(0xffffffffu, v != reach);
-      reach = v;
-      const uint32_t grow = __shfl_sync(0xffffffffu, reach, e.gy);
-      if ((grow >> e.gx) & 1u) { met.z = 1; met.w = dd; break; }
-      if (!changed) break;
-    }
-  }
+  e.gx = o.gx; e.gy = o.gy; e.sx = o.sx; e.sy = o.sy; e.sdir = o.sdir;
+  uint32_t err = o.err;
   if (!reset_agent(e)) err |= kErrNoStart;
   if (lane == 0) {
-    d.adv[env] = adv; d.metrics[env] = met;
+    d.adv[env] = adv; d.metrics[env] = o.met;
     if (err) d.err[env] |= err;
   }
   return pack(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SPECULATION of the DR auto-reset.  In step_env(reset_random=True) the env RNG is consumed by exactly two things: the
+// goal respawn (multigrid.py:821-838: draws that depend only on the current level) and reset_random itself.  So when a
+// level starts, its successor is already determined up to ONE bit -- did the episode end at the goal (respawn draws
+// first) or not -- and both candidates can be built ahead of time, off the step's critical path.  A regeneration job
+// (one warp per env) settles the MT state, computes a look-ahead window of tempered words (all derivable from the
+// present state: < 227 words), builds both candidate levels from it in shared memory and stores them as records; the
+// step kernel then resets a finished env by COPYING the right record (no RNG, no flood fill) and queues the env for its
+// next regeneration, which runs in the tail of the same launch (k_step_env's regeneration phase).
+// ---- warp-PARALLEL level construction from the look-ahead window ------------------------------------------------
+// reset_random is a chain of rejection-sampled placements; run literally it is ~5 k dependent instructions (20+ us on
+// one warp, however the work is split).  From a window of already tempered words it parallelises:
+//   * acceptance of a word by randint(0, W) (masked rejection) is a per-word predicate -> 7 ballots;
+//   * a placement TRY starting at word i consumes up to the second accepted word: nxt(i), cell(i) are per-position
+//     functions -> two byte tables built by all lanes; the k-th try after position p is k applications of nxt:
+//     pointer jumping (tables for 1, 2, 4 ... 64 steps);
+//   * the goal / start-direction / agent placements are 1-2 tries each (a short uniform walk); the wall tries are
+//     enumerated 32 at a time, one per lane: a try places a wall iff its cell is interior, not the goal, not the agent
+//     and not the cell of an EARLIER try (__match_any_sync + the rows placed by earlier rounds); the placement stops
+//     at the try holding the n_walls-th success (n-th set bit of the success ballot).
+// Anything irregular (window exhausted, more than kSpecTries wall tries) just marks the candidate invalid: the step
+// kernel then rebuilds that env the slow way.
+constexpr int kSpecTries = 96, kSpecLevels = 7, kSpecOver = 255;
+struct SpecTables {
+  uint32_t *win;    // [kSpecWindow] tempered words
+  uint32_t *am;     // [8] acceptance masks (bit j of am[c]: word 32c+j accepted), am[7] = 0
+  uint16_t *cell;   // [kSpecWindow] x | y << 5 of the try starting here
+  uint8_t *jump;    // [kSpecLevels][kSpecWindow + 32] start of the (2^l)-th next try (kSpecOver: beyond the window)
+};
+__device__ __forceinline__ int spec_first_acc(const uint32_t *am, int i) {
+  if (i >= kSpecWindow) return kSpecOver;
+  int c = i >> 5;
+  uint32_t m = am[c] & (0xffffffffu << (i & 31));
+  while (m == 0) {
+    if (++c >= kSpecWindow / 32) return kSpecOver;
+    m = am[c];
+  }
+  return c * 32 + __ffs(m) - 1;
+}
+__device__ __forceinline__ void spec_build_tables(const SpecTables &T, int W, int lane) {
+  const uint32_t rng = (uint32_t)(W - 1), mask = 0xffffffffu >> __clz(rng);
+#pragma unroll
+  for (int c = 0; c < kSpecWindow / 32; c++) {
+    const uint32_t m = __ballot_sync(0xffffffffu, (T.win[32 * c + lane] & mask) <= rng);
+    if (lane == 0) T.am[c] = m;
+  }
+  if (lane == 0) T.am[kSpecWindow / 32] = 0;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < kSpecWindow / 32; c++) {
+    const int i = 32 * c + lane;
+    const int px = spec_first_acc(T.am, i);
+    const int py = (px == kSpecOver) ? kSpecOver : spec_first_acc(T.am, px + 1);
+    const bool ok = py != kSpecOver;
+    T.jump[i] = ok ? (uint8_t)(py + 1) : (uint8_t)kSpecOver;
+    T.cell[i] = ok ? (uint16_t)((T.win[px] & mask) | ((T.win[py] & mask) << 5)) : (uint16_t)0;
+  }
+  if (lane < 32) T.jump[kSpecWindow + lane] = (uint8_t)kSpecOver;  // positions >= window: absorbing
+  __syncwarp();
+  constexpr int S = kSpecWindow + 32;
+  for (int l = 1; l < kSpecLevels; l++) {
+    const uint8_t *src = T.jump + (l - 1) * S;
+    uint8_t *dst = T.jump + l * S;
+#pragma unroll
+    for (int c = 0; c < S / 32; c++) {
+      const int i = 32 * c + lane;
+      const int m = src[i];
+      dst[i] = (m >= kSpecWindow) ? (uint8_t)kSpecOver : src[m];
+    }
+    __syncwarp();
+  }
+}
+
+// wall count + Manhattan distance + reachability / hop count with lane y owning row y (compute_metrics, adversarial.py:407-447)
+__device__ __forceinline__ int4 coop_metrics(uint32_t row, int gx, int gy, int sx, int sy, int W, int lane) {
+  const int unreachable = (W - 2) * (W - 2) + 1;
+  const uint32_t interior = ((W >= 32) ? 0xffffffffu : ((1u << W) - 1u)) & ~1u & ~(1u << (W - 1));
+  const bool inner = lane >= 1 && lane < W - 1;
+  int n = inner ? __popc(row & interior) : 0;
+  for (int s = 16; s > 0; s >>= 1) n += __shfl_xor_sync(0xffffffffu, n, s);
+  int4 met = make_int4(n, abs(gx - sx) + abs(gy - sy), 0, unreachable);
+  const uint32_t fr = inner ? (~row & interior) : 0u;
+  uint32_t reach = (lane == sy) ? (1u << sx) : 0u;
+  for (int dd = 1; dd <= unreachable; dd++) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, reach, 1), dn = __shfl_down_sync(0xffffffffu, reach, 1);
+    const uint32_t v = (reach | (reach << 1) | (reach >> 1) | (lane > 0 ? up : 0u) | (lane < 31 ? dn : 0u)) & fr;
+    const bool changed = __any_sync(0xffffffffu, v != reach);
+    reach = v;
+    const uint32_t grow = __shfl_sync(0xffffffffu, reach, gy);
+    if ((grow >> gx) & 1u) { met.z = 1; met.w = dd; break; }
+    if (!changed) break;
+  }
+  return met;
+}
+
+// One candidate level.  `respawn`: first replay the goal respawn's draws against the current level `cur` (goal cgx, cgy).
+// Returns false when the window / try budget did not suffice.  `lvl` = 32 words of shared memory (the new rows).
+__device__ __forceinline__ bool spec_level(const SpecTables &T, const uint32_t *cur, int cgx, int cgy, bool respawn, uint32_t *lvl, int W,
+                                           int n_walls, int lane, LevelOut &o, int &consumed) {
+  constexpr int S = kSpecWindow + 32;
+  int p = 0;
+  o.err = 0;
+  auto interior = [W](int x, int y) { return x >= 1 && x < W - 1 && y >= 1 && y < W - 1; };
+  if (respawn) {
+    for (;;) {  // place_obj(max_tries unbounded) on the current level, agent off the grid
+      const int q = T.jump[p];
+      if (q == kSpecOver) return false;
+      const int c = T.cell[p], x = c & 31, y = c >> 5;
+      p = q;
+      if (!((cur[y] >> x) & 1u) && !(x == cgx && y == cgy)) break;
+      if (p >= kSpecWindow) return false;
+    }
+  }
+  if (p >= kSpecWindow) return false;
+  for (;;) {  // goal: first interior cell (the fresh grid is empty inside its border)
+    const int q = T.jump[p];
+    if (q == kSpecOver) return false;
+    const int c = T.cell[p];
+    p = q;
+    o.gx = c & 31; o.gy = c >> 5;
+    if (interior(o.gx, o.gy)) break;
+    if (p >= kSpecWindow) return false;
+  }
+  if (p >= kSpecWindow) return false;
+  o.sdir = (int)(T.win[p] & 3u);  // randint(0, 4): one word, never rejected
+  p++;
+  if (p >= kSpecWindow) return false;
+  for (;;) {  // agent: interior and not the goal
+    const int q = T.jump[p];
+    if (q == kSpecOver) return false;
+    const int c = T.cell[p];
+    p = q;
+    o.sx = c & 31; o.sy = c >> 5;
+    if (interior(o.sx, o.sy) && !(o.sx == o.gx && o.sy == o.gy)) break;
+    if (p >= kSpecWindow) return false;
+  }
+  // fresh grid: lane y writes row y
+  __syncwarp();
+  if (lane < W) {
+    const uint32_t full = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
+    lvl[lane] = (lane == 0 || lane == W - 1) ? full : (1u | (1u << (W - 1)));
+  }
+  __syncwarp();
+  consumed = p;
+  int placed = 0;
+  bool done = n_walls == 0;
+  for (int r = 0; r < kSpecTries / 32 && !done; r++) {
+    const int k = 32 * r + lane;
+    int tp = p;  // start of this lane's try: k applications of nxt
+#pragma unroll
+    for (int l = 0; l < kSpecLevels; l++)
+      if ((k >> l) & 1) tp = T.jump[l * S + tp];
+    const int q = (tp < kSpecWindow) ? (int)T.jump[tp] : kSpecOver;
+    const bool complete = q != kSpecOver;
+    const int c = complete ? (int)T.cell[tp] : 0, x = c & 31, y = c >> 5;
+    const bool valid = complete && interior(x, y) && !(x == o.gx && y == o.gy) && !(x == o.sx && y == o.sy);
+    const unsigned mm = __match_any_sync(0xffffffffu, valid ? c : (0x10000 + lane));
+    const bool success = valid && (lane == __ffs(mm) - 1) && !((lvl[y] >> x) & 1u);
+    const unsigned sm = __ballot_sync(0xffffffffu, success);
+    const int cnt = __popc(sm), need = n_walls - placed;
+    int last = 32;  // lanes <= last place their wall
+    if (cnt >= need) {  // the need-th set bit of the success mask
+      unsigned t = sm;
+      for (int i = 1; i < need; i++) t &= t - 1;
+      last = __ffs(t) - 1;
+      done = true;
+    }
+    __syncwarp();
+    if (success && lane <= last) atomicOr(&lvl[y], 1u << x);
+    if (done) {
+      consumed = __shfl_sync(0xffffffffu, q, last);  // the try holding the last wall is complete (it succeeded)
+    } else {
+      placed += cnt;
+      const int comp = __shfl_sync(0xffffffffu, (int)complete, 31);  // the window must cover the whole round
+      if (!comp) return false;
+    }
+    __syncwarp();
+  }
+  return done;  // metrics are computed lazily (kMetricsDirty): no getter reads them inside a rollout
+}
+
+// One regeneration job = ONE candidate (k = 0: the episode ends without a goal, 1: at the goal) of one env, one warp.
+// The env's MT state is settled (the step kernel applies a committed record's words when it commits), so a job only
+// READS env state and writes its own record and validity bit.
+__device__ __noinline__ void rr_regen_job(Dev d, int job, int lane, uint32_t *scr /* 1024 words of shared memory */) {
+  const Cfg &c = d.c;
+  const int e = job >> 1, k = job & 1;
+  const int W = c.W, RW = cand_words(W);
+  SpecTables T;
+  T.win = scr; T.am = scr + kSpecWindow; uint32_t *cur = scr + kSpecWindow + 8, *lvl = cur + 32;
+  T.cell = reinterpret_cast<uint16_t *>(lvl + 32);
+  T.jump = reinterpret_cast<uint8_t *>(T.cell + kSpecWindow);
+  const size_t N = d.N;
+  const uint32_t idx = d.mti[e];
+  const uint4 hot = d.hot[e];
+  cur[lane] = (k == 1 && lane < W) ? env_rows(d, e).get(lane) : 0xffffffffu;
+  // look-ahead window: tempered outputs idx .. idx + kSpecWindow - 1 of the present state (nothing is stored to mt)
+#pragma unroll
+  for (int i = 0; i < kSpecWindow / 32; i++) {
+    uint32_t p = idx + lane + 32 * i, p1 = p + 1, pm = p + 397;
+    if (p >= 624) p -= 624;
+    if (p1 >= 624) p1 -= 624;
+    if (pm >= 624) pm -= 624;
+    if (pm >= 624) pm -= 624;
+    const uint32_t x = d.mt[p * N + e], b = d.mt[p1 * N + e], cc = d.mt[pm * N + e];
+    uint32_t y = (x & 0x80000000u) | (b & 0x7fffffffu);
+    y = cc ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    T.win[lane + 32 * i] = y;
+  }
+  const Env s = unpack(hot);
+  __syncwarp();
+  spec_build_tables(T, W, lane);
+  LevelOut o;
+  int consumed = 0;
+  const bool ok = spec_level(T, cur, s.gx, s.gy, k == 1, lvl, W, c.n_clutter / 2, lane, o, consumed);
+  __syncwarp();
+  if (ok) {
+    uint32_t *rec = d.cand + ((size_t)e * 2 + k) * RW;
+    if (lane < W) rec[lane] = lvl[lane];
+    if (lane == 0) {
+      rec[W] = ((uint32_t)o.gx & 31u) | (((uint32_t)o.gy & 31u) << 5) | (1u << 10) | (((uint32_t)o.sx & 31u) << 11) |
+               (((uint32_t)o.sy & 31u) << 16) | (1u << 21) | ((uint32_t)o.sdir << 22);
+      rec[W + 5] = (uint32_t)consumed;
+      rec[W + 6] = o.err;
+    }
+    __syncwarp();
+    if (lane == 0) { __threadfence(); atomicOr(&d.spec[e], k ? kSpecValid1 : kSpecValid0); }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

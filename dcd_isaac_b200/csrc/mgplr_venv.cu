@@ -49,6 +49,8 @@ struct mgplr_venv {
   uint8_t *res_pin_dev;    // the same allocation as the device sees it
   uint32_t host_steps;     // host-driven steps issued (selects the ping-pong counter)
   int pdl;                 // launch the step kernel with programmatic stream serialization
+  int rr_spec;             // DR auto-reset: speculative next-level candidates (MGPLR_RR_SPEC=0 disables)
+  int rr_grid;             // co-resident CTA capacity of the DR step kernel (its regeneration phase spins on grid-wide progress)
   int sm_count;
 };
 
@@ -437,7 +439,11 @@ __global__ void k_flush(Dev d) {
 __global__ void k_get_metrics(Dev d, int32_t *m) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
-  const int4 v = d.metrics[e];
+  int4 v = d.metrics[e];
+  if (v.z == kMetricsDirty) {  // level taken from a speculative candidate record: metrics are computed on demand
+    v = compute_metrics(env_rows(d, e), unpack(d.hot[e]), d.c.W, true);
+    d.metrics[e] = v;
+  }
   m[4 * e] = v.x; m[4 * e + 1] = v.y; m[4 * e + 2] = v.z; m[4 * e + 3] = v.w;
 }
 __global__ void k_get_agent_state(Dev d, int32_t *o) {
@@ -466,15 +472,16 @@ struct StepArgs {
   uint32_t *done_count_next;     // the counter of the NEXT host-driven step, zeroed by this launch
   mgplr_done_record *done_list;  // device view of pinned host memory: records cross PCIe as posted writes
   uint8_t *flags_host;           // second flags destination (mapped pinned host memory) or NULL
+  int spec;                      // DR auto-reset: speculative next-level candidates enabled (mgplr_env.cuh "SPECULATION")
 };
 
 // ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
 
 // agent_is_done's respawn (multigrid.py:821-838): `count` random empty cells drawn with the env RNG (the deferred
 // ones first, see Env::pending).  Returns the last one as x | y<<8.
-__device__ __noinline__ uint32_t rare_respawn(uint32_t *mt, uint32_t *mti, uint32_t *words, int N, int e, uint32_t *rows,
+__device__ __noinline__ uint32_t rare_respawn(uint32_t *mt, uint32_t *mti, uint32_t *words, uint32_t *spec, int N, int e, uint32_t *rows,
                                               int stride, int W, int gx, int gy, int count) {
-  RngSlow rng(mt, mti, words, N, e);
+  RngSlow rng(mt, mti, words, spec, N, e);
   const uint32_t p = replay_respawns(Rows{rows, stride}, gx, gy, rng, W, count);
   rng.store();
   return p;
@@ -526,7 +533,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
       // agent_is_done: remove the agent, done, respawn (dir forced to 0, multigrid.py:668-672); reward = _reward()
       s.done_flag = 1;
       if (RR || (want_trunc && s.elapsed + 1 >= c.max_episode_steps) || s.pending >= kMaxPending) {
-        const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.N, e, rows, stride, c.W, s.gx, s.gy, s.pending + 1);
+        const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.spec, d.N, e, rows, stride, c.W, s.gx, s.gy, s.pending + 1);
         s.pending = 0; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
       } else s.pending++;
       rew = __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)s.step_count, (double)c.max_steps)));
@@ -734,7 +741,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   // records, so the NEXT launch is allowed to become resident as this one's CTAs retire and to run its on-chip
   // prologue; it blocks at griddepcontrol.wait (below) until this grid has completed and its writes are visible.
   asm volatile("griddepcontrol.launch_dependents;");
-  if (tile >= n_tiles) return;
+  if (!RR && tile >= n_tiles) return;  // (the DR variant's idle warps still serve the regeneration phase)
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
   // the state plane of every observation is all zero: written once here, never touched by emit_packed_f32
 #pragma unroll
@@ -744,10 +751,15 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
   if (A.done_count_next && blockIdx.x == 0 && threadIdx.x == 0) *A.done_count_next = 0;
   // prologue: first tile's rows and scalars
-  warp_issue_rows(d, s_rows, &bars[0], tile, lane, pol_keep);
+  if (tile < n_tiles) warp_issue_rows(d, s_rows, &bars[0], tile, lane, pol_keep);
   uint4 nh = make_uint4(0, 0, 0, 0);
   int na = 6;
-  if (tile * kWarpTile + lane < N) { nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep); na = (int)A.action[tile * kWarpTile + lane]; }
+  uint32_t nsp = 0;  // speculation word of the env (DR variant)
+  const bool use_spec = RR && A.spec;
+  if (tile < n_tiles && tile * kWarpTile + lane < N) {
+    nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep); na = (int)A.action[tile * kWarpTile + lane];
+    if (use_spec) nsp = d.spec[tile * kWarpTile + lane];
+  }
   uint32_t phase = 0;  // bit s = parity to wait for on bars[s]
   for (int k = 0; tile < n_tiles; tile += total, k++) {
     const int st = k & 1, base = tile * kWarpTile, e = base + lane;
@@ -755,13 +767,17 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     const bool valid = lane < n_tile;
     const uint4 h = nh;
     const int a = na;
+    const uint32_t sp = nsp;
     uint32_t *rows = s_rows + st * W * kWarpTile;
     // prefetch the next tile into the other stage (its last readers, the previous tile, are done: __syncwarp)
     const int next = tile + total;
     __syncwarp();
     if (next < n_tiles) {
       warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane, pol_keep);
-      if (next * kWarpTile + lane < N) { nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_keep); na = (int)A.action[next * kWarpTile + lane]; }
+      if (next * kWarpTile + lane < N) {
+        nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_keep); na = (int)A.action[next * kWarpTile + lane];
+        if (use_spec) nsp = d.spec[next * kWarpTile + lane];
+      }
     }
     mbar_wait(&bars[st], (phase >> st) & 1u);
     phase ^= 1u << st;
@@ -772,6 +788,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     uint32_t flags = 0;
     double rew = 0.0;
     bool dirty = false, need_rr = false;
+    int cand_pick = -1;  // DR variant: candidate record to reset from (0 no goal / 1 goal), -1 = none
+    int cand_used = 0;   // MT words that record consumed
     float fin_ret = 0.f;
     int fin_len = 0;
     if (valid) {
@@ -785,8 +803,11 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         if (fx == s.gx && fy == s.gy) {
           // agent_is_done (multigrid.py:821-838): done; the respawn draw is deferred unless something observes it
           s.done_flag = 1;
-          if (RR || (want_trunc && s.elapsed + 1 >= c.max_episode_steps) || s.pending >= kMaxPending) {
-            const uint32_t p = rare_respawn(d.mt, d.mti, d.words, N, e, rows + lane, kWarpTile, W, s.gx, s.gy, s.pending + 1);
+          // DR variant with a valid goal candidate: its record already accounts for the respawn draws (SPECULATION)
+          const bool observed = want_trunc && s.elapsed + 1 >= c.max_episode_steps;
+          if (use_spec && (sp & kSpecValid1) && !observed && s.pending == 0) cand_pick = 1;
+          else if (RR || observed || s.pending >= kMaxPending) {
+            const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.spec, N, e, rows + lane, kWarpTile, W, s.gx, s.gy, s.pending + 1);
             s.pending = 0; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
           } else s.pending++;
           rew = __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)s.step_count, (double)c.max_steps)));  // _reward()
@@ -810,18 +831,43 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         if (A.o.ep_return) A.o.ep_return[e] = s.ep_ret;
         if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
         s.ep_ret = 0.f; s.ep_len = 0;
-        if (RR) need_rr = true;  // worker.step_env (parallel_wrappers.py:27-37): reset_random below, warp-converged
-        else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+        if (RR) {  // worker.step_env (parallel_wrappers.py:27-37): reset_random
+          if (use_spec && !(flags & MGPLR_F_GOAL) && (sp & kSpecValid0) && s.pending == 0) cand_pick = 0;
+          if (cand_pick >= 0) {
+            // take the pre-built successor level: goal / start (rows and the MT advance are done warp-wide below)
+            const uint32_t *rec = d.cand + ((size_t)e * 2 + cand_pick) * cand_words(W) + W;
+            const uint32_t gs = rec[0], cerr = rec[6];
+            cand_used = (int)rec[5];
+            s.gx = gs & 31; s.gy = (gs >> 5) & 31; s.sx = (gs >> 11) & 31; s.sy = (gs >> 16) & 31; s.sdir = (gs >> 22) & 3;
+            d.metrics[e] = make_int4(0, 0, kMetricsDirty, 0);  // recomputed on demand by mgplr_get_metrics
+            d.adv[e] &= ~0xfffu;  // adversary_step_count = 0 (adversarial.py:546)
+            if (cerr) d.err[e] |= cerr;
+            reset_agent(s);
+            dirty = true;
+          } else need_rr = true;  // no candidate: rebuilt below, warp-converged
+        } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
       } else if ((A.last_step & 3) == 3 && want_trunc) {
         rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
       }
     }
     if (RR) {
-      // Finished envs get a fresh random level.  Few per tile (the common case): the warp rebuilds them one at a time
-      // cooperatively; many (a synchronized time-limit storm): every lane rebuilds its own (lane-parallel).
+      // committed candidate records, all lanes together per finished env: one coalesced W-word read of the rows, and
+      // the words the record consumed are applied to the env's MT state (so regeneration jobs only read env state)
+      for (unsigned rest = __ballot_sync(0xffffffffu, cand_pick >= 0); rest; rest &= rest - 1) {
+        const int le = __ffs(rest) - 1, env = base + le;
+        const int pick = __shfl_sync(0xffffffffu, cand_pick, le), used_w = __shfl_sync(0xffffffffu, cand_used, le);
+        const uint32_t *rec = d.cand + ((size_t)env * 2 + pick) * cand_words(W);
+        if (lane < W) rows[lane * kWarpTile + le] = rec[lane];
+        uint32_t idx = d.mti[env], used = d.words[env];
+        coop_mt_advance(d, env, lane, idx, used, used_w);
+        if (lane == 0) { d.mti[env] = idx; d.words[env] = used; d.spec[env] = 0; }
+      }
+      __syncwarp();
+      // Finished envs without a candidate get a fresh random level the slow way.  Few per tile: the warp rebuilds them
+      // one at a time cooperatively; many (a synchronized time-limit storm): every lane rebuilds its own.
       const unsigned m = __ballot_sync(0xffffffffu, need_rr);
       if (m) {
-        dirty = need_rr;
+        dirty = dirty || need_rr;
         if (__popc(m) > 10) {
           if (need_rr)
             s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1,
@@ -865,10 +911,67 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
       if (RR && dirty) {
         const Rows G = env_rows(d, e);
         for (int r = 0; r < W; r++) G.set(r, rows[r * kWarpTile + lane]);
+        if (use_spec) {  // queue the env: its next candidates are built in the regeneration phase of this launch
+          __threadfence();
+          const uint32_t k = atomicAdd(&d.sched[0], 2u);
+          *(volatile int32_t *)&d.rr_list[k] = 2 * e; *(volatile int32_t *)&d.rr_list[k + 1] = 2 * e + 1;
+        }
       }
     }
   }
   if (lane == 0) bulk_wait_read0();
+  unsigned long long prof_t0 = 0;
+  if (RR && d.prof && lane == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t0));
+    atomicMax(&d.prof[1], prof_t0);            // end of the last warp's tiles
+    atomicMin(&d.prof[0], prof_t0);            // end of the first warp's tiles
+  }
+  if (RR && use_spec) {
+    // ---- regeneration phase: warps that are past their tiles take tickets on the job list until it is drained.
+    // A ticket beyond the current count waits for either the slot to fill or every warp to be past its tiles.
+    __syncwarp();
+    __threadfence();
+    if (lane == 0) atomicAdd(&d.sched[1], 1u);
+    uint32_t *scr = reinterpret_cast<uint32_t *>(s_obs);  // the observation tile is free now
+    for (;;) {
+      int job = -1, env = -1;
+      if (lane == 0) {
+        job = (int)atomicAdd(&d.sched[2], 1u);
+        for (;;) {
+          env = *(volatile int32_t *)&d.rr_list[job];
+          if (env >= 0) break;
+          if (*(volatile uint32_t *)&d.sched[1] == (uint32_t)total) {  // every append is visible by now
+            __threadfence();
+            env = *(volatile int32_t *)&d.rr_list[job];
+            break;
+          }
+          __nanosleep(100);
+        }
+        if (env >= 0) *(volatile int32_t *)&d.rr_list[job] = -1;  // the slot is empty again for the next launch
+      }
+      env = __shfl_sync(0xffffffffu, env, 0);
+      if (env < 0) break;
+      __threadfence();
+      const long long c0 = clock64();
+      rr_regen_job(d, env, lane, scr);
+      __syncwarp();
+      if (d.prof && lane == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - c0);
+        atomicAdd(&d.prof[3], dt); atomicAdd(&d.prof[4], 1ull); atomicMax(&d.prof[5], dt);
+      }
+    }
+    if (d.prof && lane == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicMax(&d.prof[2], t1);               // end of the regeneration phase
+    }
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(&d.sched[3], 1u) == (uint32_t)total - 1u) {  // last warp out: reset the scheduler for the next launch
+        d.sched[0] = 0; d.sched[1] = 0; d.sched[2] = 0; d.sched[3] = 0;
+      }
+    }
+  }
 }
 
 // T transitions in one launch from a recorded action stream u8 [T][N]; state stays on chip and the observation
@@ -986,8 +1089,21 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(dalloc(&d.limbs, 3 * N, total));
   CK(dalloc(&d.words, N, total));
   CK(dalloc(&d.err, N, total));
-  CK(dalloc(&d.sched, 2, total));
-  CK(cudaMemset(d.sched, 0, 2 * sizeof(uint32_t)));
+  CK(dalloc(&d.sched, 4, total));
+  CK(cudaMemset(d.sched, 0, 4 * sizeof(uint32_t)));
+  CK(dalloc(&d.spec, N, total));
+  CK(cudaMemset(d.spec, 0, N * sizeof(uint32_t)));
+  CK(dalloc(&d.cand, N * 2 * (size_t)cand_words(cfg->width), total));
+  CK(dalloc(&d.rr_list, 2 * N + kRrListSlack, total));
+  CK(cudaMemset(d.rr_list, 0xff, (2 * N + kRrListSlack) * sizeof(int32_t)));
+  // off by default: measured at parity with the in-kernel rebuild -- a regeneration job is a ~15 us
+  // dependent chain on its warp however it is parallelised, and it sits on the launch's critical path
+  v->rr_spec = getenv("MGPLR_RR_SPEC") ? atoi(getenv("MGPLR_RR_SPEC")) : 0;
+  d.prof = nullptr;
+  if (getenv("MGPLR_RR_PROF")) {  // debug: phase timestamps / job cycles of the DR step kernel (mgplr_debug_prof)
+    CK(cudaMalloc((void **)&d.prof, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(d.prof, 0, 8 * sizeof(unsigned long long)));
+  }
   CK(dalloc(&v->seed_scratch, 4 * N, total));
   CK(dalloc(&v->act_dev, N, total));
   CK(dalloc(&v->cnt_dev, 2, total));
@@ -1031,8 +1147,19 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
   cudaSetDevice(v->device);
   Dev &d = v->d;
   cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
-  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->cnt_dev); cudaFreeHost(v->res_pin);
+  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(d.spec); cudaFree(d.cand); cudaFree(d.rr_list); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->cnt_dev); cudaFreeHost(v->res_pin);
   delete v;
+}
+
+// debug (MGPLR_RR_PROF=1): out[0..5] = first / last warp past its tiles, end of regeneration (globaltimer ns), job cycles sum,
+// jobs, max job cycles -- of the launches since the last call; resets the counters
+extern "C" int mgplr_debug_prof(mgplr_venv *v, unsigned long long *out) {
+  if (!v || !v->d.prof) return fail(MGPLR_E_BADARG, "profiling is off (MGPLR_RR_PROF)");
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, v->d.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+  CK(cudaMemcpy(v->d.prof, init, sizeof(init), cudaMemcpyHostToDevice));
+  return 0;
 }
 
 extern "C" int32_t mgplr_venv_num_envs(const mgplr_venv *v) { return v ? v->d.N : 0; }
@@ -1184,9 +1311,23 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   const int n_tiles = (v->d.N + kWarpTile - 1) / kWarpTile;
   const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
   int grid = v->sm_count * per_sm;
+  const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
+  A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample;
+  if (A.spec) {
+    // the regeneration phase waits on grid-wide progress: every CTA of the grid must be resident at the same time
+    if (!v->rr_grid) {
+      int per = 0;
+#define OCC(SEE, EXT) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_step_env<SEE, true, EXT>, wpc * 32, smem))
+      if (narrow) { if (see) OCC(true, uint32_t); else OCC(false, uint32_t); }
+      else { if (see) OCC(true, uint64_t); else OCC(false, uint64_t); }
+#undef OCC
+      if (per < 1) return fail(MGPLR_E_UNSUPPORTED, "DR step kernel does not fit on an SM");
+      v->rr_grid = per * v->sm_count;
+    }
+    if (grid > v->rr_grid) grid = v->rr_grid;
+  }
   const int need = (n_tiles + wpc - 1) / wpc;
   if (grid > need) grid = need;
-  const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = dim3(grid); lc.blockDim = dim3(wpc * 32); lc.dynamicSmemBytes = smem; lc.stream = st;

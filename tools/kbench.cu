@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <vector>
 #include "../include/mgplr.h"
+extern "C" int mgplr_debug_prof(mgplr_venv *v, unsigned long long *out);
 
 #define CKC(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("cuda %s line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 #define CKM(x) do { int rc = (x); if (rc) { printf("mgplr rc=%d %s line %d\n", rc, mgplr_last_error(), __LINE__); exit(1);} } while (0)
@@ -68,6 +69,20 @@ int main(int argc, char **argv) {
     for (int t = 0; t < T; t++) {
       float msx; cudaEventElapsedTime(&msx, ev[t + 1], ev[t + 2]);
       if (msx * 1e3 > 80.0 || t < 2) printf("trace: step %d  %.1f us\n", t, msx * 1e3);
+    }
+  }
+  if (getenv("MGPLR_RR_PROF")) {  // phase timing of single DR launches
+    unsigned long long pr[8];
+    mgplr_debug_prof(v, pr);
+    for (int t = 0; t < 6; t++) {
+      mgplr_step_out o = {};
+      o.image = img + (size_t)(t + 1) * N * 75; o.reward = rew + (size_t)t * N; o.flags = fl + (size_t)t * N;
+      CKM(mgplr_step_env(v, act + (size_t)t * N, rr, nullptr, 0, &o, st));
+      CKC(cudaStreamSynchronize(st));
+      mgplr_debug_prof(v, pr);
+      printf("prof step %d: tiles first->last %.1f us, regen phase %.1f us, jobs %llu, avg %.1f us, max %.1f us\n", t,
+             (pr[1] - pr[0]) * 1e-3, pr[2] > pr[1] ? (pr[2] - pr[1]) * 1e-3 : 0.0, pr[4], pr[4] ? pr[3] / (double)pr[4] / 1965.0 : 0.0,
+             pr[5] / 1965.0);
     }
   }
   cudaGraph_t g; cudaGraphExec_t ge;
