@@ -52,6 +52,7 @@ SYMBOLS = (
     'mgplr_reset_random', 'mgplr_reset_to_encoding', 'mgplr_load_levels', 'mgplr_reset_to_actions', 'mgplr_mutate_edits',
     'mgplr_mutate_finalize', 'mgplr_step_env', 'mgplr_step_env_host', 'mgplr_rollout', 'mgplr_get_encodings',
     'mgplr_get_metrics', 'mgplr_get_agent_state', 'mgplr_get_errors', 'mgplr_peek_rng', 'mgplr_gae',
+    'mgplr_discounted_returns', 'mgplr_batched_value_loss',
     'mgplr_plr_episode_scores', 'mgplr_plr_sample_weights', 'mgplr_plr_score_weights', 'mgplr_plr_sample_replay',
 )
 
@@ -102,6 +103,8 @@ def load():
     L.mgplr_get_errors.argtypes = [vp, vp, i32, vp]
     L.mgplr_peek_rng.argtypes = [vp, i32, vp, i32]
     L.mgplr_gae.argtypes = [vp, vp, vp, vp, i32, i32, f64, f64, vp]
+    L.mgplr_discounted_returns.argtypes = [vp, vp, vp, i32, i32, f64, vp]
+    L.mgplr_batched_value_loss.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     L.mgplr_plr_episode_scores.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp]
     L.mgplr_plr_sample_weights.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, i32, f64, vp, vp, vp]
     L.mgplr_plr_score_weights.argtypes = [vp, vp, i32, i32, f64, f64, vp, vp]

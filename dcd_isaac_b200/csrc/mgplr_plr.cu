@@ -49,6 +49,58 @@ extern "C" int mgplr_gae(const float *rewards, const float *value_preds, const f
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ discounted returns
+// returns[t] = (returns[t+1] * gamma) * masks[t+1] + rewards[t]  (algos/storage.py:276-279), one thread per actor
+__global__ void k_discounted_returns(const float *__restrict__ rewards, const float *__restrict__ masks, float *__restrict__ returns,
+                                     int T, int N, float gamma) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  float ret = returns[(size_t)T * N + e];
+  for (int t = T - 1; t >= 0; t--) {
+    ret = __fadd_rn(__fmul_rn(__fmul_rn(ret, gamma), masks[(size_t)(t + 1) * N + e]), rewards[(size_t)t * N + e]);
+    returns[(size_t)t * N + e] = ret;
+  }
+}
+
+extern "C" int mgplr_discounted_returns(const float *rewards, const float *masks, float *returns, int32_t T, int32_t N, double gamma,
+                                        void *stream) {
+  if (!rewards || !masks || !returns || T < 1 || N < 1) return pfail(MGPLR_E_BADARG, "mgplr_discounted_returns: bad arguments");
+  k_discounted_returns<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, masks, returns, T, N, (float)gamma);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ batched value loss
+// per-actor mean over the rollout of |ret - v| / (ret - v) / max(ret - v, 0), optionally ^power, optionally clamped
+// (algos/storage.py:290-327).  The per-step term is float32 like the reference's; the T-term sum is accumulated in
+// double and rounded once (torch's float32 column sum differs from it by rounding only: tests use 1e-5 relative).
+__global__ void k_batched_value_loss(const float *__restrict__ returns, const float *__restrict__ values, int T, int N, int mode,
+                                     int power, int clipped, float *__restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  double acc = 0.0;
+  for (int t = 0; t < T; t++) {
+    float td = __fsub_rn(returns[(size_t)t * N + e], values[(size_t)t * N + e]);
+    if (mode == 0) td = fabsf(td);
+    else if (mode == 2) td = fmaxf(td, 0.0f);
+    float p = td;
+    for (int k = 1; k < power; k++) p = __fmul_rn(p, td);
+    acc += (double)p;
+  }
+  float m = (float)(acc / (double)T);
+  if (clipped) m = fminf(fmaxf(m, -1.0f), 1.0f);
+  out[e] = m;
+}
+
+extern "C" int mgplr_batched_value_loss(const float *returns, const float *value_preds, int32_t T, int32_t N, int32_t mode,
+                                        int32_t power, int32_t clipped, float *out, void *stream) {
+  if (!returns || !value_preds || !out || T < 1 || N < 1 || mode < 0 || mode > 2 || power < 1 || power > 16)
+    return pfail(MGPLR_E_BADARG, "mgplr_batched_value_loss: bad arguments");
+  k_batched_value_loss<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(returns, value_preds, T, N, mode, power, clipped, out);
+  PCK(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ episode scores
 // done[t] = !(masks[t] > 0) for t in 0..T.  An episode is [start_t, t) for every done step t >= 1
 // (t == 0 is skipped WITHOUT moving start_t, level_sampler.py:504-505).

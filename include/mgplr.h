@@ -188,6 +188,19 @@ int mgplr_peek_rng(mgplr_venv *v, int32_t index, uint32_t *words_host, int32_t c
 int mgplr_gae(const float *rewards, const float *value_preds, const float *masks, float *returns, int32_t T,
               int32_t N, double gamma, double gae_lambda, void *stream);
 
+/* RolloutStorage.compute_discounted_returns (algos/storage.py:258-279): returns[T] must hold the bootstrap value
+ * (value_preds[-1], or its truncated / denormalised version); rows T-1..0 are filled with
+ * returns[t+1] * gamma * masks[t+1] + rewards[t] in float32, the reference's operand order. */
+int mgplr_discounted_returns(const float *rewards, const float *masks, float *returns, int32_t T, int32_t N, double gamma,
+                             void *stream);
+
+/* RolloutStorage.get_batched_value_loss(batched=True) (algos/storage.py:290-327), used for ACCEL's base-level scores
+ * (adversarial_runner.py:608-613,762-770).  returns / value_preds f32 [T+1][N] (rows 0..T-1 are used).
+ * mode 0: |returns - value|, 1: signed, 2: positive part; power > 1 raises the per-step term to that power;
+ * out f32 [N] = mean over the T steps, clamped to [-1, 1] when `clipped`. */
+int mgplr_batched_value_loss(const float *returns, const float *value_preds, int32_t T, int32_t N, int32_t mode,
+                             int32_t power, int32_t clipped, float *out, void *stream);
+
 #define MGPLR_SCORE_POSITIVE_VALUE_LOSS 0
 #define MGPLR_SCORE_SIGNED_VALUE_LOSS 1
 #define MGPLR_SCORE_VALUE_L1 2

@@ -201,9 +201,118 @@ def gen_weights():
     print('weights fixtures ok')
 
 
+class _StubPopart(object):
+    def denormalize(self, x):
+        return x
+
+
+class _StubModel(object):
+    """A deterministic stand-in critic for the truncated-value path (the NN itself is out of scope): the value of an
+    observation is a fixed linear functional of its image plus its direction."""
+
+    def __init__(self):
+        import torch
+        g = torch.Generator().manual_seed(5)
+        self.w = torch.randn(75, generator=g) * 0.05
+
+    def get_value(self, obs, rnn_hxs, masks):
+        img = obs['image'].reshape(-1, 75)
+        return (img @ self.w).unsqueeze(-1) + 0.1 * obs['direction'].reshape(-1, 1)
+
+
+def gen_storage():
+    """algos/storage.py beyond GAE, executed: discounted returns, get_batched_value_loss variants,
+    get_action_traj(as_string), insert / after_update bookkeeping and the truncated-value path
+    (use_proper_time_limits) with a stub critic."""
+    import numpy as np
+    import torch
+    from gym import spaces
+    from algos.storage import RolloutStorage
+    rs = np.random.RandomState(23)
+    out = {}
+    for tag, T, N in (('a', 256, 32), ('b', 33, 5)):
+        st, _ = _storage(T, N, rs)
+        nv = torch.from_numpy(rs.randn(N, 1).astype(np.float32))
+        acts = rs.randint(0, 7, size=(T, N, 1))
+        st.actions.copy_(torch.from_numpy(acts))
+        st.compute_returns(nv, False, 0.995, 0.95)
+        out['rewards_' + tag] = st.rewards.numpy()[:, :, 0].copy()
+        out['values_' + tag] = st.value_preds.numpy()[:, :, 0].copy()
+        out['masks_' + tag] = st.masks.numpy()[:, :, 0].copy()
+        out['disc_returns_' + tag] = st.returns.numpy()[:, :, 0].copy()
+        st.compute_returns(nv, True, 0.995, 0.95)
+        out['gae_returns_' + tag] = st.returns.numpy()[:, :, 0].copy()
+        k = 0
+        for signed, pos in ((False, False), (True, False), (False, True)):
+            for power in (1, 2):
+                for clipped in (True, False):
+                    out['bvl_%s_%d' % (tag, k)] = st.get_batched_value_loss(signed=signed, positive_only=pos, power=power,
+                                                                            clipped=clipped, batched=True).numpy()[:, 0].copy()
+                    out['bvl_params_%s_%d' % (tag, k)] = np.array([signed, pos, power, clipped], np.int32)
+                    k += 1
+        out['bvl_scalar_' + tag] = np.float64(st.get_batched_value_loss(signed=False, positive_only=True, batched=False))
+        out['actions_' + tag] = acts[:, :, 0].astype(np.int64)
+        out['traj_' + tag] = np.array(st.get_action_traj(as_string=True))
+    # insert / truncated obs / after_update, then the truncated-value GAE
+    T, N = 24, 6
+    obs_space = {'image': spaces.Box(0, 255, (3, 5, 5), 'uint8'), 'direction': spaces.Box(0, 3, (1,), 'uint8')}
+    st = RolloutStorage(model=_StubModel(), num_steps=T, num_processes=N, observation_space=obs_space,
+                        action_space=spaces.Discrete(7), recurrent_hidden_state_size=4, recurrent_arch='lstm',
+                        use_proper_time_limits=True)
+    st.model.popart = _StubPopart()
+    first = {'image': torch.from_numpy(rs.rand(N, 3, 5, 5).astype(np.float32)), 'direction': torch.from_numpy(rs.randint(0, 4, (N, 1)).astype(np.float32))}
+    st.copy_obs_to_index(first, 0)
+    ins = []
+    for t in range(T):
+        obs = {'image': torch.from_numpy(rs.rand(N, 3, 5, 5).astype(np.float32)),
+               'direction': torch.from_numpy(rs.randint(0, 4, (N, 1)).astype(np.float32))}
+        hx = (torch.from_numpy(rs.randn(N, 4).astype(np.float32)), torch.from_numpy(rs.randn(N, 4).astype(np.float32)))
+        action = torch.from_numpy(rs.randint(0, 7, (N, 1)))
+        logp = torch.from_numpy(rs.randn(N, 1).astype(np.float32))
+        logd = torch.from_numpy(rs.randn(N, 7).astype(np.float32))
+        val = torch.from_numpy(rs.randn(N, 1).astype(np.float32))
+        rew = torch.from_numpy((rs.rand(N, 1) < 0.1).astype(np.float32))
+        done = rs.rand(N) < 0.15
+        trunc = done & (rs.rand(N) < 0.5)
+        if t == T - 1:
+            done[:] = True
+        masks = torch.from_numpy(1.0 - done.astype(np.float32)).unsqueeze(-1)
+        bad = torch.from_numpy(1.0 - trunc.astype(np.float32)).unsqueeze(-1)
+        cliff = torch.ones(N, 1)
+        seeds = torch.from_numpy(rs.randint(1, 100, (N, 1)).astype(np.int32))
+        tr_obs = {}
+        for i in np.nonzero(trunc)[0]:
+            tr = {'image': rs.rand(3, 5, 5).astype(np.float32), 'direction': rs.randint(0, 4, (1,)).astype(np.float32)}
+            st.insert_truncated_obs({k: torch.from_numpy(v) for k, v in tr.items()}, index=int(i))
+            tr_obs[int(i)] = tr
+        st.insert(obs, hx, action, logp, logd, val, rew, masks, bad, level_seeds=seeds, cliffhanger_masks=cliff)
+        ins.append(dict(obs={k: v.numpy() for k, v in obs.items()}, hx=[h.numpy() for h in hx], action=action.numpy(),
+                        logp=logp.numpy(), logd=logd.numpy(), val=val.numpy(), rew=rew.numpy(), masks=masks.numpy(),
+                        bad=bad.numpy(), cliff=cliff.numpy(), seeds=seeds.numpy(), trunc=tr_obs))
+    nv = torch.from_numpy(rs.randn(N, 1).astype(np.float32))
+    st.compute_returns(nv, True, 0.995, 0.95)
+    final = dict(first={k: v.numpy() for k, v in first.items()}, inserts=ins, next_value=nv.numpy(),
+                 obs={k: v.numpy().copy() for k, v in st.obs.items()},
+                 truncated_obs={k: v.numpy().copy() for k, v in st.truncated_obs.items()},
+                 recurrent_hidden_states=st.recurrent_hidden_states.numpy().copy(), actions=st.actions.numpy().copy(),
+                 action_log_probs=st.action_log_probs.numpy().copy(), action_log_dist=st.action_log_dist.numpy().copy(),
+                 value_preds=st.value_preds.numpy().copy(), rewards=st.rewards.numpy().copy(), masks=st.masks.numpy().copy(),
+                 bad_masks=st.bad_masks.numpy().copy(), level_seeds=st.level_seeds.numpy().copy(),
+                 truncated_value_preds=st.truncated_value_preds.numpy().copy(), returns=st.returns.numpy().copy(),
+                 stub_w=st.model.w.numpy().copy(), step=st.step)
+    st.after_update()
+    final['after_update'] = dict(obs0={k: v[0].numpy().copy() for k, v in st.obs.items()}, masks0=st.masks[0].numpy().copy(),
+                                 bad0=st.bad_masks[0].numpy().copy(), rnn0=st.recurrent_hidden_states[0].numpy().copy())
+    np.savez_compressed(os.path.join(GOLDEN, 'plr_storage.npz'), **out)
+    with gzip.open(os.path.join(GOLDEN, 'plr_storage_session.pkl.gz'), 'wb') as f:
+        pickle.dump(final, f, protocol=4)
+    print('storage fixtures', len(out), 'arrays + 1 session')
+
+
 def gen_plr():
     rh.activate()
     gen_gae()
+    gen_storage()
     gen_weights()
     gen_sampler()
 

@@ -3,6 +3,7 @@ dcd_isaac_b200).  Pinned by tests/test_plr_oracle.py against fixtures produced b
 (oracle/gen_golden_plr.py -> tests/golden/plr_*.npz / .pkl.gz).
 
   gae             RolloutStorage.compute_gae_returns        algos/storage.py:233-256
+  discounted_returns / batched_value_loss   algos/storage.py:258-279,290-327
   episode_scores  LevelSampler._update_with_rollouts + score functions   level_replay/level_sampler.py:486-549,307-349
   sample_weights  LevelSampler.sample_weights / _score_transform          level_sampler.py:726-785
   sample_replay   _sample_replay_level + _update_staleness                level_sampler.py:664-680,601-604
@@ -23,6 +24,38 @@ def gae(rewards, values, masks, gamma, gae_lambda):
         acc = delta + (gl32 * m[t + 1]) * acc
         out[t] = acc + v[t]
     return out
+
+
+def discounted_returns(rewards, masks, last_value, gamma):
+    """RolloutStorage.compute_discounted_returns (algos/storage.py:258-279): rewards [T,N], masks [T+1,N], last_value [N]
+    -> returns [T+1,N], float32 op by op."""
+    f = np.float32
+    T = rewards.shape[0]
+    out = np.zeros((T + 1, rewards.shape[1]), f)
+    out[T] = last_value
+    g = f(gamma)
+    for t in reversed(range(T)):
+        out[t] = (out[t + 1] * g) * masks[t + 1].astype(f) + rewards[t].astype(f)
+    return out
+
+
+def batched_value_loss(returns, values, signed=False, positive_only=False, power=1, clipped=True):
+    """RolloutStorage.get_batched_value_loss(batched=True) (algos/storage.py:290-327): returns/values [T+1,N] -> [N]."""
+    f = np.float32
+    td = returns[:-1].astype(f) - values[:-1].astype(f)
+    if signed:
+        pass
+    elif positive_only:
+        td = np.maximum(td, f(0))
+    else:
+        td = np.abs(td)
+    p = td.copy()
+    for _ in range(1, power):
+        p = p * td
+    m = p.astype(np.float64).mean(0).astype(f)
+    if clipped:
+        m = np.clip(m, f(-1), f(1))
+    return m
 
 
 def episode_scores(masks, cliff, returns, values, rewards, seeds, strategy):

@@ -29,3 +29,18 @@ def test_sample_weights_and_draws():
         idx, stale = po.sample_replay(g['scores_' + tag], g['stale_' + tag], g['unseen_' + tag], g['u_' + tag], **kw)
         assert np.array_equal(idx, g['picks_' + tag])
         assert np.array_equal(stale, g['stale_after_' + tag])
+
+
+def test_storage_returns_and_value_loss():
+    """discounted returns bit-exact, batched value loss to 1e-6 against the executed reference RolloutStorage."""
+    g = golden('plr_storage.npz')
+    for tag in 'ab':
+        ret = po.discounted_returns(g['rewards_' + tag], g['masks_' + tag], g['values_' + tag][-1], 0.995)
+        assert np.array_equal(ret, g['disc_returns_' + tag]), tag
+        k = 0
+        while 'bvl_%s_%d' % (tag, k) in g.files:
+            signed, pos, power, clipped = [int(x) for x in g['bvl_params_%s_%d' % (tag, k)]]
+            got = po.batched_value_loss(g['gae_returns_' + tag], g['values_' + tag], bool(signed), bool(pos), power, bool(clipped))
+            assert np.allclose(got, g['bvl_%s_%d' % (tag, k)], rtol=1e-5, atol=1e-7), (tag, k)
+            k += 1
+        assert k == 12
