@@ -157,9 +157,10 @@ constexpr int kFuseAdvMaxEnvs = 16384;
 // mode 0: image only; 1: AdversarialEnv.reset first; 2: step_adversary(loc) first -- the state update of the group's
 // envs runs on the first n_env threads of the same CTA, so reset()/step_adversary() + observation is ONE launch.
 // FUSED is a template parameter so that the image-only instance keeps its small register footprint (occupancy).
+// raw != 0: unscaled codes (obs['full_obs'] of MultiGridFullyObsWrapper) instead of /10.
 template <bool FUSED>
 __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *time_step, int mode, const int64_t *loc,
-                                                   uint8_t *done) {
+                                                   uint8_t *done, int raw = 0) {
   RNG_SCRATCH();
   extern __shared__ __align__(128) float s_img[];
   const int W = d.c.W, WW = W * W, per_env = 3 * WW;
@@ -190,6 +191,11 @@ __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *t
     else if ((env_rows(d, e).get(y) >> x) & 1u) { t = 0.2f; c = 0.5f; }
     else if (x == s.gx && y == s.gy) { t = 0.8f; c = 0.1f; }
     else { t = 0.1f; c = 0.0f; }
+    if (raw) {  // exact small integers (0.2f * 10 is not 2.0f)
+      t = (t == 1.0f) ? 10.f : (t == 0.2f) ? 2.f : (t == 0.8f) ? 8.f : 1.f;
+      c = (c == 0.5f) ? 5.f : (c == 0.1f) ? 1.f : 0.f;
+      st = (s.has_agent && x == s.ax && y == s.ay) ? (float)s.adir : 0.f;
+    }
     float *o = s_img + k * per_env + cell;
     o[0] = t; o[WW] = c; o[2 * WW] = st;
   }
@@ -489,12 +495,24 @@ __device__ __noinline__ uint32_t rare_respawn(uint32_t *mt, uint32_t *mti, uint3
 
 // info['truncated_obs'] (time_limit.py:29-31) / runner cliffhanger obs (adversarial_runner.py:523-528)
 __device__ __noinline__ void rare_emit_trunc(uint32_t *rows, int stride, uint4 hot, int W, int see, float *image, float *direction,
-                                             int e) {
+                                             int e, float *full = nullptr) {
   const Env s = unpack(hot);
   const Rows R{rows, stride};
   const View v = see ? render_view<true>(R, s, W) : render_view<false>(R, s, W);
   if (image) emit_obs_f32(v, image + (size_t)e * kObsFloats);
   if (direction) direction[e] = (float)s.adir;
+  if (full) {  // MultiGridFullyObsWrapper.agent_observation on the pre-reset state: raw codes, [3][W][W] indexed [c][x][y]
+    float *o = full + (size_t)e * 3 * W * W;
+    for (int x = 0; x < W; x++)
+      for (int y = 0; y < W; y++) {
+        float t, c, st = 0.f;
+        if (s.has_agent && x == s.ax && y == s.ay) { t = 10.f; c = 0.f; st = (float)s.adir; }
+        else if ((R.get(y) >> x) & 1u) { t = 2.f; c = 5.f; }
+        else if (x == s.gx && y == s.gy) { t = 8.f; c = 1.f; }
+        else { t = 1.f; c = 0.f; }
+        o[x * W + y] = t; o[W * W + x * W + y] = c; o[2 * W * W + x * W + y] = st;
+      }
+  }
 }
 
 // worker.step_env's reset_random branch (parallel_wrappers.py:30-33)
@@ -522,7 +540,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
   const Rows R{rows, stride};
   uint32_t flags = 0;
   double rew = 0.0;
-  const bool want_trunc = A.o.trunc_image || A.o.trunc_direction;
+  const bool want_trunc = A.o.trunc_image || A.o.trunc_direction || A.o.trunc_full_obs;
   // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
   s.step_count++;
   const int fx = s.ax + ((s.adir == 0) - (s.adir == 2)), fy = s.ay + ((s.adir == 1) - (s.adir == 3));
@@ -545,7 +563,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
   s.elapsed++;
   if (s.elapsed >= c.max_episode_steps) {
     flags |= MGPLR_F_TRUNC_KEY | (done ? 0u : MGPLR_F_TRUNC_VAL);
-    if (want_trunc) rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+    if (want_trunc) rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e, A.o.trunc_full_obs);
     done = true;
   }
   // VecMonitor.step_wait (vec_monitor.py:60-85): eprets(f32) += rews(f64) is evaluated in double
@@ -562,7 +580,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
       rows_dirty = true;
     } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
   } else if ((A.last_step & 3) == 3 && want_trunc) {
-    rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+    rare_emit_trunc(rows, stride, pack(s), c.W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e, A.o.trunc_full_obs);
   }
   const PackedView v = render_packed<SEE, EXT>(R, s, c.W);
   emit_packed_f32<SEE, false>(v, s_obs);
@@ -793,7 +811,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     float fin_ret = 0.f;
     int fin_len = 0;
     if (valid) {
-      const bool want_trunc = A.o.trunc_image || A.o.trunc_direction;
+      const bool want_trunc = A.o.trunc_image || A.o.trunc_direction || A.o.trunc_full_obs;
       // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
       s.step_count++;
       const int fx = s.ax + ((s.adir == 0) - (s.adir == 2)), fy = s.ay + ((s.adir == 1) - (s.adir == 3));
@@ -819,7 +837,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
       s.elapsed++;
       if (s.elapsed >= c.max_episode_steps) {
         flags |= MGPLR_F_TRUNC_KEY | (done ? 0u : MGPLR_F_TRUNC_VAL);
-        if (want_trunc) rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+        if (want_trunc) rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e, A.o.trunc_full_obs);
         done = true;
       }
       // VecMonitor.step_wait (vec_monitor.py:60-85): eprets(f32) += rews(f64) is evaluated in double
@@ -847,7 +865,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
           } else need_rr = true;  // no candidate: rebuilt below, warp-converged
         } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
       } else if ((A.last_step & 3) == 3 && want_trunc) {
-        rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e);
+        rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e, A.o.trunc_full_obs);
       }
     }
     if (RR) {
@@ -1007,6 +1025,7 @@ __global__ void __launch_bounds__(TILE) k_rollout(Dev d, const uint8_t *actions,
     if (A.o.ep_length) A.o.ep_length += off;
     if (A.o.trunc_image) A.o.trunc_image += off * kObsFloats;
     if (A.o.trunc_direction) A.o.trunc_direction += off;
+    if (A.o.trunc_full_obs) A.o.trunc_full_obs += off * 3 * W * W;
     if (A.o.masks) A.o.masks += off;
     if (A.o.bad_masks) A.o.bad_masks += off;
     if (A.o.cliffhanger_masks) A.o.cliffhanger_masks += off;
@@ -1200,11 +1219,11 @@ extern "C" int mgplr_seed(mgplr_venv *v, const uint32_t *limbs_host, const int32
 }
 
 static int launch_adv_image(mgplr_venv *v, float *adv_image, float *time_step, int mode, const int64_t *loc, uint8_t *done,
-                            cudaStream_t st) {
+                            cudaStream_t st, int raw = 0) {
   const size_t smem = (size_t)kAdvGroup * 3 * v->d.c.W * v->d.c.W * sizeof(float);
   const int grid = (v->d.N + kAdvGroup - 1) / kAdvGroup;
   if (mode) k_adv_image<true><<<grid, 128, smem, st>>>(v->d, adv_image, time_step, mode, loc, done);
-  else k_adv_image<false><<<grid, 128, smem, st>>>(v->d, adv_image, time_step, 0, nullptr, nullptr);
+  else k_adv_image<false><<<grid, 128, smem, st>>>(v->d, adv_image, time_step, 0, nullptr, nullptr, raw);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1433,6 +1452,12 @@ extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, i
 #undef LAUNCH
   CK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mgplr_full_obs(mgplr_venv *v, float *full_obs, void *stream) {
+  NEED(v);
+  if (!full_obs) return fail(MGPLR_E_BADARG, "full_obs is NULL");
+  return launch_adv_image(v, full_obs, nullptr, 0, nullptr, nullptr, st, 1);
 }
 
 extern "C" int mgplr_get_encodings(mgplr_venv *v, uint8_t *enc, void *stream) {

@@ -37,7 +37,8 @@ def seed_limbs(seed):
 
 
 class CudaAdversarialVecEnv(object):
-    def __init__(self, env_name, num_envs, device='cuda:0', seed=None, fixed_environment=None, spec=None, **overrides):
+    def __init__(self, env_name, num_envs, device='cuda:0', seed=None, fixed_environment=None, spec=None, full_obs=False,
+                 **overrides):
         if spec is None:
             spec = env_spec(env_name, fixed_environment=fixed_environment, **overrides)
         self.env_name = env_name
@@ -76,6 +77,11 @@ class CudaAdversarialVecEnv(object):
             'time_step': Box(0, self.adversary_max_steps, (1,), 'uint8'),
             'random_z': Box(0, 1.0, (self.random_z_dim,), 'float32')}
         self.adversary_action_space = Discrete(self.adversary_action_dim)
+        # MultiGridFullyObsWrapper (util/__init__.py:175-178 with --use_global_critic / --use_global_policy): every agent
+        # observation also carries 'full_obs' = the whole grid's encoding, channels first, unscaled
+        self.full_obs = bool(full_obs)
+        if self.full_obs:
+            self.observation_space['full_obs'] = Box(0, 255, (3, self.W, self.W), 'uint8')
         self.processed_action_dim = 1
         # persistent small device buffers
         dev = self.device
@@ -103,6 +109,14 @@ class CudaAdversarialVecEnv(object):
         n = self.num_envs if n is None else n
         obs = {'image': torch.empty(n, 3, 5, 5, dtype=torch.float32, device=self.device),
                'direction': torch.empty(n, 1, dtype=torch.float32, device=self.device)}
+        return obs
+
+    def _add_full_obs(self, obs):
+        """MultiGridFullyObsWrapper.agent_observation (multigrid_wrappers.py:30-44) for all envs: one launch."""
+        if self.full_obs:
+            full = torch.empty(self.num_envs, 3, self.W, self.W, dtype=torch.float32, device=self.device)
+            check(self.L.mgplr_full_obs(self.h, ptr(full), self._stream()), 'mgplr_full_obs')
+            obs['full_obs'] = full
         return obs
 
     def _out(self, obs=None, **kw):
@@ -197,7 +211,7 @@ class CudaAdversarialVecEnv(object):
         o = self._out(obs)
         check(self.L.mgplr_reset_agent(self.h, C.byref(o), self._stream()), 'mgplr_reset_agent')
         self._raise_errors()
-        return obs
+        return self._add_full_obs(obs)
 
     def reset_random(self):
         self._assert_not_closed()
@@ -208,7 +222,7 @@ class CudaAdversarialVecEnv(object):
             nw = torch.from_numpy(np.random.randint(0, self.n_clutter, size=self.num_envs).astype(np.int32)).to(self.device)
         check(self.L.mgplr_reset_random(self.h, ptr(nw), C.byref(o), self._stream()), 'mgplr_reset_random')
         self._raise_errors()
-        return obs
+        return self._add_full_obs(obs)
 
     def _levels_to_device(self, levels):
         """list of levels -> ('bytes', u8 [n,W,W,3]) or ('str', i32 [n,len])."""
@@ -233,7 +247,7 @@ class CudaAdversarialVecEnv(object):
             check(self.L.mgplr_reset_to_actions(self.h, ptr(data), ln, ptr(idx), n, C.byref(o), self._stream()),
                   'mgplr_reset_to_actions')
         self._raise_errors()
-        return obs
+        return self._add_full_obs(obs)
 
     def reset_to_level(self, level, index):
         """venv.reset_to_level(level, index) -> obs of that env, leading dim 1 (parallel_wrappers.py:334-340)."""
@@ -308,6 +322,9 @@ class CudaAdversarialVecEnv(object):
         rew = torch.empty(N, 1, dtype=torch.float32, device=self.device)
         o = self._out(obs, reward=rew, flags=self._flags, ep_return=self._ep_r, ep_length=self._ep_l,
                       trunc_image=tr['image'], trunc_direction=tr['direction'])
+        if self.full_obs:
+            tr['full_obs'] = torch.empty(N, 3, self.W, self.W, dtype=torch.float32, device=self.device)
+            o.trunc_full_obs = ptr(tr['full_obs'])
         a = torch.as_tensor(action)
         if reset_random and self.resample_n_clutter:
             raise NotImplementedError('step_env(reset_random=True) with resample_n_clutter: use step_env_device')
@@ -338,12 +355,12 @@ class CudaAdversarialVecEnv(object):
                 info = infos[i]
                 if flags[i] & F_TRUNC_KEY:
                     info['truncated'] = bool(flags[i] & F_TRUNC_VAL)
-                    info['truncated_obs'] = {'image': tr['image'][i], 'direction': tr['direction'][i]}
+                    info['truncated_obs'] = {k: v[i] for k, v in tr.items()}
                 if flags[i] & F_DONE:
                     info['episode'] = {'r': ep_r[i], 'l': ep_l[i], 't': t_now}
             if (flags & F_DONE).any():
                 self._check_errors_lazily()
-        return obs, rew, done, infos
+        return self._add_full_obs(obs), rew, done, infos
 
     def _check_errors_lazily(self):
         self._raise_errors()
@@ -456,7 +473,7 @@ class CudaMazeVecEnv(CudaAdversarialVecEnv):
     auto-`reset()` on done (parallel_wrappers.py:20-25), VecMonitor episode infos, preprocessed float32 observations.
     Same step / render kernels as the adversarial env; the level is loaded once with mgplr_load_levels."""
 
-    def __init__(self, env_name, num_envs, device='cuda:0'):
+    def __init__(self, env_name, num_envs, device='cuda:0', full_obs=False):
         from .mazes import MAZES
         if env_name not in MAZES:
             raise KeyError('No registered env with id: %s' % env_name)
@@ -464,7 +481,7 @@ class CudaMazeVecEnv(CudaAdversarialVecEnv):
         spec = dict(n_clutter=0, size=m['size'], choose_goal_last=True, see_through_walls=True, max_steps=m['max_steps'],
                     max_episode_steps=32767, resample_n_clutter=False, editor_actions='walls_none_agent_goal',
                     fixed_environment=False)
-        super().__init__(env_name, num_envs, device=device, spec=spec)
+        super().__init__(env_name, num_envs, device=device, spec=spec, full_obs=full_obs)  # eval.py:200-202
         self.maze = m
         W = m['size']
         if 'goal' in m:
@@ -499,7 +516,7 @@ class CudaMazeVecEnv(CudaAdversarialVecEnv):
         check(self.L.mgplr_load_levels(self.h, ptr(self._levels), int(self._levels.shape[0]), ptr(self._level_index), 0,
                                        C.byref(o), self._stream()), 'mgplr_load_levels')
         self._raise_errors()
-        return obs
+        return self._add_full_obs(obs)
 
     def step(self, action):
         """venv.step(action): worker.step auto-reset()s on done (parallel_wrappers.py:20-25); for a fixed maze that is the
@@ -517,7 +534,8 @@ def create_parallel_env(args, adversary=True, device='cuda:0'):
         raise NotImplementedError('only the MultiGrid adversarial environments are built (SURVEY.md 8)')
     singleton = bool(getattr(args, 'singleton_env', False))
     venv = CudaAdversarialVecEnv(args.env_name, args.num_processes, device=device,
-                                 fixed_environment=True if singleton else None)
+                                 fixed_environment=True if singleton else None,
+                                 full_obs=bool(getattr(args, 'use_global_critic', False) or getattr(args, 'use_global_policy', False)))
     if singleton:
         seeds = [args.seed] * args.num_processes
     else:

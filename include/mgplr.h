@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MGPLR_ABI_VERSION 1
+#define MGPLR_ABI_VERSION 2
 
 #define MGPLR_E_BADARG (-1)
 #define MGPLR_E_UNSUPPORTED (-2)
@@ -67,6 +67,7 @@ typedef struct mgplr_step_out {
   float *bad_masks;         /* f32 [N][1] 0 iff TRUNC_KEY   (adversarial_runner.py:568-570) */
   float *cliffhanger_masks; /* f32 [N][1] 0 iff cliffhanger (adversarial_runner.py:571-573) */
   uint8_t *image_u8;        /* u8  [N][5][5][3] raw gym_minigrid encoding (packed secondary layout) */
+  float *trunc_full_obs;    /* f32 [N][3][W][W] info['truncated_obs']['full_obs'] (MultiGridFullyObsWrapper), where TRUNC_KEY */
 } mgplr_step_out;
 
 const char *mgplr_last_error(void);
@@ -166,6 +167,11 @@ int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset
  * [T][N][1], reward [T][N][1], flags u8 [T][N]; masks f32 [T][N][1] etc.  Any may be NULL. */
 int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random,
                   const mgplr_step_out *out_t0, void *stream);
+
+/* obs['full_obs'] of MultiGridFullyObsWrapper (envs/wrappers/multigrid_wrappers.py:14-51; used with
+ * --use_global_critic / --use_global_policy, util/__init__.py:175-178): the whole grid's encoding with the agent cell
+ * (10, 0, dir), channels first and NOT scaled (obs_wrappers.py:108-110 only transposes it): f32 [N][3][W][W]. */
+int mgplr_full_obs(mgplr_venv *v, float *full_obs, void *stream);
 
 /* Getters (parallel_wrappers.py:422-448): encodings u8 [N][W][W][3] = AdversarialEnv.encoding;
  * metrics i32 [N][4] = n_clutter_placed, distance_to_goal, passable, shortest_path_length. */

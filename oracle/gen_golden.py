@@ -160,6 +160,49 @@ def gen_venv():
         venv.close()
 
 
+def gen_fullobs():
+    """MultiGridFullyObsWrapper (use_global_critic / use_global_policy, util/__init__.py:175-178): the real vectorised
+    path with the extra 'full_obs' observation, through reset_random / reset_agent / step_env / reset_to_level."""
+    import numpy as np
+    import torch
+    from types import SimpleNamespace
+    import util
+    for tag, env_name in (('gl15', 'MultiGrid-GoalLastAdversarial-v0'), ('tl50', 'MultiGrid-GoalLastAdversarialEnv30-v0')):
+        N, T = 4, 140
+        args = SimpleNamespace(env_name=env_name, seed=1, singleton_env=False, use_global_critic=True,
+                               use_global_policy=False, num_processes=N, normalize_returns=False)
+        venv, _ = util.create_parallel_env(args)
+        out = dict(env_name=env_name, space_shape=np.array(venv.observation_space['full_obs'].shape))
+        for mode in (False, True):
+            m = 'random' if mode else 'agent'
+            venv.set_seed(list(range(N)))
+            o = venv.reset_random()
+            out['rr_full_' + m] = o['full_obs'].numpy().copy()
+            o = venv.reset_agent()
+            out['first_full_' + m] = o['full_obs'].numpy().copy()
+            out['first_image_' + m] = o['image'].numpy().copy()
+            rs = np.random.RandomState(7)
+            acts = np.stack([_biased_actions(rs, N) for _ in range(T)])
+            full, img, dones, tfull, tkey = [], [], [], [], []
+            for t in range(T):
+                o, r, d, infos = venv.step_env(torch.from_numpy(acts[t].astype(np.int64)).view(N, 1), reset_random=mode)
+                full.append(o['full_obs'].numpy().copy()); img.append(o['image'].numpy().copy()); dones.append(np.array(d, dtype=bool))
+                tkey.append([('truncated_obs' in i) for i in infos])
+                tfull.append([i['truncated_obs']['full_obs'].numpy() if ('truncated_obs' in i and 'full_obs' in i['truncated_obs'])
+                              else np.zeros(out['space_shape'], np.float32) for i in infos])
+            out['actions_' + m] = acts
+            out['full_' + m] = np.stack(full); out['image_' + m] = np.stack(img); out['done_' + m] = np.stack(dones)
+            out['trunc_key_' + m] = np.array(tkey); out['trunc_full_' + m] = np.array(tfull, dtype=np.float32)
+        enc = venv.get_encodings()
+        o = venv.reset_to_level_batch(enc)
+        out['level_full'] = o['full_obs'].numpy().copy()
+        out['level_enc'] = np.stack(venv.get_encodings())
+        np.savez_compressed(os.path.join(GOLDEN, 'fullobs_%s.npz' % tag), **out)
+        print('fullobs', tag, out['space_shape'], 'episodes', int(out['done_agent'].sum()), int(out['done_random'].sum()),
+              'trunc', int(out['trunc_key_agent'].sum()))
+        venv.close()
+
+
 ADV_CASES = [
     ('gl50', 'MultiGrid-GoalLastAdversarial-v0'),
     ('fb25_opaque', 'MultiGrid-GoalLastFewerBlocksOpaqueWallsAdversarial-v0'),
@@ -296,7 +339,7 @@ def main():
     a = ap.parse_args()
     rh.activate()
     os.makedirs(GOLDEN, exist_ok=True)
-    todo = {'env': gen_env_traces, 'venv': gen_venv, 'adv': gen_adversary, 'mutate': gen_mutate}
+    todo = {'env': gen_env_traces, 'venv': gen_venv, 'fullobs': gen_fullobs, 'adv': gen_adversary, 'mutate': gen_mutate}
     try:
         from gen_golden_plr import gen_plr
         todo['plr'] = gen_plr
