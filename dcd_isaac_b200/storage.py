@@ -260,10 +260,15 @@ class RolloutStorage(object):
     # ---- returns (algos/storage.py:208-288)
     def _compute_truncated_value_preds(self):
         """value_preds with the critic's value of the truncated observation wherever bad_masks == 0 (`:208-231`).
-        One batched critic call over all (step, process) pairs, in the reference's process-major order."""
+        One batched critic call over all (step, process) pairs, in the reference's process-major order.
+        Reference quirk kept: `steps = (...).nonzero().squeeze()` is 0-dimensional for a process with exactly ONE
+        truncated step, and `len(steps.shape) == 0` then skips that process (`:213-215`) -- only processes with two or
+        more truncated steps get truncated values."""
         self.truncated_value_preds.copy_(self.value_preds)
         with torch.no_grad():
-            idx = (self.bad_masks[:, :, 0].t() == 0).nonzero()  # rows (process, step), process-major
+            bad = self.bad_masks[:, :, 0].t() == 0  # [process, step]
+            bad = bad & (bad.sum(1, keepdim=True) >= 2)
+            idx = bad.nonzero()  # rows (process, step), process-major
             if idx.shape[0]:
                 proc, steps = idx[:, 0], idx[:, 1]
                 if self.is_dict_obs:
