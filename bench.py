@@ -33,7 +33,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--envs', type=int, default=131072, help='environments per GPU')
+    ap.add_argument('--envs', type=int, default=524288, help='environments per GPU (SURVEY.md 8d sizes: 32 / 4096 / 131072 / 524288 = the 1M-env sweep on 2 GPUs)')
     ap.add_argument('--T', type=int, default=256, help='rollout length (num_steps)')
     ap.add_argument('--size', type=int, default=15)
     ap.add_argument('--blocks', type=int, default=25)

@@ -29,6 +29,7 @@ struct Cfg {
 // Device view of one venv (all pointers are HBM).
 struct Dev {
   int N;
+  int use_tma;       // 1: TMA bulk copies for the tile rows / observation tile; 0: cp.async + vector stores (A/B knob)
   int l2_hints;      // 1: L2 eviction-priority hints in the step kernel (level + hot records evict_last, observations evict_first)
   Cfg c;
   uint32_t *wall;    // [ceil(N/32)][W][32] wall bit-plane rows (bit x of row y), tile-major: see env_rows()

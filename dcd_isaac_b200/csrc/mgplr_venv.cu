@@ -666,6 +666,16 @@ __device__ __forceinline__ uint4 ld_hint_u4(const uint4 *p, uint64_t pol) {
 __device__ __forceinline__ void st_hint_u4(uint4 *p, const uint4 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
+// Ampere-style asynchronous copies (LDGSTS): 16 bytes per lane, no uniform-datapath instruction on the issuing warp
+__device__ __forceinline__ void cp_async16_hint(void *sdst, const void *gsrc, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(sdst)), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+__device__ __forceinline__ void st_hint_f4(float4 *p, const float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk stores have finished READING shared memory (the global writes complete before the grid does)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -732,6 +742,13 @@ __device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot,
 
 // rows of one 32-env tile -> shared memory: ONE bulk asynchronous copy of W*128 bytes completing on `bar`
 __device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, uint64_t *bar, int tile, int lane, uint64_t pol) {
+  if (!d.use_tma) {  // W*128 bytes = 8W 16-byte chunks, lanes in turn (coalesced); one commit group per tile
+    const uint4 *src = reinterpret_cast<const uint4 *>(d.wall + (size_t)tile * d.c.W * kWarpTile);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_rows);
+    for (int i = lane; i < 8 * d.c.W; i += 32) cp_async16_hint(dst + i, src + i, pol);
+    cp_async_commit();
+    return;
+  }
   if (lane == 0) {
     const uint32_t bytes = (uint32_t)(d.c.W * kWarpTile * 4);
     mbar_expect_tx(bar, bytes);
@@ -797,8 +814,13 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         if (use_spec) nsp = d.spec[next * kWarpTile + lane];
       }
     }
-    mbar_wait(&bars[st], (phase >> st) & 1u);
-    phase ^= 1u << st;
+    if (d.use_tma) {
+      mbar_wait(&bars[st], (phase >> st) & 1u);
+      phase ^= 1u << st;
+    } else {  // this tile's group is the older of at most two pending ones
+      if (next < n_tiles) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+    }
 
     Env s = unpack(h);
     const Cfg &c = d.c;
@@ -907,12 +929,20 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     }
     const PackedView v = render_packed<SEE, EXT>(R, s, W);
     // re-acquire the observation buffer: the previous tile's bulk store must have finished reading it
-    if (lane == 0) bulk_wait_read0();
+    if (d.use_tma && lane == 0) bulk_wait_read0();
     __syncwarp();
     emit_packed_f32<SEE, false>(v, s_obs + lane * kObsFloats);
     if (A.o.image) {
       float *gdst = A.o.image + (size_t)base * kObsFloats;
-      if (n_tile == kWarpTile && (((uintptr_t)gdst) & 15u) == 0) {
+      if (n_tile == kWarpTile && (((uintptr_t)gdst) & 15u) == 0 && !d.use_tma) {
+        // 600 consecutive 16-byte chunks, lanes in turn: conflict-free LDS.128, fully coalesced STG.128
+        __syncwarp();
+        const float4 *src = reinterpret_cast<const float4 *>(s_obs);
+        float4 *dst = reinterpret_cast<float4 *>(gdst);
+#pragma unroll 5
+        for (int i = lane; i < kWarpTile * kObsFloats / 4; i += 32) st_hint_f4(dst + i, src[i], pol_stream);
+        __syncwarp();
+      } else if (n_tile == kWarpTile && (((uintptr_t)gdst) & 15u) == 0) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) { bulk_store_hint(gdst, s_obs, kWarpTile * kObsFloats * 4, pol_stream); bulk_commit(); }
@@ -1092,6 +1122,7 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   Dev &d = v->d;
   d.N = num_envs;
   d.l2_hints = getenv("MGPLR_L2_HINTS") ? atoi(getenv("MGPLR_L2_HINTS")) : 1;
+  d.use_tma = getenv("MGPLR_TMA") ? atoi(getenv("MGPLR_TMA")) : 1;
   v->pdl = getenv("MGPLR_PDL") ? atoi(getenv("MGPLR_PDL")) : 0;  // measured: no gain at 131 072 envs, slower at 4 096
   d.c = Cfg{cfg->width, cfg->max_steps, cfg->max_episode_steps, cfg->see_through_walls != 0, cfg->n_clutter,
             cfg->resample_n_clutter != 0, cfg->choose_goal_last != 0, cfg->fixed_environment != 0, cfg->n_editor_actions};
