@@ -29,12 +29,27 @@ __global__ void k_gae(const float *__restrict__ rewards, const float *__restrict
   if (e >= N) return;
   float gae = 0.0f;
   float v_next = values[(size_t)T * N + e];
-  for (int t = T - 1; t >= 0; t--) {
-    const float r = rewards[(size_t)t * N + e], m = masks[(size_t)(t + 1) * N + e], v = values[(size_t)t * N + e];
-    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, v_next), m)), v);
-    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, m), gae));
-    returns[(size_t)t * N + e] = __fadd_rn(gae, v);
-    v_next = v;
+  constexpr int kB = 8;  // steps loaded together (3 kB independent loads in flight), consumed in reverse order
+  for (int t1 = T; t1 > 0; t1 -= kB) {
+    float rb[kB], mb[kB], vb[kB];
+#pragma unroll
+    for (int u = 0; u < kB; u++) {
+      const int t = t1 - 1 - u;
+      const bool in = t >= 0;
+      rb[u] = in ? rewards[(size_t)t * N + e] : 0.f;
+      mb[u] = in ? masks[(size_t)(t + 1) * N + e] : 0.f;
+      vb[u] = in ? values[(size_t)t * N + e] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kB; u++) {
+      const int t = t1 - 1 - u;
+      if (t < 0) break;
+      const float r = rb[u], m = mb[u], v = vb[u];
+      const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, v_next), m)), v);
+      gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, m), gae));
+      returns[(size_t)t * N + e] = __fadd_rn(gae, v);
+      v_next = v;
+    }
   }
 }
 
@@ -108,6 +123,7 @@ __global__ void k_count_episodes(const float *__restrict__ masks, int T, int N, 
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   int c = 0;
+#pragma unroll 8
   for (int t = 1; t <= T; t++) c += !(masks[(size_t)t * N + e] > 0.f);
   c += (masks[(size_t)T * N + e] > 0.f);  // trailing partial episode (level_sampler.py:551-578)
   counts[e] = c;
@@ -177,29 +193,47 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
   int start = 0;
   double sum = 0.0, vsum = 0.0;
   float mx = -INFINITY, rsum = 0.f, vmin = INFINITY;
-  for (int t = 0; t < T; t++) {
-    // accumulate step t into the running episode [start, ...)
-    const float ret = returns ? returns[(size_t)t * N + e] : 0.f, v = values[(size_t)t * N + e], r = rewards[(size_t)t * N + e];
-    float a = ret - v;
-    if (strategy == MGPLR_SCORE_POSITIVE_VALUE_LOSS) a = fmaxf(a, 0.f);
-    else if (strategy == MGPLR_SCORE_VALUE_L1) a = fabsf(a);
-    sum += (double)a; mx = fmaxf(mx, a);
-    rsum += r;  // torch sums the f32 rewards of the slice (level_sampler.py:534)
-    vsum += (double)v; vmin = fminf(vmin, v);
-    // done at t+1 closes the episode [start, t+1)
-    if (!(masks[(size_t)(t + 1) * N + e] > 0.f)) {
-      const int t_end = t + 1;
-      if (k < max_out) {
-        mgplr_episode ep;
-        ep.actor = e; ep.t_start = start; ep.t_end = t_end; ep.seed = seeds ? seeds[(size_t)start * N + e] : -1;
-        const int n = t_end - start;
-        ep.mean_score = (float)(sum / (double)n); ep.max_score = mx; ep.reward_sum = rsum;
-        ep.value_sum = (float)vsum; ep.value_min = vmin;
-        ep.cliffhanger = cliff ? !(cliff[(size_t)t_end * N + e] > 0.f) : 0;
-        out[k] = ep;
+  // The time loop is latency-bound if it issues one step's loads at a time (4 x 128 B in flight per warp): steps are
+  // loaded kB at a time (4 kB independent loads in flight) and then consumed in order.
+  constexpr int kB = 8;
+  for (int t0 = 0; t0 < T; t0 += kB) {
+    float retb[kB], vb[kB], rb[kB], mb[kB];
+#pragma unroll
+    for (int u = 0; u < kB; u++) {
+      const int t = t0 + u;
+      const bool in = t < T;
+      retb[u] = (in && returns) ? returns[(size_t)t * N + e] : 0.f;
+      vb[u] = in ? values[(size_t)t * N + e] : 0.f;
+      rb[u] = in ? rewards[(size_t)t * N + e] : 0.f;
+      mb[u] = in ? masks[(size_t)(t + 1) * N + e] : 1.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kB; u++) {
+      const int t = t0 + u;
+      if (t >= T) break;
+      // accumulate step t into the running episode [start, ...)
+      const float v = vb[u], r = rb[u];
+      float a = retb[u] - v;
+      if (strategy == MGPLR_SCORE_POSITIVE_VALUE_LOSS) a = fmaxf(a, 0.f);
+      else if (strategy == MGPLR_SCORE_VALUE_L1) a = fabsf(a);
+      sum += (double)a; mx = fmaxf(mx, a);
+      rsum += r;  // torch sums the f32 rewards of the slice (level_sampler.py:534)
+      vsum += (double)v; vmin = fminf(vmin, v);
+      // done at t+1 closes the episode [start, t+1)
+      if (!(mb[u] > 0.f)) {
+        const int t_end = t + 1;
+        if (k < max_out) {
+          mgplr_episode ep;
+          ep.actor = e; ep.t_start = start; ep.t_end = t_end; ep.seed = seeds ? seeds[(size_t)start * N + e] : -1;
+          const int n = t_end - start;
+          ep.mean_score = (float)(sum / (double)n); ep.max_score = mx; ep.reward_sum = rsum;
+          ep.value_sum = (float)vsum; ep.value_min = vmin;
+          ep.cliffhanger = cliff ? !(cliff[(size_t)t_end * N + e] > 0.f) : 0;
+          out[k] = ep;
+        }
+        k++;
+        start = t_end; sum = 0.0; vsum = 0.0; mx = -INFINITY; rsum = 0.f; vmin = INFINITY;
       }
-      k++;
-      start = t_end; sum = 0.0; vsum = 0.0; mx = -INFINITY; rsum = 0.f; vmin = INFINITY;
     }
   }
   if (start < T && k < max_out) {  // not-done tail: a partial record (cliffhanger field = 2)

@@ -48,6 +48,9 @@ struct mgplr_venv {
   uint8_t *res_pin;        // pinned + device-mapped: [N done records (env = -1: empty slot)][N flags]
   uint8_t *res_pin_dev;    // the same allocation as the device sees it
   uint32_t host_steps;     // host-driven steps issued (selects the ping-pong counter)
+  int host_dma;            // host-driven step: chunked copy-engine staging of pinned actions for large batches
+  cudaStream_t copy_stream;
+  cudaEvent_t copy_done[8];
   int pdl;                 // launch the step kernel with programmatic stream serialization
   int rr_spec;             // DR auto-reset: speculative next-level candidates (MGPLR_RR_SPEC=0 disables)
   int rr_grid;             // co-resident CTA capacity of the DR step kernel (its regeneration phase spins on grid-wide progress)
@@ -759,7 +762,7 @@ __device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, 
 // reset_agent mode: the shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids; the DR
 // variant keeps the batched RNG of its in-kernel reset_random in registers instead (2 CTAs/SM).
 template <bool SEE, bool RR, typename EXT>
-__global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int n_tiles) {
+__global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int tile0, int n_tiles) {  // tiles [tile0, n_tiles)
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = d.c.W, N = d.N;
   const int wpc = blockDim.x >> 5;
@@ -771,7 +774,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   const int total = gridDim.x * wpc;
   // Static round-robin tile assignment (tile = global_warp + k * total_warps).  A dynamic scheduler on one global
   // atomic counter was measured: ~9 k same-address atomics per launch doubled the launch time (10 -> 20 us).
-  int tile = blockIdx.x * wpc + warp;
+  int tile = tile0 + blockIdx.x * wpc + warp;
   // Programmatic dependent launch: consecutive step launches of a rollout are serially dependent through the hot
   // records, so the NEXT launch is allowed to become resident as this one's CTAs retire and to run its on-chip
   // prologue; it blocks at griddepcontrol.wait (below) until this grid has completed and its writes are visible.
@@ -1149,6 +1152,9 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   // off by default: measured at parity with the in-kernel rebuild -- a regeneration job is a ~15 us
   // dependent chain on its warp however it is parallelised, and it sits on the launch's critical path
   v->rr_spec = getenv("MGPLR_RR_SPEC") ? atoi(getenv("MGPLR_RR_SPEC")) : 0;
+  v->host_dma = getenv("MGPLR_HOST_DMA") ? atoi(getenv("MGPLR_HOST_DMA")) : 0;
+  CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < 8; c++) CK(cudaEventCreateWithFlags(&v->copy_done[c], cudaEventDisableTiming));
   d.prof = nullptr;
   if (getenv("MGPLR_RR_PROF")) {  // debug: phase timestamps / job cycles of the DR step kernel (mgplr_debug_prof)
     CK(cudaMalloc((void **)&d.prof, 8 * sizeof(unsigned long long)));
@@ -1196,6 +1202,8 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
   if (!v) return;
   cudaSetDevice(v->device);
   Dev &d = v->d;
+  if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+  for (int c = 0; c < 8; c++) if (v->copy_done[c]) cudaEventDestroy(v->copy_done[c]);
   cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
   cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(d.spec); cudaFree(d.cand); cudaFree(d.rr_list); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->cnt_dev); cudaFreeHost(v->res_pin);
   delete v;
@@ -1345,7 +1353,7 @@ extern "C" int mgplr_mutate_finalize(mgplr_venv *v, const int32_t *choice, const
   return 0;
 }
 
-static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st);
+static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st, int tile0 = 0, int tile1 = -1);
 static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls, int32_t last_step,
                        const mgplr_step_out *out, cudaStream_t st) {
   StepArgs A;
@@ -1354,11 +1362,12 @@ static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_rando
   if (out) A.o = *out;
   return launch_step_args(v, A, reset_random, st);
 }
-static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st) {
+static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st, int tile0, int tile1) {
   // persistent grid: as many 4-warp CTAs as fit on the chip (shared-memory bound), capped by the tile count
   const int W = v->d.c.W, wpc = 4;
   const size_t smem = wpc * warp_smem_bytes(W, reset_random != 0);
-  const int n_tiles = (v->d.N + kWarpTile - 1) / kWarpTile;
+  const int all_tiles = (v->d.N + kWarpTile - 1) / kWarpTile;
+  const int n_tiles = (tile1 < 0 || tile1 > all_tiles) ? all_tiles : tile1;  // exclusive end of this launch's tile range
   const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
   int grid = v->sm_count * per_sm;
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
@@ -1376,8 +1385,9 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
     }
     if (grid > v->rr_grid) grid = v->rr_grid;
   }
-  const int need = (n_tiles + wpc - 1) / wpc;
+  const int need = (n_tiles - tile0 + wpc - 1) / wpc;
   if (grid > need) grid = need;
+  if (grid < 1) return 0;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = dim3(grid); lc.blockDim = dim3(wpc * 32); lc.dynamicSmemBytes = smem; lc.stream = st;
@@ -1385,7 +1395,7 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr; lc.numAttrs = v->pdl ? 1 : 0;
-#define LAUNCH(SEE, RR, EXT) CK(cudaLaunchKernelEx(&lc, k_step_env<SEE, RR, EXT>, v->d, A, n_tiles))
+#define LAUNCH(SEE, RR, EXT) CK(cudaLaunchKernelEx(&lc, k_step_env<SEE, RR, EXT>, v->d, A, tile0, n_tiles))
 #define BY_MODE(EXT)                                  \
   do {                                                \
     if (see && rr) LAUNCH(true, true, EXT);           \
@@ -1407,6 +1417,7 @@ extern "C" int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t rese
   return launch_step(v, action, reset_random, n_walls, last_step, out, st);
 }
 
+constexpr int kHostChunks = 8;
 // Device view of a host pointer when it is pinned (cudaHostAlloc / cudaHostRegister) memory, else NULL.
 static void *mapped_view(const void *host) {
   if (!host) return nullptr;
@@ -1429,6 +1440,15 @@ extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, in
   mgplr_done_record *list_h = (mgplr_done_record *)v->res_pin;
   uint8_t *flags_pin = v->res_pin + 16 * N;
   const int64_t *act = (const int64_t *)mapped_view(action_host);
+  // A/B knob (MGPLR_HOST_DMA=1, off): stage the pinned actions with the copy engine in chunks on a side stream and run
+  // the step as one sub-launch per chunk behind its copy.  Measured slower than the zero-copy read on both sizes
+  // (524 288 envs: 3.2 vs 4.4 G env-steps/s; 131 072: 2.2 vs 2.8): the event hand-offs cost more than the PCIe gain.
+  int chunks = 1;
+  if (act && v->host_dma && N >= 65536) {
+    chunks = (int)(N / 65536);
+    if (chunks > kHostChunks) chunks = kHostChunks;
+    act = v->act_dev;
+  }
   if (!act) {
     CK(cudaMemcpyAsync(v->act_dev, action_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     act = v->act_dev;
@@ -1444,7 +1464,19 @@ extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, in
   A.done_list = (mgplr_done_record *)v->res_pin_dev;
   A.flags_host = stage_flags ? v->res_pin_dev + 16 * N : flags_map;
   v->host_steps++;
-  if (int rc = launch_step_args(v, A, reset_random, st)) return rc;
+  if (chunks > 1) {
+    const int all_tiles = (int)((N + kWarpTile - 1) / kWarpTile);
+    const int per = ((all_tiles + chunks - 1) / chunks + 3) & ~3;  // tiles per chunk, a multiple of the CTA's 4 warps
+    for (int c = 0; c < chunks; c++) {
+      const int t0 = c * per, t1 = (t0 + per < all_tiles) ? t0 + per : all_tiles;
+      if (t0 >= t1) break;
+      const size_t e0 = (size_t)t0 * kWarpTile, e1 = ((size_t)t1 * kWarpTile < N) ? (size_t)t1 * kWarpTile : N;
+      CK(cudaMemcpyAsync(v->act_dev + e0, action_host + e0, (e1 - e0) * sizeof(int64_t), cudaMemcpyHostToDevice, v->copy_stream));
+      CK(cudaEventRecord(v->copy_done[c], v->copy_stream));
+      CK(cudaStreamWaitEvent(st, v->copy_done[c], 0));
+      if (int rc = launch_step_args(v, A, reset_random, st, t0, t1)) return rc;
+    }
+  } else if (int rc = launch_step_args(v, A, reset_random, st)) return rc;
   CK(cudaStreamSynchronize(st));
   if (stage_flags) memcpy(flags_host, flags_pin, N);
   // the records are a dense prefix of the sentinel-filled list
