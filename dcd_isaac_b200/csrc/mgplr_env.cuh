@@ -36,23 +36,37 @@ struct Dev {
   uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx5|gy5|hasgoal1|sx5|sy5|hasstart1|sdir2|pending8  z: elapsed16|eplen16  w: ep_ret bits
   uint32_t *adv;     // [N] adversary_step_count12 | adversary_max_steps12 | n_clutter_sampled1
   int4 *metrics;     // [N] n_clutter_placed, distance_to_goal, passable, shortest_path_length
-  uint32_t *mt;      // [624][N] MT19937 state (numpy RandomState of each env)
+  uint32_t *mt;      // [ceil(N/32)][624][32] MT19937 state (numpy RandomState of each env), see mt_at()
   uint32_t *mti;     // [N] index of the next word to generate (incremental twist), 0..623
   uint32_t *limbs;   // [3][N] seed limbs lo, hi, count (re-seed of fixed_environment)
   uint32_t *words;   // [N] MT words consumed since seeding
   uint32_t *err;     // [N] sticky error bits
   // speculative next-level generation of the DR auto-reset (step_env(reset_random=True)), see the "speculation" block
-  uint32_t *spec;    // [N] bits 0-15: MT words logically consumed but not yet applied to mt / mti / words; bit 16 / 17:
-                     //     candidate 0 (episode ended without a goal) / 1 (ended at the goal) is valid
-  uint32_t *cand;    // [N][2][W + 8] candidate records: wall rows, packed goal/start, metrics[4], words consumed, error bits
-  int32_t *rr_list;  // [2N + slack] regeneration jobs 2*env + candidate (-1 = empty slot)
+  uint32_t *spec;    // [N] bits 16+2p / 17+2p: candidate 0 (episode ended without a goal) / 1 (ended at the goal) built for a
+                     //     level epoch of parity p is valid; bits 20-26: level epoch (bumped by every DR reset)
+  uint32_t *cand;    // [N][2 epochs][2][W + 8] candidate records: wall rows, packed goal/start, -, words consumed, error bits
+  uint2 *rr_list;    // [2][2N] regeneration jobs {env << 8 | candidate << 7 | epoch, MT cursor}, one list per launch parity
   unsigned long long *prof;  // debug counters (MGPLR_RR_PROF), else NULL
-  uint32_t *sched;   // [4] regeneration phase of the step kernel: jobs appended, warps past their tiles, next ticket, warps exited
+  uint32_t *sched;   // [8] regeneration phase: [0..1] jobs appended to list p, [2..3] next ticket of list p, [4] warps exited,
+                     //     [5] parity of the running / next DR launch (device-side so that graph replays stay consistent)
 };
+// MT19937 state layout: tile-major like the wall plane -- the 624 words of 32 consecutive envs form one contiguous
+// 624*128-byte block (word i of env e at mt[((e/32)*624 + i)*32 + e%32]).  32 lanes stepping 32 consecutive envs read
+// 128 contiguous bytes per word index (coalesced), AND all 624 words of one env live in one 78 KB span: a warp that
+// walks ONE env's state (cooperative rebuild, MT advance at a commit, a regeneration job's look-ahead window) stays
+// inside one 2 MB page.  The earlier [624][N] layout put consecutive words of an env N*4 bytes apart -- a different page
+// for every few words, i.e. a TLB miss storm on exactly those paths.
+__host__ __device__ inline size_t mt_at(int e, uint32_t i) { return ((size_t)(e >> 5) * 624 + i) * 32 + (size_t)(e & 31); }
 constexpr int kMetricsDirty = -2;  // metrics.z of an env whose level came from a candidate record: recomputed by the getter
-constexpr uint32_t kSpecAdvMask = 0xffffu, kSpecValid0 = 1u << 16, kSpecValid1 = 1u << 17;
+constexpr uint32_t kSpecValidMask = 15u << 16;
+constexpr int kSpecEpochShift = 20;
+// validity bit of candidate k for a level epoch ep: a job sets it with one fire-and-forget atomic OR.  Bits are per epoch
+// PARITY and every reset stores a fresh word, so a bit set late by a job of the previous level (it runs during the launch
+// that may reset the env again) lands on the other parity and is never consulted.
+__host__ __device__ inline uint32_t spec_valid_bit(uint32_t ep, int k) { return 1u << (16 + 2 * (ep & 1u) + k); }
+constexpr uint32_t kSpecEpochMask = 127u << kSpecEpochShift;
+__host__ __device__ inline uint32_t spec_epoch(uint32_t sp) { return (sp & kSpecEpochMask) >> kSpecEpochShift; }
 constexpr int kSpecWindow = 224;   // MT words one regeneration job can look ahead (< 227: all computable from the present state)
-constexpr int kRrListSlack = 32768;
 __host__ __device__ inline int cand_words(int W) { return W + 8; }
 
 // `pending` = goal respawns (multigrid.py:821-838) whose env-RNG draws have not been made yet.  A respawn draw
@@ -131,38 +145,27 @@ struct Rng {
   __device__ __forceinline__ Rng(const Dev &dev, int env, uint32_t *buf_, int stride_)
       : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), spec_p(dev.spec), N(dev.N), e(env), idx(0), used(0), have(0), pos(0),
         loaded(false), buf(buf_), stride(stride_) {}
-  // Any consumer of the env RNG other than the speculation itself first applies the words a committed candidate consumed
-  // logically (one word at a time: rare) and drops the candidates, whose stream position is about to become stale.
-  __device__ __noinline__ void settle(uint32_t sp) {
-    for (uint32_t k = sp & kSpecAdvMask; k; k--) {
-      const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
-      const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
-      uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-      mt[(size_t)i * N + e] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      idx = i1; used++;
-    }
-    spec_p[e] = 0;
-    mti_p[e] = idx; words_p[e] = used;
-  }
+  // Any consumer of the env RNG other than the DR speculation itself drops the env's candidates: their stream position
+  // is about to become stale.
   __device__ __forceinline__ void load() {
     if (!loaded) {
       idx = mti_p[e]; used = words_p[e]; loaded = true;
       const uint32_t sp = spec_p[e];
-      if (sp) settle(sp);
+      if (sp & kSpecValidMask) spec_p[e] = sp & kSpecEpochMask;
     }
   }
   __device__ __forceinline__ void refill() {
     load();
     uint32_t b[kBatch], c[kBatch];
-    uint32_t a = mt[(size_t)idx * N + e];
+    uint32_t a = mt[mt_at(e, idx)];
 #pragma unroll
     for (int u = 0; u < kBatch; u++) {
       uint32_t i1 = idx + u + 1, im = idx + u + 397;
       if (i1 >= 624) i1 -= 624;
       if (im >= 624) im -= 624;
       if (im >= 624) im -= 624;
-      b[u] = mt[(size_t)i1 * N + e];
-      c[u] = mt[(size_t)im * N + e];
+      b[u] = mt[mt_at(e, i1)];
+      c[u] = mt[mt_at(e, im)];
     }
 #pragma unroll
     for (int u = 0; u < kBatch; u++) {
@@ -187,7 +190,7 @@ struct Rng {
   __device__ __forceinline__ uint32_t next() {
     if (__any_sync(__activemask(), pos >= have)) refill();
     const uint32_t v = buf[pos * stride];
-    mt[(size_t)idx * N + e] = buf[(kBatch + pos) * stride];  // commit this word's new state
+    mt[mt_at(e, idx)] = buf[(kBatch + pos) * stride];  // commit this word's new state
     idx = (idx + 1 == 624) ? 0 : idx + 1;
     used++;
     pos++;
@@ -215,18 +218,15 @@ struct RngSlow {
     if (!loaded) {
       idx = mti_p[e]; used = words_p[e]; loaded = true;
       const uint32_t sp = spec_p[e];
-      if (sp) {  // see Rng::settle
-        for (uint32_t k = sp & kSpecAdvMask; k; k--) next_raw();
-        spec_p[e] = 0;
-      }
+      if (sp & kSpecValidMask) spec_p[e] = sp & kSpecEpochMask;  // see Rng::load
     }
   }
   __device__ __forceinline__ uint32_t next_raw() {
     const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
-    const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
+    const uint32_t a = mt[mt_at(e, i)], b = mt[mt_at(e, i1)], c = mt[mt_at(e, im)];
     uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    mt[(size_t)i * N + e] = y;
+    mt[mt_at(e, i)] = y;
     idx = i1; used++;
     return y;
   }
@@ -257,36 +257,35 @@ struct RngSlow {
 // MT19937 init_by_array for one env (RandomState.seed([lo, hi])), SoA state.
 __device__ __noinline__ void mt_seed(const Dev &d, int e, uint32_t k0, uint32_t k1, int klen) {
   uint32_t *mt = d.mt;
-  const size_t N = d.N;
   uint32_t prev = 19650218u;
-  mt[e] = prev;
-  for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; mt[(size_t)i * N + e] = prev; }
+  mt[mt_at(e, 0)] = prev;
+  for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; mt[mt_at(e, i)] = prev; }
   int i = 1, j = 0;
-  prev = mt[e];
+  prev = mt[mt_at(e, 0)];
   for (int k = 624; k; k--) {
     const uint32_t key = (j == 0) ? k0 : k1;
-    uint32_t v = (mt[(size_t)i * N + e] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key + (uint32_t)j;
-    mt[(size_t)i * N + e] = v; prev = v;
+    uint32_t v = (mt[mt_at(e, i)] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key + (uint32_t)j;
+    mt[mt_at(e, i)] = v; prev = v;
     i++; j++;
-    if (i >= 624) { mt[e] = prev; i = 1; }
+    if (i >= 624) { mt[mt_at(e, 0)] = prev; i = 1; }
     if (j >= klen) j = 0;
   }
   for (int k = 623; k; k--) {
-    uint32_t v = (mt[(size_t)i * N + e] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
-    mt[(size_t)i * N + e] = v; prev = v;
+    uint32_t v = (mt[mt_at(e, i)] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
+    mt[mt_at(e, i)] = v; prev = v;
     i++;
-    if (i >= 624) { mt[e] = prev; i = 1; }
+    if (i >= 624) { mt[mt_at(e, 0)] = prev; i = 1; }
   }
-  mt[e] = 0x80000000u;
+  mt[mt_at(e, 0)] = 0x80000000u;
   d.mti[e] = 0;  // numpy's mti = 624 ("regenerate everything") == incremental index 0
   d.words[e] = 0;
-  d.spec[e] = 0;  // a new stream: pending logical advance and candidates are moot
+  d.spec[e] &= kSpecEpochMask;  // a new stream: the candidates are moot
 }
 
 // level edits that do not draw from the env RNG: the candidates' respawn draws depended on the old level
 __device__ __forceinline__ void spec_invalidate(const Dev &d, int e) {
   const uint32_t sp = d.spec[e];
-  if (sp & ~kSpecAdvMask) d.spec[e] = sp & kSpecAdvMask;
+  if (sp & kSpecValidMask) d.spec[e] = sp & kSpecEpochMask;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,22 +486,22 @@ __device__ __forceinline__ void reset_random(const Rows &R, Env &e, uint32_t &ad
 // state word of the span only depends on PRESENT state words (j, j+1, j+397 mod 624), so all are loaded first, then stored.
 __device__ __forceinline__ void coop_mt_advance(const Dev &d, int e, int lane, uint32_t &idx, uint32_t &used, int a) {
   constexpr int kPer = (kSpecWindow + 31) / 32;
-  uint32_t ns[kPer];
-  const size_t N = d.N;
+  uint32_t ns[kPer], xs[kPer], bs[kPer], cs[kPer];
+  // all 3*kPer loads are issued before anything consumes them (lanes past `a` re-read word 0: no branch in the way)
 #pragma unroll
   for (int i = 0; i < kPer; i++) {
-    const int j = lane + 32 * i;
-    ns[i] = 0;
-    if (j < a) {
-      uint32_t p = idx + j, p1 = p + 1, pm = p + 397;
-      if (p >= 624) p -= 624;
-      if (p1 >= 624) p1 -= 624;
-      if (pm >= 624) pm -= 624;
-      if (pm >= 624) pm -= 624;
-      const uint32_t x = d.mt[p * N + e], b = d.mt[p1 * N + e], c = d.mt[pm * N + e];
-      const uint32_t y = (x & 0x80000000u) | (b & 0x7fffffffu);
-      ns[i] = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    }
+    const int j = (lane + 32 * i < a) ? lane + 32 * i : 0;
+    uint32_t p = idx + j, p1 = p + 1, pm = p + 397;
+    if (p >= 624) p -= 624;
+    if (p1 >= 624) p1 -= 624;
+    if (pm >= 624) pm -= 624;
+    if (pm >= 624) pm -= 624;
+    xs[i] = d.mt[mt_at(e, p)]; bs[i] = d.mt[mt_at(e, p1)]; cs[i] = d.mt[mt_at(e, pm)];
+  }
+#pragma unroll
+  for (int i = 0; i < kPer; i++) {
+    const uint32_t y = (xs[i] & 0x80000000u) | (bs[i] & 0x7fffffffu);
+    ns[i] = cs[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
   }
   __syncwarp();
 #pragma unroll
@@ -511,7 +510,7 @@ __device__ __forceinline__ void coop_mt_advance(const Dev &d, int e, int lane, u
     if (j < a) {
       uint32_t p = idx + j;
       if (p >= 624) p -= 624;
-      d.mt[p * N + e] = ns[i];
+      d.mt[mt_at(e, p)] = ns[i];
     }
   }
   __syncwarp();
@@ -529,10 +528,10 @@ struct CoopRng {
   __device__ __forceinline__ CoopRng(const Dev &dev, int env, int lane_)
       : mt(dev.mt), mti_p(dev.mti), words_p(dev.words), N(dev.N), e(env), lane(lane_), have(0), pos(0), w_out(0), w_nst(0) {
     idx = mti_p[e]; used = words_p[e];
-    const uint32_t sp = dev.spec[e];  // see Rng::settle
-    if (sp) {
-      coop_mt_advance(dev, e, lane, idx, used, (int)(sp & kSpecAdvMask));
-      if (lane == 0) dev.spec[e] = 0;
+    const uint32_t sp = dev.spec[e];  // see Rng::load
+    if (sp & kSpecValidMask) {
+      __syncwarp();
+      if (lane == 0) dev.spec[e] = sp & kSpecEpochMask;
       __syncwarp();
     }
   }
@@ -540,7 +539,7 @@ struct CoopRng {
     if (lane < pos) {
       uint32_t i = idx + lane;
       if (i >= 624) i -= 624;
-      mt[(size_t)i * N + e] = w_nst;
+      mt[mt_at(e, i)] = w_nst;
     }
     idx += pos;
     if (idx >= 624) idx -= 624;
@@ -555,7 +554,7 @@ struct CoopRng {
     if (i1 >= 624) i1 -= 624;
     if (im >= 624) im -= 624;
     if (im >= 624) im -= 624;
-    const uint32_t a = mt[(size_t)i * N + e], b = mt[(size_t)i1 * N + e], c = mt[(size_t)im * N + e];
+    const uint32_t a = mt[mt_at(e, i)], b = mt[mt_at(e, i1)], c = mt[mt_at(e, im)];
     uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
     w_nst = y;
@@ -891,56 +890,84 @@ __device__ __forceinline__ bool spec_level(const SpecTables &T, const uint32_t *
   return done;  // metrics are computed lazily (kMetricsDirty): no getter reads them inside a rollout
 }
 
+// Record of candidate k of env e built for level epoch `ep` (double-buffered by epoch parity so that a job of the
+// previous level can never write the records the current level's commit reads).
+__device__ __forceinline__ uint32_t *cand_record(const Dev &d, int e, uint32_t ep, int k) {
+  return d.cand + (((size_t)e * 2 + (ep & 1u)) * 2 + k) * cand_words(d.c.W);
+}
+
 // One regeneration job = ONE candidate (k = 0: the episode ends without a goal, 1: at the goal) of one env, one warp.
-// The env's MT state is settled (the step kernel applies a committed record's words when it commits), so a job only
-// READS env state and writes its own record and validity bit.
-__device__ __noinline__ void rr_regen_job(Dev d, int job, int lane, uint32_t *scr /* 1024 words of shared memory */) {
+// Jobs queued by launch t run in the tail of launch t+1, next to its tiles, so a job may race with a step warp that
+// resets the very env it is reading.  That is harmless by construction: a job only READS env state (the step kernel
+// applies a committed record's words to the MT state when it commits), every reset bumps the env's level epoch and
+// stores a fresh speculation word, records and validity bits are per epoch parity, and jobs live for one launch --
+// whatever a job computed from a torn state lands on the parity that is no longer consulted (spec_valid_bit).
+__device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *scr /* 1024 words of shared memory */) {
   const Cfg &c = d.c;
-  const int e = job >> 1, k = job & 1;
-  const int W = c.W, RW = cand_words(W);
+  const uint32_t job = jb.x;
+  const int e = (int)(job >> 8), k = (int)((job >> 7) & 1u);
+  const uint32_t ep = job & 127u;
+  const int W = c.W;
   SpecTables T;
   T.win = scr; T.am = scr + kSpecWindow; uint32_t *cur = scr + kSpecWindow + 8, *lvl = cur + 32;
   T.cell = reinterpret_cast<uint16_t *>(lvl + 32);
   T.jump = reinterpret_cast<uint8_t *>(T.cell + kSpecWindow);
-  const size_t N = d.N;
-  const uint32_t idx = d.mti[e];
-  const uint4 hot = d.hot[e];
-  cur[lane] = (k == 1 && lane < W) ? env_rows(d, e).get(lane) : 0xffffffffu;
-  // look-ahead window: tempered outputs idx .. idx + kSpecWindow - 1 of the present state (nothing is stored to mt)
+  const uint32_t idx = jb.y % 624u;  // the cursor travels with the job: every load of the job is issued in one go
+  const uint32_t sp0 = __ldcg(d.spec + e);
+  const uint4 hot = __ldcg(d.hot + e);
+  const uint32_t cur_row = (k == 1 && lane < W) ? __ldcg(env_rows(d, e).p + lane * 32) : 0xffffffffu;
+  // look-ahead window: tempered outputs idx .. idx + kSpecWindow - 1 of the present state (nothing is stored to mt).
+  // All 21 loads per lane are issued before the first shared-memory store (which the compiler must order against them).
+  {
+    constexpr int kPer = kSpecWindow / 32;
+    uint32_t xs[kPer], bs[kPer], cs[kPer];
 #pragma unroll
-  for (int i = 0; i < kSpecWindow / 32; i++) {
-    uint32_t p = idx + lane + 32 * i, p1 = p + 1, pm = p + 397;
-    if (p >= 624) p -= 624;
-    if (p1 >= 624) p1 -= 624;
-    if (pm >= 624) pm -= 624;
-    if (pm >= 624) pm -= 624;
-    const uint32_t x = d.mt[p * N + e], b = d.mt[p1 * N + e], cc = d.mt[pm * N + e];
-    uint32_t y = (x & 0x80000000u) | (b & 0x7fffffffu);
-    y = cc ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    T.win[lane + 32 * i] = y;
+    for (int i = 0; i < kPer; i++) {
+      uint32_t p = idx + lane + 32 * i, p1 = p + 1, pm = p + 397;
+      if (p >= 624) p -= 624;
+      if (p1 >= 624) p1 -= 624;
+      if (pm >= 624) pm -= 624;
+      if (pm >= 624) pm -= 624;
+      xs[i] = __ldcg(d.mt + mt_at(e, p)); bs[i] = __ldcg(d.mt + mt_at(e, p1)); cs[i] = __ldcg(d.mt + mt_at(e, pm));
+    }
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+      uint32_t y = (xs[i] & 0x80000000u) | (bs[i] & 0x7fffffffu);
+      y = cs[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      T.win[lane + 32 * i] = y;
+    }
   }
+  cur[lane] = cur_row;
   const Env s = unpack(hot);
   __syncwarp();
+  if (spec_epoch(sp0) != ep) return;  // the level is gone already
+  const long long c1 = d.prof ? clock64() : 0;
   spec_build_tables(T, W, lane);
+  const long long c2 = d.prof ? clock64() : 0;
   LevelOut o;
   int consumed = 0;
-  const bool ok = spec_level(T, cur, s.gx, s.gy, k == 1, lvl, W, c.n_clutter / 2, lane, o, consumed);
+  const bool ok = spec_level(T, cur, s.gx & 31, s.gy & 31, k == 1, lvl, W, c.n_clutter / 2, lane, o, consumed);
   __syncwarp();
-  if (ok) {
-    uint32_t *rec = d.cand + ((size_t)e * 2 + k) * RW;
-    if (lane < W) rec[lane] = lvl[lane];
-    if (lane == 0) {
-      rec[W] = ((uint32_t)o.gx & 31u) | (((uint32_t)o.gy & 31u) << 5) | (1u << 10) | (((uint32_t)o.sx & 31u) << 11) |
-               (((uint32_t)o.sy & 31u) << 16) | (1u << 21) | ((uint32_t)o.sdir << 22);
-      rec[W + 5] = (uint32_t)consumed;
-      rec[W + 6] = o.err;
-    }
-    __syncwarp();
-    if (lane == 0) { __threadfence(); atomicOr(&d.spec[e], k ? kSpecValid1 : kSpecValid0); }
+  if (d.prof && lane == 0) {
+    atomicAdd(&d.prof[6], (unsigned long long)(c2 - c1)); atomicAdd(&d.prof[7], (unsigned long long)(clock64() - c2));
+  }
+  if (!ok) return;
+  uint32_t *rec = cand_record(d, e, ep, k);
+  if (lane < W) rec[lane] = lvl[lane];
+  if (lane == 0) {
+    rec[W] = ((uint32_t)o.gx & 31u) | (((uint32_t)o.gy & 31u) << 5) | (1u << 10) | (((uint32_t)o.sx & 31u) << 11) |
+             (((uint32_t)o.sy & 31u) << 16) | (1u << 21) | ((uint32_t)o.sdir << 22);
+    rec[W + 5] = (uint32_t)consumed;
+    rec[W + 6] = o.err;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    atomicOr(d.spec + e, spec_valid_bit(ep, k));  // result unused: a reduction, no round trip
   }
 }
 

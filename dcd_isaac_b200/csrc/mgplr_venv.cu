@@ -53,7 +53,6 @@ struct mgplr_venv {
   cudaEvent_t copy_done[8];
   int pdl;                 // launch the step kernel with programmatic stream serialization
   int rr_spec;             // DR auto-reset: speculative next-level candidates (MGPLR_RR_SPEC=0 disables)
-  int rr_grid;             // co-resident CTA capacity of the DR step kernel (its regeneration phase spins on grid-wide progress)
   int sm_count;
 };
 
@@ -732,8 +731,26 @@ __device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, 
 //     that drains while tile k+1 steps and renders; the single obs buffer is only re-acquired
 //     (cp.async.bulk.wait_group.read) right before tile k+1 emits.
 // per warp: obs tile | two row buffers | two mbarriers | (DR variant) batched-RNG scratch [32][32]
+constexpr int kPendCap = 96;  // DR variant: regeneration jobs a warp collects before it appends them to the global list
 __host__ __device__ inline size_t warp_smem_bytes(int W, bool rr) {
-  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + (rr ? 32 * kWarpTile * 4 : 0) + 127) & ~(size_t)127;
+  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + (rr ? 32 * kWarpTile * 4 + kPendCap * 8 : 0) + 127) &
+         ~(size_t)127;
+}
+// append a warp's collected jobs (one entry per reset env) to the launch's list: ONE atomic per flush, both candidates
+__device__ __forceinline__ void flush_pending_jobs(const Dev &d, int rr_par, const uint2 *s_pend, int &pend_n, int lane) {
+  __syncwarp();
+  if (pend_n) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&d.sched[rr_par], 2u * (uint32_t)pend_n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    uint2 *list = d.rr_list + (size_t)rr_par * 2 * d.N + base;
+    for (int i = lane; i < pend_n; i += 32) {
+      const uint2 jb = s_pend[i];
+      list[2 * i] = jb; list[2 * i + 1] = make_uint2(jb.x | 128u, jb.y);
+    }
+    pend_n = 0;
+  }
+  __syncwarp();
 }
 
 __device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot, int W, int see, uint8_t *image_u8, int e) {
@@ -771,6 +788,11 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   uint32_t *s_rows = reinterpret_cast<uint32_t *>(wbase + (size_t)kWarpTile * kObsFloats * 4);
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 2 * W * kWarpTile);
   uint32_t *s_rng = reinterpret_cast<uint32_t *>(bars + 2);  // only present (and used) when RR
+  uint2 *s_pend = reinterpret_cast<uint2 *>(s_rng + 32 * kWarpTile);  // (RR) jobs collected by this warp
+  int pend_n = 0;
+  unsigned long long prof_start = 0;
+  int prof_commits = 0;
+  if (RR && d.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_start));
   const int total = gridDim.x * wpc;
   // Static round-robin tile assignment (tile = global_warp + k * total_warps).  A dynamic scheduler on one global
   // atomic counter was measured: ~9 k same-address atomics per launch doubled the launch time (10 -> 20 us).
@@ -794,6 +816,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   int na = 6;
   uint32_t nsp = 0;  // speculation word of the env (DR variant)
   const bool use_spec = RR && A.spec;
+  const int rr_par = use_spec ? (int)(*(volatile uint32_t *)&d.sched[5] & 1u) : 0;  // stable for the whole launch
   if (tile < n_tiles && tile * kWarpTile + lane < N) {
     nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep); na = (int)A.action[tile * kWarpTile + lane];
     if (use_spec) nsp = d.spec[tile * kWarpTile + lane];
@@ -825,6 +848,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
       __syncwarp();
     }
 
+    const long long pc0 = (RR && d.prof) ? clock64() : 0;
     Env s = unpack(h);
     const Cfg &c = d.c;
     const Rows R{rows + lane, kWarpTile};
@@ -833,6 +857,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     bool dirty = false, need_rr = false;
     int cand_pick = -1;  // DR variant: candidate record to reset from (0 no goal / 1 goal), -1 = none
     int cand_used = 0;   // MT words that record consumed
+    uint32_t cand_idx = 0, cand_words_used = 0, new_idx = 0;  // MT cursor / words drawn before and cursor after the reset
     float fin_ret = 0.f;
     int fin_len = 0;
     if (valid) {
@@ -848,7 +873,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
           s.done_flag = 1;
           // DR variant with a valid goal candidate: its record already accounts for the respawn draws (SPECULATION)
           const bool observed = want_trunc && s.elapsed + 1 >= c.max_episode_steps;
-          if (use_spec && (sp & kSpecValid1) && !observed && s.pending == 0) cand_pick = 1;
+          if (use_spec && (sp & spec_valid_bit(spec_epoch(sp), 1)) && !observed && s.pending == 0) cand_pick = 1;
           else if (RR || observed || s.pending >= kMaxPending) {
             const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.spec, N, e, rows + lane, kWarpTile, W, s.gx, s.gy, s.pending + 1);
             s.pending = 0; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
@@ -875,12 +900,13 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
         s.ep_ret = 0.f; s.ep_len = 0;
         if (RR) {  // worker.step_env (parallel_wrappers.py:27-37): reset_random
-          if (use_spec && !(flags & MGPLR_F_GOAL) && (sp & kSpecValid0) && s.pending == 0) cand_pick = 0;
+          if (use_spec && !(flags & MGPLR_F_GOAL) && (sp & spec_valid_bit(spec_epoch(sp), 0)) && s.pending == 0) cand_pick = 0;
           if (cand_pick >= 0) {
             // take the pre-built successor level: goal / start (rows and the MT advance are done warp-wide below)
-            const uint32_t *rec = d.cand + ((size_t)e * 2 + cand_pick) * cand_words(W) + W;
-            const uint32_t gs = rec[0], cerr = rec[6];
-            cand_used = (int)rec[5];
+            const uint32_t *rec = cand_record(d, e, spec_epoch(sp), cand_pick) + W;  // (L2 loads: written by another SM)
+            const uint32_t gs = __ldcg(rec), cerr = __ldcg(rec + 6);
+            cand_used = (int)__ldcg(rec + 5);
+            cand_idx = d.mti[e]; cand_words_used = d.words[e];  // (same round trip as the record fields)
             s.gx = gs & 31; s.gy = (gs >> 5) & 31; s.sx = (gs >> 11) & 31; s.sy = (gs >> 16) & 31; s.sdir = (gs >> 22) & 3;
             d.metrics[e] = make_int4(0, 0, kMetricsDirty, 0);  // recomputed on demand by mgplr_get_metrics
             d.adv[e] &= ~0xfffu;  // adversary_step_count = 0 (adversarial.py:546)
@@ -893,22 +919,32 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e, A.o.trunc_full_obs);
       }
     }
+    const long long pc1 = (RR && d.prof) ? clock64() : 0;
     if (RR) {
       // committed candidate records, all lanes together per finished env: one coalesced W-word read of the rows, and
       // the words the record consumed are applied to the env's MT state (so regeneration jobs only read env state)
       for (unsigned rest = __ballot_sync(0xffffffffu, cand_pick >= 0); rest; rest &= rest - 1) {
         const int le = __ffs(rest) - 1, env = base + le;
         const int pick = __shfl_sync(0xffffffffu, cand_pick, le), used_w = __shfl_sync(0xffffffffu, cand_used, le);
-        const uint32_t *rec = d.cand + ((size_t)env * 2 + pick) * cand_words(W);
-        if (lane < W) rows[lane * kWarpTile + le] = rec[lane];
-        uint32_t idx = d.mti[env], used = d.words[env];
+        const uint32_t *rec = cand_record(d, env, spec_epoch(__shfl_sync(0xffffffffu, sp, le)), pick);
+        if (lane < W) rows[lane * kWarpTile + le] = __ldcg(rec + lane);
+        uint32_t idx = __shfl_sync(0xffffffffu, cand_idx, le), used = __shfl_sync(0xffffffffu, cand_words_used, le);
         coop_mt_advance(d, env, lane, idx, used, used_w);
-        if (lane == 0) { d.mti[env] = idx; d.words[env] = used; d.spec[env] = 0; }
+        if (lane == 0) { d.mti[env] = idx; d.words[env] = used; }
+        if (lane == le) new_idx = idx;
       }
       __syncwarp();
+      const long long pc2 = d.prof ? clock64() : 0;
+      if (d.prof) {
+        const unsigned cm = __ballot_sync(0xffffffffu, cand_pick >= 0);
+        if (cm && lane == 0) { atomicAdd(&d.prof[16], (unsigned long long)(pc1 - pc0)); atomicAdd(&d.prof[17], (unsigned long long)(pc2 - pc1)); atomicAdd(&d.prof[18], 1ull); }
+      }
       // Finished envs without a candidate get a fresh random level the slow way.  Few per tile: the warp rebuilds them
       // one at a time cooperatively; many (a synchronized time-limit storm): every lane rebuilds its own.
       const unsigned m = __ballot_sync(0xffffffffu, need_rr);
+      if (d.prof && need_rr) atomicAdd(&d.prof[9], 1ull);
+      if (d.prof && cand_pick >= 0) atomicAdd(&d.prof[8], 1ull);
+      if (d.prof) prof_commits += __popc(__ballot_sync(0xffffffffu, cand_pick >= 0 || need_rr));
       if (m) {
         dirty = dirty || need_rr;
         if (__popc(m) > 10) {
@@ -955,6 +991,9 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         __syncwarp();
       }
     }
+    bool queue_me = false;
+    uint2 queue_job = make_uint2(0, 0);
+    const long long pc3 = (RR && d.prof) ? clock64() : 0;
     if (valid) {
       st_hint_u4(&d.hot[e], pack(s), pol_keep);
       write_step_scalars(A, e, s, flags, (float)rew, fin_ret, fin_len);
@@ -962,49 +1001,51 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
       if (RR && dirty) {
         const Rows G = env_rows(d, e);
         for (int r = 0; r < W; r++) G.set(r, rows[r * kWarpTile + lane]);
-        if (use_spec) {  // queue the env: its next candidates are built in the regeneration phase of this launch
-          __threadfence();
-          const uint32_t k = atomicAdd(&d.sched[0], 2u);
-          *(volatile int32_t *)&d.rr_list[k] = 2 * e; *(volatile int32_t *)&d.rr_list[k + 1] = 2 * e + 1;
+        if (use_spec) {  // new level epoch (drops the old candidates); its two candidates are built during the next launch
+          const uint32_t ne = (spec_epoch(sp) + 1u) & 127u;
+          *(volatile uint32_t *)&d.spec[e] = ne << kSpecEpochShift;
+          if (cand_pick < 0) new_idx = *(volatile uint32_t *)&d.mti[e];  // rebuilt the slow way: cursor as stored by the rebuild
+          queue_me = true;
+          queue_job = make_uint2(((uint32_t)e << 8) | ne, new_idx);
         }
       }
     }
+    if (RR && use_spec) {
+      const unsigned qm = __ballot_sync(0xffffffffu, queue_me);
+      if (d.prof && qm && lane == 0) { atomicAdd(&d.prof[19], (unsigned long long)(pc3 - pc1)); atomicAdd(&d.prof[20], (unsigned long long)(clock64() - pc3)); }
+      if (qm) {
+        if (pend_n + __popc(qm) > kPendCap) flush_pending_jobs(d, rr_par, s_pend, pend_n, lane);
+        if (queue_me) s_pend[pend_n + __popc(qm & ((1u << lane) - 1u))] = queue_job;
+        pend_n += __popc(qm);
+      }
+    }
   }
+  if (RR && use_spec) flush_pending_jobs(d, rr_par, s_pend, pend_n, lane);
   if (lane == 0) bulk_wait_read0();
   unsigned long long prof_t0 = 0;
   if (RR && d.prof && lane == 0) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t0));
     atomicMax(&d.prof[1], prof_t0);            // end of the last warp's tiles
     atomicMin(&d.prof[0], prof_t0);            // end of the first warp's tiles
+    const unsigned long long dur = prof_t0 - prof_start;
+    const int cls = prof_commits ? 13 : 10;
+    atomicAdd(&d.prof[cls], dur); atomicAdd(&d.prof[cls + 1], 1ull); atomicMax(&d.prof[cls + 2], dur);
   }
   if (RR && use_spec) {
-    // ---- regeneration phase: warps that are past their tiles take tickets on the job list until it is drained.
-    // A ticket beyond the current count waits for either the slot to fill or every warp to be past its tiles.
+    // ---- regeneration phase: the jobs queued by the PREVIOUS launch (list of the other parity; its count is final)
+    // are drained by warps that are past their tiles -- no waiting on this launch's progress.
     __syncwarp();
-    __threadfence();
-    if (lane == 0) atomicAdd(&d.sched[1], 1u);
+    const int q = rr_par ^ 1;
+    const uint32_t n_jobs = *(volatile uint32_t *)&d.sched[q];
+    const uint2 *list = d.rr_list + (size_t)q * 2 * N;
     uint32_t *scr = reinterpret_cast<uint32_t *>(s_obs);  // the observation tile is free now
     for (;;) {
-      int job = -1, env = -1;
-      if (lane == 0) {
-        job = (int)atomicAdd(&d.sched[2], 1u);
-        for (;;) {
-          env = *(volatile int32_t *)&d.rr_list[job];
-          if (env >= 0) break;
-          if (*(volatile uint32_t *)&d.sched[1] == (uint32_t)total) {  // every append is visible by now
-            __threadfence();
-            env = *(volatile int32_t *)&d.rr_list[job];
-            break;
-          }
-          __nanosleep(100);
-        }
-        if (env >= 0) *(volatile int32_t *)&d.rr_list[job] = -1;  // the slot is empty again for the next launch
-      }
-      env = __shfl_sync(0xffffffffu, env, 0);
-      if (env < 0) break;
-      __threadfence();
-      const long long c0 = clock64();
-      rr_regen_job(d, env, lane, scr);
+      uint32_t j = 0;
+      if (lane == 0) j = atomicAdd(&d.sched[2 + q], 1u);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= n_jobs) break;
+      const long long c0 = d.prof ? clock64() : 0;
+      rr_regen_job(d, __ldcg(list + j), lane, scr);
       __syncwarp();
       if (d.prof && lane == 0) {
         const unsigned long long dt = (unsigned long long)(clock64() - c0);
@@ -1018,8 +1059,9 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     }
     if (lane == 0) {
       __threadfence();
-      if (atomicAdd(&d.sched[3], 1u) == (uint32_t)total - 1u) {  // last warp out: reset the scheduler for the next launch
-        d.sched[0] = 0; d.sched[1] = 0; d.sched[2] = 0; d.sched[3] = 0;
+      if (atomicAdd(&d.sched[4], 1u) == (uint32_t)total - 1u) {  // last warp out: the drained list becomes the next append list
+        d.sched[q] = 0; d.sched[2 + q] = 0; d.sched[4] = 0;
+        d.sched[5] = (uint32_t)q;
       }
     }
   }
@@ -1137,28 +1179,26 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(dalloc(&d.hot, N, total));
   CK(dalloc(&d.adv, N, total));
   CK(dalloc(&d.metrics, N, total));
-  CK(dalloc(&d.mt, 624 * N, total));
+  const size_t mt_words = 624 * 32 * ((N + 31) / 32);  // padded to whole 32-env tiles
+  CK(dalloc(&d.mt, mt_words, total));
   CK(dalloc(&d.mti, N, total));
   CK(dalloc(&d.limbs, 3 * N, total));
   CK(dalloc(&d.words, N, total));
   CK(dalloc(&d.err, N, total));
-  CK(dalloc(&d.sched, 4, total));
-  CK(cudaMemset(d.sched, 0, 4 * sizeof(uint32_t)));
+  CK(dalloc(&d.sched, 8, total));
+  CK(cudaMemset(d.sched, 0, 8 * sizeof(uint32_t)));
   CK(dalloc(&d.spec, N, total));
   CK(cudaMemset(d.spec, 0, N * sizeof(uint32_t)));
-  CK(dalloc(&d.cand, N * 2 * (size_t)cand_words(cfg->width), total));
-  CK(dalloc(&d.rr_list, 2 * N + kRrListSlack, total));
-  CK(cudaMemset(d.rr_list, 0xff, (2 * N + kRrListSlack) * sizeof(int32_t)));
-  // off by default: measured at parity with the in-kernel rebuild -- a regeneration job is a ~15 us
-  // dependent chain on its warp however it is parallelised, and it sits on the launch's critical path
-  v->rr_spec = getenv("MGPLR_RR_SPEC") ? atoi(getenv("MGPLR_RR_SPEC")) : 0;
+  CK(dalloc(&d.cand, N * 4 * (size_t)cand_words(cfg->width), total));
+  CK(dalloc(&d.rr_list, 4 * N, total));  // uint2 entries
+  v->rr_spec = getenv("MGPLR_RR_SPEC") ? atoi(getenv("MGPLR_RR_SPEC")) : 1;  // DR speculation; 0 = in-kernel rebuild only
   v->host_dma = getenv("MGPLR_HOST_DMA") ? atoi(getenv("MGPLR_HOST_DMA")) : 0;
   CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
   for (int c = 0; c < 8; c++) CK(cudaEventCreateWithFlags(&v->copy_done[c], cudaEventDisableTiming));
   d.prof = nullptr;
   if (getenv("MGPLR_RR_PROF")) {  // debug: phase timestamps / job cycles of the DR step kernel (mgplr_debug_prof)
-    CK(cudaMalloc((void **)&d.prof, 8 * sizeof(unsigned long long)));
-    CK(cudaMemset(d.prof, 0, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&d.prof, 24 * sizeof(unsigned long long)));
+    CK(cudaMemset(d.prof, 0, 24 * sizeof(unsigned long long)));
   }
   CK(dalloc(&v->seed_scratch, 4 * N, total));
   CK(dalloc(&v->act_dev, N, total));
@@ -1190,7 +1230,7 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
     CK(cudaFuncSetAttribute(k_adv_image<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem));
     CK(cudaFuncSetAttribute(k_reset_random, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->width * 128 * 4));
   }
-  CK(cudaMemset(d.mt, 0, 624 * N * sizeof(uint32_t)));
+  CK(cudaMemset(d.mt, 0, mt_words * sizeof(uint32_t)));
   k_init<<<grid_for(num_envs, 256), 256>>>(d);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -1214,8 +1254,8 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
 extern "C" int mgplr_debug_prof(mgplr_venv *v, unsigned long long *out) {
   if (!v || !v->d.prof) return fail(MGPLR_E_BADARG, "profiling is off (MGPLR_RR_PROF)");
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, v->d.prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+  CK(cudaMemcpy(out, v->d.prof, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long init[24] = {~0ull};
   CK(cudaMemcpy(v->d.prof, init, sizeof(init), cudaMemcpyHostToDevice));
   return 0;
 }
@@ -1371,20 +1411,8 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
   int grid = v->sm_count * per_sm;
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
-  A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample;
-  if (A.spec) {
-    // the regeneration phase waits on grid-wide progress: every CTA of the grid must be resident at the same time
-    if (!v->rr_grid) {
-      int per = 0;
-#define OCC(SEE, EXT) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_step_env<SEE, true, EXT>, wpc * 32, smem))
-      if (narrow) { if (see) OCC(true, uint32_t); else OCC(false, uint32_t); }
-      else { if (see) OCC(true, uint64_t); else OCC(false, uint64_t); }
-#undef OCC
-      if (per < 1) return fail(MGPLR_E_UNSUPPORTED, "DR step kernel does not fit on an SM");
-      v->rr_grid = per * v->sm_count;
-    }
-    if (grid > v->rr_grid) grid = v->rr_grid;
-  }
+  // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing job phase
+  A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample && (v->d.N >= 16384 || v->rr_spec > 1);
   const int need = (n_tiles - tile0 + wpc - 1) / wpc;
   if (grid > need) grid = need;
   if (grid < 1) return 0;
@@ -1394,7 +1422,7 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = attr; lc.numAttrs = v->pdl ? 1 : 0;
+  lc.attrs = attr; lc.numAttrs = (v->pdl && !A.spec) ? 1 : 0;  // (the DR speculation reads a per-launch parity word)
 #define LAUNCH(SEE, RR, EXT) CK(cudaLaunchKernelEx(&lc, k_step_env<SEE, RR, EXT>, v->d, A, tile0, n_tiles))
 #define BY_MODE(EXT)                                  \
   do {                                                \
@@ -1563,7 +1591,7 @@ extern "C" int mgplr_peek_rng(mgplr_venv *v, int32_t index, uint32_t *words_host
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   uint32_t mt[624], idx = 0;
-  CK(cudaMemcpy2D(mt, sizeof(uint32_t), v->d.mt + index, (size_t)v->d.N * sizeof(uint32_t), sizeof(uint32_t), 624,
+  CK(cudaMemcpy2D(mt, sizeof(uint32_t), v->d.mt + mt_at(index, 0), 32 * sizeof(uint32_t), sizeof(uint32_t), 624,
                   cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&idx, v->d.mti + index, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   for (int k = 0; k < count; k++) {
