@@ -1,2 +1,4 @@
-MGPLR_RR_PROF=1 timeout 120 ./tools/kbench 131072 15 256 3 0 1 0 1 | grep -v reset_random | tail -5
-timeout 600 python -m pytest tests/test_gpu_env_parity.py -m gpu -x -q -k "random or spec or oracle_large or rollout" 2>&1 | tail -3
+python __graft_entry__.py smoke 2>&1 | tail -2
+python bench.py --steps 3 --reset-random 1 --no-cpu --envs 131072 > gpurun_out/r1d_b_rr.json 2>gpurun_out/r1d.err; python profiles/summarize_bench.py gpurun_out/r1d_b_rr.json
+python bench.py --steps 3 --reset-random 1 --no-cpu > gpurun_out/r1d_b_rr_512k.json 2>>gpurun_out/r1d.err; python profiles/summarize_bench.py gpurun_out/r1d_b_rr_512k.json
+tail -2 gpurun_out/r1d.err
