@@ -246,9 +246,11 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
   }
 }
 
-static int32_t *g_scratch = nullptr;
-static size_t g_scratch_n = 0;
-static int g_scratch_dev = -1;
+// scan scratch of the episode-score launcher: one grow-only buffer PER DEVICE (a process may drive several GPUs); growing
+// synchronises that device first so that no in-flight launch still uses the old buffer
+constexpr int kMaxDevices = 64;
+static int32_t *g_scratch[kMaxDevices] = {nullptr};
+static size_t g_scratch_n[kMaxDevices] = {0};
 
 extern "C" int mgplr_plr_episode_scores(const float *masks, const float *cliffhanger_masks, const float *returns,
                                         const float *value_preds, const float *rewards, const int32_t *level_seeds, int32_t T,
@@ -261,14 +263,15 @@ extern "C" int mgplr_plr_episode_scores(const float *masks, const float *cliffha
   PCK(cudaGetDevice(&dev));
   const int n_blocks = (N + 1023) / 1024;
   const size_t need = 2 * (size_t)N + (size_t)n_blocks;
-  if (g_scratch_dev != dev || g_scratch_n < need) {
-    if (g_scratch) cudaFree(g_scratch);
-    g_scratch = nullptr;
-    PCK(cudaMalloc((void **)&g_scratch, need * sizeof(int32_t)));
-    g_scratch_n = need; g_scratch_dev = dev;
+  if (dev < 0 || dev >= kMaxDevices) return pfail(MGPLR_E_UNSUPPORTED, "device index out of range");
+  if (g_scratch_n[dev] < need) {
+    if (g_scratch[dev]) { PCK(cudaDeviceSynchronize()); cudaFree(g_scratch[dev]); }
+    g_scratch[dev] = nullptr; g_scratch_n[dev] = 0;
+    PCK(cudaMalloc((void **)&g_scratch[dev], need * sizeof(int32_t)));
+    g_scratch_n[dev] = need;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  int32_t *counts = g_scratch, *offsets = g_scratch + N, *block_off = g_scratch + 2 * (size_t)N;
+  int32_t *counts = g_scratch[dev], *offsets = counts + N, *block_off = counts + 2 * (size_t)N;
   k_count_episodes<<<(N + 127) / 128, 128, 0, st>>>(masks, T, N, counts);
   k_scan_blocks<<<n_blocks, 1024, 0, st>>>(counts, N, offsets, block_off);
   k_scan_tops<<<1, 1024, 0, st>>>(block_off, n_blocks, n_episodes);
