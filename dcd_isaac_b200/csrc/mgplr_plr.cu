@@ -195,7 +195,7 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
   float mx = -INFINITY, rsum = 0.f, vmin = INFINITY;
   // The time loop is latency-bound if it issues one step's loads at a time (4 x 128 B in flight per warp): steps are
   // loaded kB at a time (4 kB independent loads in flight) and then consumed in order.
-  constexpr int kB = 8;
+  constexpr int kB = 8;  // (16 was measured slower: 403 vs 235 us at 131 072 actors -- registers, occupancy)
   for (int t0 = 0; t0 < T; t0 += kB) {
     float retb[kB], vb[kB], rb[kB], mb[kB];
 #pragma unroll

@@ -218,21 +218,49 @@ __global__ void __launch_bounds__(128) k_adv_image(Dev d, float *image, float *t
   }
 }
 
-__global__ void k_reset_agent(Dev d, OutPtrs o) {
+// The float32 observation of all N envs is written once per rollout (obs[0]): each warp stages its 32 observations in
+// shared memory (75 floats per lane, conflict-free) and writes them as 600 consecutive float4 (coalesced); one thread
+// writing its own 300 bytes would touch 10 sectors per store instruction.
+__global__ void __launch_bounds__(128) k_reset_agent(Dev d, OutPtrs o) {
   RNG_SCRATCH();
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d.N) return;
-  const Rows R = env_rows(d, e);
-  Env s = unpack(d.hot[e]);
-  if (s.pending) {  // replay the deferred respawn draws of the last rollout (level unchanged since)
-    Rng rng = RNG_OF(d, e);
-    flush_pending(R, s, rng, d.c.W);
-    rng.store();
+  extern __shared__ __align__(16) float s_tile[];  // [4 warps][32][75]
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = e - lane;
+  bool ok = false;
+  Env s{};
+  if (e < d.N) {
+    const Rows R = env_rows(d, e);
+    s = unpack(d.hot[e]);
+    if (s.pending) {  // replay the deferred respawn draws of the last rollout (level unchanged since)
+      Rng rng = RNG_OF(d, e);
+      flush_pending(R, s, rng, d.c.W);
+      rng.store();
+    }
+    ok = reset_agent(s);
+    if (!ok) d.err[e] |= kErrNoStart;
+    else { s.ep_ret = 0.f; s.ep_len = 0; }  // VecMonitor.reset_agent (vec_monitor.py:42-46)
+    d.hot[e] = pack(s);
+    if (ok && o.image_u8) emit_direct(R, s, d.c, OutPtrs{nullptr, nullptr, o.image_u8}, e);
+    if (ok && o.direction) o.direction[e] = (float)s.adir;
   }
-  if (!reset_agent(s)) { d.err[e] |= kErrNoStart; d.hot[e] = pack(s); return; }
-  s.ep_ret = 0.f; s.ep_len = 0;  // VecMonitor.reset_agent (vec_monitor.py:42-46)
-  d.hot[e] = pack(s);
-  emit_direct(R, s, d.c, o, e);
+  if (!o.image) return;
+  float *tile = s_tile + warp * (32 * kObsFloats);
+  if (ok) {
+    const Rows R = env_rows(d, e);
+    const View v = d.c.see_through ? render_view<true>(R, s, d.c.W) : render_view<false>(R, s, d.c.W);
+    emit_obs_f32(v, tile + lane * kObsFloats);
+  }
+  const unsigned okm = __ballot_sync(0xffffffffu, ok);
+  float *gdst = o.image + (size_t)base * kObsFloats;
+  if (okm == 0xffffffffu && (((uintptr_t)gdst) & 15u) == 0) {
+    const float4 *src = reinterpret_cast<const float4 *>(tile);
+    float4 *dst = reinterpret_cast<float4 *>(gdst);
+    for (int i = lane; i < 32 * kObsFloats / 4; i += 32) dst[i] = src[i];
+  } else {  // ragged tile / envs in error keep their previous observation
+    for (int k = 0; k < 32; k++)
+      if ((okm >> k) & 1u)
+        for (int i = lane; i < kObsFloats; i += 32) gdst[k * kObsFloats + i] = tile[k * kObsFloats + i];
+  }
 }
 
 __global__ void __launch_bounds__(128) k_reset_random(Dev d, const int32_t *n_walls, OutPtrs o) {
@@ -1229,6 +1257,7 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
     CK(cudaFuncSetAttribute(k_adv_image<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem));
     CK(cudaFuncSetAttribute(k_adv_image<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem));
     CK(cudaFuncSetAttribute(k_reset_random, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg->width * 128 * 4));
+    CK(cudaFuncSetAttribute(k_reset_agent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 32 * kObsFloats * sizeof(float))));
   }
   CK(cudaMemset(d.mt, 0, mt_words * sizeof(uint32_t)));
   k_init<<<grid_for(num_envs, 256), 256>>>(d);
@@ -1337,7 +1366,7 @@ static OutPtrs outptrs(const mgplr_step_out *o) {
 
 extern "C" int mgplr_reset_agent(mgplr_venv *v, const mgplr_step_out *out, void *stream) {
   NEED(v);
-  k_reset_agent<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, outptrs(out));
+  k_reset_agent<<<grid_for(v->d.N, 128), 128, 4 * 32 * kObsFloats * sizeof(float), st>>>(v->d, outptrs(out));
   CK(cudaGetLastError());
   return 0;
 }

@@ -128,3 +128,84 @@ def test_episode_invariants_full_size(rr):
         assert bool(legal.all()), t
     assert bool((img[:, :, 0, 2, 4] == 0.1).all()) and bool((img[:, :, 2] == 0).all())
     v.close()
+
+
+def test_dr_speculation_equals_in_kernel_rebuild_full_size(monkeypatch):
+    """step_env(reset_random=True) at 131 072 envs x 520 steps (two synchronized time-limit storms): the speculative,
+    pipelined level generation (default) and the in-kernel rebuild (MGPLR_RR_SPEC=0, the path checked against the oracle
+    at 4 096 envs) must agree bit for bit -- observations, rewards, flags, final levels, metrics, agent state and the
+    env-RNG stream position (words drawn)."""
+    T = 520
+    res = []
+    for spec in ('1', '0'):
+        monkeypatch.setenv('MGPLR_RR_SPEC', spec)
+        v = _venv(N_FULL)
+        v.set_seed(list(range(N_FULL)))
+        v.reset_random()
+        acts, img, rew, fl, lens = _rollout(v, T, 21, rr=True)
+        res.append((fl, rew, img, v.get_encodings_device(), torch.from_numpy(v._metrics()).cuda(),
+                    torch.from_numpy(v.get_agent_state()).cuda()))
+        v.close()
+    assert int(((res[0][0] & 1) > 0).sum()) > 2 * N_FULL  # every env was rebuilt at least twice
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+def test_dr_speculation_under_cuda_graph_replay():
+    """The job lists of the DR speculation alternate by a DEVICE-side launch parity, so a captured sequence of step
+    launches -- here an ODD number of them -- can be replayed back to back and still equals launching step by step."""
+    from dcd_isaac_b200._lib import StepOut, ptr
+    N, K, R = 32768, 7, 40
+    g = torch.Generator(device='cuda')
+    g.manual_seed(3)
+    acts = torch.randint(0, 7, (K * R, N), device='cuda', generator=g)
+    acts[torch.rand(K * R, N, device='cuda', generator=g) < 0.6] = 2
+    outs = []
+    for use_graph in (False, True):
+        v = _venv(N)
+        v.set_seed(list(range(N)))
+        v.reset_random()
+        img = torch.zeros(K, N, 3, 5, 5, device='cuda')
+        fl = torch.zeros(K, N, dtype=torch.uint8, device='cuda')
+        cur = torch.zeros(K, N, dtype=torch.int64, device='cuda')
+        hist_img, hist_fl = [], []
+
+        def k_steps():
+            for k in range(K):
+                o = StepOut()
+                o.image, o.flags = ptr(img[k]), ptr(fl[k])
+                v.step_env_device(cur[k], o, reset_random=True)
+
+        if use_graph:
+            cur.copy_(acts[:K])
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                k_steps()  # warm-up launch outside the capture (first-use attribute calls)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            hist_img.append(img.clone()); hist_fl.append(fl.clone())
+            gr = torch.cuda.CUDAGraph()
+            cur.copy_(acts[K:2 * K])
+            with torch.cuda.graph(gr):
+                k_steps()
+            gr.replay()
+            torch.cuda.synchronize()
+            hist_img.append(img.clone()); hist_fl.append(fl.clone())
+            for r in range(2, R):
+                cur.copy_(acts[r * K:(r + 1) * K])
+                gr.replay()
+                torch.cuda.synchronize()
+                hist_img.append(img.clone()); hist_fl.append(fl.clone())
+            del gr
+        else:
+            for r in range(R):
+                cur.copy_(acts[r * K:(r + 1) * K])
+                k_steps()
+                torch.cuda.synchronize()
+                hist_img.append(img.clone()); hist_fl.append(fl.clone())
+        outs.append((torch.stack(hist_fl), torch.stack(hist_img), v.get_encodings_device(), torch.from_numpy(v.get_agent_state()).cuda()))
+        v.close()
+    assert int(((outs[0][0] & 1) > 0).sum()) > N
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
