@@ -154,6 +154,8 @@ struct Rng {
       if (sp & kSpecValidMask) spec_p[e] = sp & kSpecEpochMask;
     }
   }
+  // (kept inline: out of line it shrinks the DR step kernel from 20 k to 12 k instructions, which changed nothing there, but
+  // the lane-parallel reset_random kernel got 40 % slower)
   __device__ __forceinline__ void refill() {
     load();
     uint32_t b[kBatch], c[kBatch];
@@ -259,9 +261,11 @@ __device__ __noinline__ void mt_seed(const Dev &d, int e, uint32_t k0, uint32_t 
   uint32_t *mt = d.mt;
   uint32_t prev = 19650218u;
   mt[mt_at(e, 0)] = prev;
+#pragma unroll 1
   for (int i = 1; i < 624; i++) { prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i; mt[mt_at(e, i)] = prev; }
   int i = 1, j = 0;
   prev = mt[mt_at(e, 0)];
+#pragma unroll 1
   for (int k = 624; k; k--) {
     const uint32_t key = (j == 0) ? k0 : k1;
     uint32_t v = (mt[mt_at(e, i)] ^ ((prev ^ (prev >> 30)) * 1664525u)) + key + (uint32_t)j;
@@ -270,6 +274,7 @@ __device__ __noinline__ void mt_seed(const Dev &d, int e, uint32_t k0, uint32_t 
     if (i >= 624) { mt[mt_at(e, 0)] = prev; i = 1; }
     if (j >= klen) j = 0;
   }
+#pragma unroll 1
   for (int k = 623; k; k--) {
     uint32_t v = (mt[mt_at(e, i)] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
     mt[mt_at(e, i)] = v; prev = v;
@@ -485,35 +490,35 @@ __device__ __forceinline__ void reset_random(const Rows &R, Env &e, uint32_t &ad
 // Apply `a` (<= kSpecWindow < 227) logically consumed words to env e's MT state, all lanes of the warp together: every new
 // state word of the span only depends on PRESENT state words (j, j+1, j+397 mod 624), so all are loaded first, then stored.
 __device__ __forceinline__ void coop_mt_advance(const Dev &d, int e, int lane, uint32_t &idx, uint32_t &used, int a) {
-  constexpr int kPer = (kSpecWindow + 31) / 32;
-  uint32_t ns[kPer], xs[kPer], bs[kPer], cs[kPer];
-  // all 3*kPer loads are issued before anything consumes them (lanes past `a` re-read word 0: no branch in the way)
+  // 96 words (3 per lane) per pass: one pass for a typical record (~85 words).  A later pass only reads words that
+  // earlier passes did not store (word j reads present words j, j+1 and j+397 mod 624, the latter outside the span).
+  constexpr int kPer = 3;
+#pragma unroll 1
+  for (int j0 = 0; j0 < a; j0 += 32 * kPer) {
+    uint32_t xs[kPer], bs[kPer], cs[kPer];
 #pragma unroll
-  for (int i = 0; i < kPer; i++) {
-    const int j = (lane + 32 * i < a) ? lane + 32 * i : 0;
-    uint32_t p = idx + j, p1 = p + 1, pm = p + 397;
-    if (p >= 624) p -= 624;
-    if (p1 >= 624) p1 -= 624;
-    if (pm >= 624) pm -= 624;
-    if (pm >= 624) pm -= 624;
-    xs[i] = d.mt[mt_at(e, p)]; bs[i] = d.mt[mt_at(e, p1)]; cs[i] = d.mt[mt_at(e, pm)];
-  }
-#pragma unroll
-  for (int i = 0; i < kPer; i++) {
-    const uint32_t y = (xs[i] & 0x80000000u) | (bs[i] & 0x7fffffffu);
-    ns[i] = cs[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < kPer; i++) {
-    const int j = lane + 32 * i;
-    if (j < a) {
-      uint32_t p = idx + j;
+    for (int i = 0; i < kPer; i++) {  // all loads first (lanes past `a` re-read word j0: no branch in the way)
+      const int j = (j0 + lane + 32 * i < a) ? j0 + lane + 32 * i : j0;
+      uint32_t p = idx + j, p1 = p + 1, pm = p + 397;
       if (p >= 624) p -= 624;
-      d.mt[mt_at(e, p)] = ns[i];
+      if (p1 >= 624) p1 -= 624;
+      if (pm >= 624) pm -= 624;
+      if (pm >= 624) pm -= 624;
+      xs[i] = d.mt[mt_at(e, p)]; bs[i] = d.mt[mt_at(e, p1)]; cs[i] = d.mt[mt_at(e, pm)];
     }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+      const int j = j0 + lane + 32 * i;
+      if (j < a) {
+        const uint32_t y = (xs[i] & 0x80000000u) | (bs[i] & 0x7fffffffu);
+        uint32_t p = idx + j;
+        if (p >= 624) p -= 624;
+        d.mt[mt_at(e, p)] = cs[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+    }
+    __syncwarp();
   }
-  __syncwarp();
   idx += a;
   if (idx >= 624) idx -= 624;
   used += a;
