@@ -805,7 +805,7 @@ __device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, 
 }
 
 // reset_agent mode: the shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids; the DR
-// variant keeps the batched RNG of its in-kernel reset_random in registers instead (2 CTAs/SM).
+// variant carries its in-kernel reset_random, the batched-RNG scratch and the regeneration phase (168 registers, 3 CTAs/SM).
 template <bool SEE, bool RR, typename EXT>
 __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int tile0, int n_tiles) {  // tiles [tile0, n_tiles)
   extern __shared__ __align__(128) uint8_t smem[];
