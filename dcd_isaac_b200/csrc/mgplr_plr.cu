@@ -182,9 +182,25 @@ __global__ void __launch_bounds__(1024) k_scan_tops(int32_t *__restrict__ block_
   if (threadIdx.x == 0) *total_out = carry;
 }
 
+// per-step score of the policy-logit strategies from one step's logits x[0..A): with lse = log sum exp(x),
+// least confidence = 1 - exp(max x - lse); margin = exp(x1 - lse) - exp(x2 - lse) for the two largest logits
+__device__ __forceinline__ float logit_score(const float *__restrict__ x, int A, int strategy) {
+  float m1 = -INFINITY, m2 = -INFINITY;
+  for (int j = 0; j < A; j++) {
+    const float v = x[j];
+    if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) m2 = v;
+  }
+  float sum = 0.f;
+  for (int j = 0; j < A; j++) sum += expf(x[j] - m1);
+  const float lse = m1 + logf(sum);
+  if (strategy == MGPLR_SCORE_LEAST_CONFIDENCE) return 1.0f - expf(m1 - lse);
+  return expf(m1 - lse) - expf(m2 - lse);
+}
+
 __global__ void k_episode_scores(const float *__restrict__ masks, const float *__restrict__ cliff, const float *__restrict__ returns,
                                  const float *__restrict__ values, const float *__restrict__ rewards,
-                                 const int32_t *__restrict__ seeds, int T, int N, int strategy,
+                                 const int32_t *__restrict__ seeds, const float *__restrict__ logits, int A, float gamma,
+                                 int T, int N, int strategy,
                                  const int32_t *__restrict__ offsets, const int32_t *__restrict__ block_off,
                                  mgplr_episode *__restrict__ out, int max_out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,6 +209,7 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
   int start = 0;
   double sum = 0.0, vsum = 0.0;
   float mx = -INFINITY, rsum = 0.f, vmin = INFINITY;
+  float r_prev = 0.f, v_prev = 0.f;  // ONE_STEP_TD: the term of step t-1 needs v[t]
   // The time loop is latency-bound if it issues one step's loads at a time (4 x 128 B in flight per warp): steps are
   // loaded kB at a time (4 kB independent loads in flight) and then consumed in order.
   constexpr int kB = 8;  // (16 was measured slower: 403 vs 235 us at 131 072 actors -- registers, occupancy)
@@ -216,7 +233,17 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
       float a = retb[u] - v;
       if (strategy == MGPLR_SCORE_POSITIVE_VALUE_LOSS) a = fmaxf(a, 0.f);
       else if (strategy == MGPLR_SCORE_VALUE_L1) a = fabsf(a);
-      sum += (double)a; mx = fmaxf(mx, a);
+      else if (strategy == MGPLR_SCORE_LEAST_CONFIDENCE) a = logit_score(logits + ((size_t)t * N + e) * A, A, strategy);
+      else if (strategy == MGPLR_SCORE_MIN_MARGIN) a = -logit_score(logits + ((size_t)t * N + e) * A, A, strategy);  // max of -s = -min s
+      if (strategy == MGPLR_SCORE_ONE_STEP_TD) {
+        if (t > start) {  // term of step t-1: |r[t-1] + gamma*v[t] - v[t-1]|
+          a = fabsf(__fsub_rn(__fadd_rn(r_prev, __fmul_rn(gamma, v)), v_prev));
+          sum += (double)a; mx = fmaxf(mx, a);
+        }
+        r_prev = r; v_prev = v;
+      } else {
+        sum += (double)a; mx = fmaxf(mx, a);
+      }
       rsum += r;  // torch sums the f32 rewards of the slice (level_sampler.py:534)
       vsum += (double)v; vmin = fminf(vmin, v);
       // done at t+1 closes the episode [start, t+1)
@@ -227,6 +254,11 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
           ep.actor = e; ep.t_start = start; ep.t_end = t_end; ep.seed = seeds ? seeds[(size_t)start * N + e] : -1;
           const int n = t_end - start;
           ep.mean_score = (float)(sum / (double)n); ep.max_score = mx; ep.reward_sum = rsum;
+          if (strategy == MGPLR_SCORE_MIN_MARGIN) { ep.mean_score = (float)(1.0 + sum / (double)n); ep.max_score = 1.0f + mx; }
+          if (strategy == MGPLR_SCORE_ONE_STEP_TD) {  // n-1 terms; a one-step episode scores r[0] - v[0] (level_sampler.py:431-434)
+            if (n > 1) ep.mean_score = (float)(sum / (double)(n - 1));
+            else { ep.mean_score = __fsub_rn(r_prev, v_prev); ep.max_score = ep.mean_score; }
+          }
           ep.value_sum = (float)vsum; ep.value_min = vmin;
           ep.cliffhanger = cliff ? !(cliff[(size_t)t_end * N + e] > 0.f) : 0;
           out[k] = ep;
@@ -241,6 +273,11 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
     ep.actor = e; ep.t_start = start; ep.t_end = T; ep.seed = seeds ? seeds[(size_t)start * N + e] : -1;
     const int n = T - start;
     ep.mean_score = (float)(sum / (double)n); ep.max_score = mx; ep.reward_sum = rsum;
+    if (strategy == MGPLR_SCORE_MIN_MARGIN) { ep.mean_score = (float)(1.0 + sum / (double)n); ep.max_score = 1.0f + mx; }
+    if (strategy == MGPLR_SCORE_ONE_STEP_TD) {
+      if (n > 1) ep.mean_score = (float)(sum / (double)(n - 1));
+      else { ep.mean_score = __fsub_rn(r_prev, v_prev); ep.max_score = ep.mean_score; }
+    }
     ep.value_sum = (float)vsum; ep.value_min = vmin; ep.cliffhanger = 2;
     out[k] = ep;
   }
@@ -256,9 +293,20 @@ extern "C" int mgplr_plr_episode_scores(const float *masks, const float *cliffha
                                         const float *value_preds, const float *rewards, const int32_t *level_seeds, int32_t T,
                                         int32_t N, int32_t strategy, mgplr_episode *episodes, int32_t max_episodes,
                                         int32_t *n_episodes, void *stream) {
-  if (!masks || !value_preds || !rewards || !episodes || !n_episodes || T < 1 || N < 1)
+  return mgplr_plr_episode_scores_ex(masks, cliffhanger_masks, returns, value_preds, rewards, level_seeds, nullptr, 0, 0.0, T, N,
+                                     strategy, episodes, max_episodes, n_episodes, stream);
+}
+
+extern "C" int mgplr_plr_episode_scores_ex(const float *masks, const float *cliffhanger_masks, const float *returns,
+                                           const float *value_preds, const float *rewards, const int32_t *level_seeds,
+                                           const float *action_log_dist, int32_t num_actions, double gamma, int32_t T, int32_t N,
+                                           int32_t strategy, mgplr_episode *episodes, int32_t max_episodes,
+                                           int32_t *n_episodes, void *stream) {
+  if (!masks || !value_preds || !rewards || !episodes || !n_episodes || T < 1 || N < 1 || strategy < 0 || strategy > MGPLR_SCORE_ONE_STEP_TD)
     return pfail(MGPLR_E_BADARG, "mgplr_plr_episode_scores: bad arguments");
-  if (strategy != MGPLR_SCORE_MAX_MC && !returns) return pfail(MGPLR_E_BADARG, "returns required for this strategy");
+  const bool logit = strategy == MGPLR_SCORE_LEAST_CONFIDENCE || strategy == MGPLR_SCORE_MIN_MARGIN;
+  if (logit && (!action_log_dist || num_actions < 2)) return pfail(MGPLR_E_BADARG, "action_log_dist required for this strategy");
+  if (strategy <= MGPLR_SCORE_VALUE_L1 && !returns) return pfail(MGPLR_E_BADARG, "returns required for this strategy");
   int dev = 0;
   PCK(cudaGetDevice(&dev));
   const int n_blocks = (N + 1023) / 1024;
@@ -275,7 +323,8 @@ extern "C" int mgplr_plr_episode_scores(const float *masks, const float *cliffha
   k_count_episodes<<<(N + 127) / 128, 128, 0, st>>>(masks, T, N, counts);
   k_scan_blocks<<<n_blocks, 1024, 0, st>>>(counts, N, offsets, block_off);
   k_scan_tops<<<1, 1024, 0, st>>>(block_off, n_blocks, n_episodes);
-  k_episode_scores<<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, returns, value_preds, rewards, level_seeds, T, N,
+  k_episode_scores<<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, (strategy <= MGPLR_SCORE_VALUE_L1) ? returns : nullptr,
+                                                    value_preds, rewards, level_seeds, action_log_dist, num_actions, (float)gamma, T, N,
                                                     strategy, offsets, block_off, episodes, max_episodes);
   PCK(cudaGetLastError());
   return 0;

@@ -31,6 +31,7 @@ _TRANSFORMS = {'constant': 0, 'rank': 1, 'power': 2}
 _KERNEL_STRATEGY = {  # -> (MGPLR_SCORE_* code)
     'positive_value_loss': 0, 'signed_value_loss': 1, 'gae': 1, 'value_l1': 2,
     'grounded_signed_value_loss': 3, 'uniform': 3,
+    'least_confidence': 4, 'min_margin': 5, 'one_step_td_error': 6,
 }
 
 
@@ -59,9 +60,9 @@ class LevelSampler(object):
         self.gamma = gamma
         self.use_dense_rewards = use_dense_rewards
         self.device = device
-        if strategy.startswith('tscl') or strategy in ('policy_entropy', 'least_confidence', 'min_margin',
-                                                       'one_step_td_error', 'alt_advantage_abs',
-                                                       'grounded_positive_value_loss'):
+        if strategy.startswith('tscl') or strategy in ('policy_entropy', 'alt_advantage_abs', 'grounded_positive_value_loss'):
+            # policy_entropy cannot run in the reference either ([L,7] * [L] broadcast, level_sampler.py:281); alt_returns is not
+            # a RolloutStorage buffer; grounded_positive needs a second pass with the host-side grounded value
             raise NotImplementedError('score strategy %r is not part of the B200 build' % strategy)
         if use_dense_rewards and strategy.startswith('grounded'):
             raise NotImplementedError('grounded scores with dense rewards (CarRacing) are out of scope')
@@ -319,12 +320,17 @@ class LevelSampler(object):
         seeds = cu(rollouts.level_seeds, t.int32)
         max_eps = int(N) * (int(T) + 1)
         code = _KERNEL_STRATEGY[self.strategy]
+        logits, n_act = None, 0
+        if code in (4, 5):  # policy-logit strategies read RolloutStorage.action_log_dist [T,N,A] (level_sampler.py:512-513)
+            logits = rollouts.action_log_dist.detach().to(dev).to(t.float32).contiguous()
+            n_act = int(logits.shape[-1])
         ep = t.zeros(max_eps, 10, dtype=t.int32, device=dev)
         n_ep = t.zeros(1, dtype=t.int32, device=dev)
         stream = t.cuda.current_stream(dev).cuda_stream
-        _lib.check(L.mgplr_plr_episode_scores(_lib.ptr(masks), _lib.ptr(cliff), _lib.ptr(returns), _lib.ptr(values),
-                                              _lib.ptr(rewards), _lib.ptr(seeds), int(T), int(N), code, _lib.ptr(ep),
-                                              max_eps, _lib.ptr(n_ep), stream), 'mgplr_plr_episode_scores')
+        _lib.check(L.mgplr_plr_episode_scores_ex(_lib.ptr(masks), _lib.ptr(cliff), _lib.ptr(returns), _lib.ptr(values),
+                                                 _lib.ptr(rewards), _lib.ptr(seeds), _lib.ptr(logits), n_act, float(self.gamma),
+                                                 int(T), int(N), code, _lib.ptr(ep), max_eps, _lib.ptr(n_ep), stream),
+                   'mgplr_plr_episode_scores')
         n = int(n_ep.item())
         rec = ep[:n].cpu().numpy().view(np.dtype(_lib.EPISODE_DTYPE)).reshape(-1)
         return rec

@@ -211,6 +211,9 @@ int mgplr_batched_value_loss(const float *returns, const float *value_preds, int
 #define MGPLR_SCORE_SIGNED_VALUE_LOSS 1
 #define MGPLR_SCORE_VALUE_L1 2
 #define MGPLR_SCORE_MAX_MC 3 /* per-episode pieces of grounded_* : sum of rewards and value sums */
+#define MGPLR_SCORE_LEAST_CONFIDENCE 4 /* 1 - max softmax probability           (level_sampler.py:288-296) */
+#define MGPLR_SCORE_MIN_MARGIN 5       /* mean: 1 - mean(p1 - p2), max: 1 - min  (level_sampler.py:298-306) */
+#define MGPLR_SCORE_ONE_STEP_TD 6      /* |r[t] + gamma v[t+1] - v[t]|           (level_sampler.py:425-437) */
 
 /* Episode record produced by the scoring kernel, in the reference's actor-major / time-minor order. */
 typedef struct mgplr_episode {
@@ -234,6 +237,15 @@ int mgplr_plr_episode_scores(const float *masks, const float *cliffhanger_masks,
                              const float *value_preds, const float *rewards, const int32_t *level_seeds, int32_t T,
                              int32_t N, int32_t strategy, mgplr_episode *episodes, int32_t max_episodes,
                              int32_t *n_episodes, void *stream);
+
+/* Same with the policy-logit strategies: action_log_dist f32 [T][N][num_actions] (RolloutStorage.action_log_dist; a
+ * log_softmax is applied per step as level_sampler.py:513 does) is needed by LEAST_CONFIDENCE / MIN_MARGIN, gamma by
+ * ONE_STEP_TD.  action_log_dist may be NULL for the other strategies. */
+int mgplr_plr_episode_scores_ex(const float *masks, const float *cliffhanger_masks, const float *returns,
+                                const float *value_preds, const float *rewards, const int32_t *level_seeds,
+                                const float *action_log_dist, int32_t num_actions, double gamma, int32_t T, int32_t N,
+                                int32_t strategy, mgplr_episode *episodes, int32_t max_episodes, int32_t *n_episodes,
+                                void *stream);
 
 #define MGPLR_TRANSFORM_CONSTANT 0
 #define MGPLR_TRANSFORM_RANK 1

@@ -68,10 +68,14 @@ PLR_CASES = [
     ('pvl_4000', 'positive_value_loss', 4000, 0.3, 0.3, 0.5, 0.01, 32, 256),
     ('l1_nostale', 'value_l1', 16, 1.0, 0.0, 0.95, 0.25, 4, 48),
     ('signed_power', 'signed_value_loss', 16, 0.5, 0.1, 0.9, 0.25, 4, 48),
+    # policy-logit / TD strategies (the rollouts' action_log_dist is recorded for these)
+    ('lc_small', 'least_confidence', 16, 0.3, 0.3, 0.8, 0.25, 4, 48),
+    ('mm_small', 'min_margin', 16, 0.3, 0.3, 0.8, 0.25, 4, 48),
+    ('td_small', 'one_step_td_error', 16, 0.3, 0.3, 0.8, 0.25, 4, 48),
 ]
 
 
-def gen_sampler():
+def gen_sampler(only=None):
     """A replayed PLR session: new levels observed, rollouts scored, buffer admission/eviction, replay
     decisions and draws -- all from the reference LevelSampler/LevelStore with a seeded global np.random."""
     import numpy as np
@@ -79,6 +83,8 @@ def gen_sampler():
     from level_replay import LevelSampler, LevelStore
     from gym import spaces
     for tag, strategy, buf, temp, sc, rp, rho, A, T in PLR_CASES:
+        if only is not None and tag not in only:
+            continue
         np.random.seed(77)
         rs = np.random.RandomState(5)
         transform = 'power' if tag == 'signed_power' else 'rank'
@@ -136,6 +142,8 @@ def gen_sampler():
             for k in ('rewards', 'value_preds', 'masks', 'cliffhanger_masks', 'returns'):
                 rec[k] = getattr(st, k).numpy()[:, :, 0].copy()
             rec['level_seeds'] = ls
+            if strategy in ('least_confidence', 'min_margin'):
+                rec['action_log_dist'] = st.action_log_dist.numpy().copy()
             if replay or True:  # robust PLR also scores the non-replay (exploratory) rollouts
                 sampler.update_with_rollouts(st)
                 sampler.after_update()
@@ -309,9 +317,37 @@ def gen_storage():
     print('storage fixtures', len(out), 'arrays + 1 session')
 
 
+def gen_score_functions():
+    """The reference's own per-episode score functions (level_sampler.py:288-306,425-437) on random episodes, called the
+    way _update_with_rollouts calls them (log_softmax of the stored logits): known answers for the numpy oracle."""
+    import numpy as np
+    import torch
+    from level_replay import LevelSampler
+    from gym import spaces
+    rs = np.random.RandomState(41)
+    s = LevelSampler([], {'image': spaces.Box(0, 255, (3, 5, 5), 'uint8')}, spaces.Discrete(7), num_actors=1,
+                     strategy='least_confidence', gamma=0.995, seed_buffer_size=4)
+    out = {'gamma': 0.995}
+    lens = [1, 2, 3, 7, 19, 64, 250]
+    for k, L in enumerate(lens):
+        logits = (rs.randn(L, 7) * 2).astype(np.float32)
+        rewards = (rs.rand(L) < 0.2).astype(np.float32) * rs.rand(L).astype(np.float32)
+        values = rs.randn(L).astype(np.float32)
+        lp = torch.log_softmax(torch.from_numpy(logits), -1)
+        kw = dict(episode_logits=lp, rewards=torch.from_numpy(rewards).unsqueeze(-1), value_preds=torch.from_numpy(values).unsqueeze(-1))
+        out['logits_%d' % k], out['rewards_%d' % k], out['values_%d' % k] = logits, rewards, values
+        out['lc_%d' % k] = np.array(s._average_least_confidence(**kw), np.float64)
+        out['mm_%d' % k] = np.array(s._average_min_margin(**kw), np.float64)
+        out['td_%d' % k] = np.array(s._one_step_td_error(**kw), np.float64)
+    out['n'] = len(lens)
+    np.savez_compressed(os.path.join(GOLDEN, 'plr_score_functions.npz'), **out)
+    print('score function fixtures', len(lens), 'episodes')
+
+
 def gen_plr():
     rh.activate()
     gen_gae()
+    gen_score_functions()
     gen_storage()
     gen_weights()
     gen_sampler()

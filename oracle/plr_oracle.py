@@ -58,7 +58,18 @@ def batched_value_loss(returns, values, signed=False, positive_only=False, power
     return m
 
 
-def episode_scores(masks, cliff, returns, values, rewards, seeds, strategy):
+def _logit_scores(logits, strategy):
+    """per-step scores of the policy-logit strategies (level_sampler.py:288-306) from raw logits [L, A]."""
+    x = logits.astype(np.float32)
+    lp = x - x.max(-1, keepdims=True)
+    lp = lp - np.log(np.exp(lp).sum(-1, keepdims=True))  # log_softmax (level_sampler.py:513)
+    p = np.sort(np.exp(lp), axis=-1)
+    if strategy == 'least_confidence':
+        return (np.float32(1) - p[:, -1]).astype(np.float32)
+    return (p[:, -1] - p[:, -2]).astype(np.float32)
+
+
+def episode_scores(masks, cliff, returns, values, rewards, seeds, strategy, logits=None, gamma=0.999):
     """Episode records in actor-major / time-minor order: dicts with actor, t_start, t_end, seed, mean, max,
     reward_sum, value_sum, value_min, cliffhanger."""
     T, N = rewards.shape
@@ -71,14 +82,29 @@ def episode_scores(masks, cliff, returns, values, rewards, seeds, strategy):
             sl = slice(start, t)
             adv = returns[sl, a].astype(np.float64) - values[sl, a].astype(np.float64) if returns is not None else None
             adv32 = (returns[sl, a] - values[sl, a]).astype(np.float32) if returns is not None else None
+            mean = mx = None
             if strategy == 'positive_value_loss':
                 sc = np.maximum(adv32, 0)
             elif strategy == 'value_l1':
                 sc = np.abs(adv32)
+            elif strategy == 'least_confidence':
+                sc = _logit_scores(logits[sl, a], strategy)
+            elif strategy == 'min_margin':  # mean: 1 - mean(margin), max: 1 - min(margin)  (level_sampler.py:298-306)
+                m = _logit_scores(logits[sl, a], strategy)
+                mean, mx = 1.0 - float(np.mean(m.astype(np.float64))), float(np.float32(1) - np.min(m))
+                sc = m
+            elif strategy == 'one_step_td_error':  # level_sampler.py:425-437
+                r32, v32 = rewards[sl, a].astype(np.float32), values[sl, a].astype(np.float32)
+                if len(r32) > 1:
+                    sc = np.abs((r32[:-1] + np.float32(gamma) * v32[1:]) - v32[:-1])
+                else:
+                    sc = r32[:1] - v32[:1]
             else:
                 sc = adv32
+            if mean is None:
+                mean, mx = float(np.mean(sc.astype(np.float64))), float(np.max(sc))
             recs.append(dict(actor=a, t_start=start, t_end=t, seed=int(seeds[start, a]),
-                             mean=float(np.mean(sc.astype(np.float64))), max=float(np.max(sc)),
+                             mean=mean, max=mx,
                              reward_sum=float(np.sum(rewards[sl, a].astype(np.float64))),
                              value_sum=float(np.sum(values[sl, a].astype(np.float64))), value_min=float(np.min(values[sl, a])),
                              cliffhanger=int(not (cliff[t, a] > 0))))

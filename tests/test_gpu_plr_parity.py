@@ -53,10 +53,12 @@ def _rollouts_from(rec):
     for k in ('rewards', 'value_preds', 'masks', 'cliffhanger_masks', 'returns'):
         setattr(ro, k, torch.from_numpy(rec[k]).unsqueeze(-1).contiguous())
     ro.level_seeds = torch.from_numpy(rec['level_seeds']).unsqueeze(-1).contiguous()
+    if 'action_log_dist' in rec:
+        ro.action_log_dist = torch.from_numpy(rec['action_log_dist']).contiguous()
     return ro
 
 
-@pytest.mark.parametrize('strategy', ['positive_value_loss', 'signed_value_loss', 'value_l1'])
+@pytest.mark.parametrize('strategy', ['positive_value_loss', 'signed_value_loss', 'value_l1', 'least_confidence', 'min_margin', 'one_step_td_error'])
 def test_episode_scores_vs_oracle(strategy):
     from dcd_isaac_b200.level_sampler import LevelSampler
     from oracle import plr_oracle as po
@@ -70,15 +72,16 @@ def test_episode_scores_vs_oracle(strategy):
     masks[0, ::7] = 0  # a done at t == 0 must be skipped without moving start_t (level_sampler.py:504-505)
     rec['masks'] = masks
     rec['cliffhanger_masks'] = (rs.rand(T + 1, N) > 0.1).astype(np.float32)
-    s = LevelSampler([], None, None, num_actors=N, strategy=strategy, sample_full_distribution=True, seed_buffer_size=64)
+    rec['action_log_dist'] = (rs.randn(T, N, 7) * 2).astype(np.float32)
+    s = LevelSampler([], None, None, num_actors=N, strategy=strategy, sample_full_distribution=True, seed_buffer_size=64, gamma=0.995)
     got = s.episode_records(_rollouts_from(rec))
     want = po.episode_scores(rec['masks'], rec['cliffhanger_masks'], rec['returns'], rec['value_preds'], rec['rewards'],
-                             rec['level_seeds'], strategy)
+                             rec['level_seeds'], strategy, logits=rec['action_log_dist'], gamma=0.995)
     assert len(got) == len(want)
     for k in ('actor', 't_start', 't_end', 'seed', 'cliffhanger'):
         assert np.array_equal(got[k], np.array([w[k] for w in want])), k
     assert np.allclose(got['mean_score'], [w['mean'] for w in want], rtol=RTOL, atol=1e-7)
-    assert np.allclose(got['max_score'], [w['max'] for w in want], rtol=RTOL, atol=0)
+    assert np.allclose(got['max_score'], [w['max'] for w in want], rtol=RTOL, atol=1e-6)
     assert np.allclose(got['reward_sum'], [w['reward_sum'] for w in want], rtol=RTOL, atol=1e-7)
     assert np.allclose(got['value_min'], [w['value_min'] for w in want], rtol=0, atol=0)
 

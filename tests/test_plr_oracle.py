@@ -44,3 +44,20 @@ def test_storage_returns_and_value_loss():
             assert np.allclose(got, g['bvl_%s_%d' % (tag, k)], rtol=1e-5, atol=1e-7), (tag, k)
             k += 1
         assert k == 12
+
+
+def test_logit_and_td_score_functions():
+    """least_confidence / min_margin / one_step_td_error of the oracle against the reference's own score functions
+    (called on single episodes of length 1 .. 250 by oracle/gen_golden_plr.py::gen_score_functions)."""
+    g = golden('plr_score_functions.npz')
+    for k in range(int(g['n'])):
+        logits, rewards, values = g['logits_%d' % k], g['rewards_%d' % k], g['values_%d' % k]
+        L = len(rewards)
+        masks = np.ones((L + 1, 1), np.float32)
+        masks[L] = 0
+        for tag, strategy in (('lc', 'least_confidence'), ('mm', 'min_margin'), ('td', 'one_step_td_error')):
+            rec = po.episode_scores(masks, np.ones_like(masks), None, np.append(values, 0).reshape(L + 1, 1), rewards.reshape(L, 1),
+                                    np.ones((L, 1), np.int32), strategy, logits=logits.reshape(L, 1, 7), gamma=float(g['gamma']))
+            assert len(rec) == 1 and rec[0]['t_end'] == L
+            want = g['%s_%d' % (tag, k)]
+            assert np.allclose([rec[0]['mean'], rec[0]['max']], want, rtol=1e-5, atol=1e-6), (strategy, L, rec[0], want)
