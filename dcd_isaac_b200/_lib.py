@@ -49,7 +49,7 @@ EPISODE_DTYPE = [('actor', '<i4'), ('t_start', '<i4'), ('t_end', '<i4'), ('seed'
 SYMBOLS = (
     'mgplr_last_error', 'mgplr_abi_version', 'mgplr_venv_create', 'mgplr_venv_destroy', 'mgplr_venv_num_envs',
     'mgplr_venv_state_bytes', 'mgplr_seed', 'mgplr_reset', 'mgplr_step_adversary', 'mgplr_reset_agent',
-    'mgplr_reset_random', 'mgplr_reset_to_encoding', 'mgplr_load_levels', 'mgplr_reset_to_actions', 'mgplr_mutate_edits',
+    'mgplr_reset_random', 'mgplr_reset_to_encoding', 'mgplr_load_levels', 'mgplr_load_levels_at', 'mgplr_reset_to_actions', 'mgplr_mutate_edits',
     'mgplr_mutate_finalize', 'mgplr_step_env', 'mgplr_step_env_host', 'mgplr_rollout', 'mgplr_full_obs', 'mgplr_get_encodings',
     'mgplr_get_metrics', 'mgplr_get_agent_state', 'mgplr_get_errors', 'mgplr_peek_rng', 'mgplr_gae',
     'mgplr_discounted_returns', 'mgplr_batched_value_loss',
@@ -91,6 +91,7 @@ def load():
     L.mgplr_reset_random.argtypes = [vp, vp, C.POINTER(StepOut), vp]
     L.mgplr_reset_to_encoding.argtypes = [vp, vp, vp, i32, C.POINTER(StepOut), vp]
     L.mgplr_load_levels.argtypes = [vp, vp, i32, vp, i32, C.POINTER(StepOut), vp]
+    L.mgplr_load_levels_at.argtypes = [vp, vp, vp, i32, i32, C.POINTER(StepOut), vp]
     L.mgplr_reset_to_actions.argtypes = [vp, vp, i32, vp, i32, C.POINTER(StepOut), vp]
     L.mgplr_mutate_edits.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     L.mgplr_mutate_finalize.argtypes = [vp, vp, C.POINTER(StepOut), vp]

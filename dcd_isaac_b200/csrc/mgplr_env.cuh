@@ -417,6 +417,10 @@ __device__ __forceinline__ bool step_adversary(const Rows &R, Env &e, uint32_t &
   const int W = c.W, I = W - 2, A = I * I;
   if (loc < 0 || loc >= A) { err |= kErrBadLoc; return false; }
   flush_pending(R, e, rng, W);
+  {  // the level is edited below, possibly without a draw: DR candidates (their respawn draws) go stale
+    const uint32_t sp = rng.spec_p[rng.e];
+    if (sp & kSpecValidMask) rng.spec_p[rng.e] = sp & kSpecEpochMask;
+  }
   int adv_step = adv & 0xfff, adv_max = (adv >> 12) & 0xfff, sampled = (adv >> 24) & 1;
   if (c.resample && !sampled) {
     adv_max = (int)(((double)loc / (double)A) * (double)c.n_clutter) + 2;

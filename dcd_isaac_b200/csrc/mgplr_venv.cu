@@ -345,6 +345,39 @@ __global__ void k_load_levels(Dev d, const uint8_t *enc, int n_levels, const int
   s.sdir = start_dir & 3;
   s.pending = 0;  // deferred respawn draws belong to the previous level's stream position: dropped with it
   s.ep_ret = 0.f; s.ep_len = 0;
+  spec_invalidate(d, e);  // (DR candidates depend on the level through the respawn draws)
+  d.metrics[e] = compute_metrics(R, s, W, true);
+  if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+  d.hot[e] = pack(s);
+  emit_direct(R, s, d.c, o, e);
+}
+
+// The same for a subset of the envs with one level each: env_index[k] gets level k (environments that regenerate their
+// level on every reset, e.g. the Kruskal mazes of envs/multigrid/mst_maze.py, whose generator runs on the host).
+__global__ void k_load_levels_at(Dev d, const uint8_t *enc, const int32_t *env_index, int n, int start_dir, OutPtrs o) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int e = env_index[k];
+  if (e < 0 || e >= d.N) return;
+  const int W = d.c.W;
+  const Rows R = env_rows(d, e);
+  Env s = unpack(d.hot[e]);
+  const uint8_t *src = enc + (size_t)k * W * W * 3;
+  s.gx = s.gy = s.sx = s.sy = kNone;
+  for (int y = 0; y < W; y++) {
+    uint32_t row = 0;
+    for (int x = 0; x < W; x++) {
+      const uint8_t t = src[((size_t)x * W + y) * 3];
+      if (t == 2) row |= 1u << x;
+      else if (t == 8) { s.gx = x; s.gy = y; }
+      else if (t == 10) { s.sx = x; s.sy = y; }
+    }
+    R.set(y, row);
+  }
+  s.sdir = start_dir & 3;
+  s.pending = 0;
+  s.ep_ret = 0.f; s.ep_len = 0;
+  spec_invalidate(d, e);
   d.metrics[e] = compute_metrics(R, s, W, true);
   if (!reset_agent(s)) d.err[e] |= kErrNoStart;
   d.hot[e] = pack(s);
@@ -396,6 +429,7 @@ __global__ void k_mutate_edits(Dev d, const int32_t *locs, const int32_t *ops, c
   const Rows R = env_rows(d, e);
   Env s = unpack(d.hot[e]);
   if (s.pending) { Rng rng = RNG_OF(d, e); flush_pending(R, s, rng, W); rng.store(); }
+  spec_invalidate(d, e);
   const int k = n_edits[e];
   for (int n = 0; n < k && n < max_edits; n++) {
     const int loc = locs[(size_t)e * max_edits + n], op = ops[(size_t)e * max_edits + n];
@@ -435,6 +469,7 @@ __global__ void k_mutate_finalize(Dev d, const int32_t *choice, OutPtrs o) {
     if (sel >= 0) { s.sx = sel % I + 1; s.sy = sel / I + 1; s.has_agent = 1; s.ax = s.sx; s.ay = s.sy; }
   }
   s.step_count = 0;
+  spec_invalidate(d, e);
   d.adv[e] = d.adv[e] & ~0xfffu;  // adversary_step_count = 0
   d.metrics[e] = compute_metrics(R, s, W, true);
   if (!reset_agent(s)) d.err[e] |= kErrNoStart;
@@ -1393,6 +1428,15 @@ extern "C" int mgplr_load_levels(mgplr_venv *v, const uint8_t *enc, int32_t n_le
   if (!enc || n_levels < 1) return fail(MGPLR_E_BADARG, "mgplr_load_levels: bad arguments");
   k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d);  // the RNG stream keeps its reference position
   k_load_levels<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, enc, n_levels, level_index, start_dir, outptrs(out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mgplr_load_levels_at(mgplr_venv *v, const uint8_t *enc, const int32_t *env_index, int32_t n, int32_t start_dir,
+                                    const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  if (!enc || !env_index || n < 1 || n > v->d.N) return fail(MGPLR_E_BADARG, "mgplr_load_levels_at: bad arguments");
+  k_load_levels_at<<<grid_for(n, 128), 128, 0, st>>>(v->d, enc, env_index, n, start_dir, outptrs(out));
   CK(cudaGetLastError());
   return 0;
 }

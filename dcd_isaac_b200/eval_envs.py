@@ -1,0 +1,15 @@
+"""Zero-shot evaluation environments: one constructor for what eval.py's Evaluator builds per
+test env name (eval.py:176-204: gym_make + optional MultiGridFullyObsWrapper, then the vector-env wrappers)."""
+from .mazes import MAZES
+from .mst_maze import MST_MAZES, CudaMSTMazeVecEnv
+from .vec_env import CudaMazeVecEnv
+
+
+def make_eval_venv(env_name, num_processes, device='cuda:0', full_obs=False):
+    """env_name: one of the fixed-bitmap mazes of envs/multigrid/maze.py (MultiGrid-SixteenRooms-v0, -Labyrinth-v0,
+    -Maze-v0, ...) or a Kruskal perfect maze of envs/multigrid/mst_maze.py (Small / Medium)."""
+    if env_name in MAZES:
+        return CudaMazeVecEnv(env_name, num_processes, device=device, full_obs=full_obs)
+    if env_name in MST_MAZES:
+        return CudaMSTMazeVecEnv(env_name, num_processes, device=device, full_obs=full_obs)
+    raise NotImplementedError('%s: MiniGrid-Crossing / FourRooms are plain gym-minigrid envs (third-party, not built)' % env_name)

@@ -119,6 +119,13 @@ int mgplr_reset_to_encoding(mgplr_venv *v, const uint8_t *enc, const int32_t *in
 int mgplr_load_levels(mgplr_venv *v, const uint8_t *enc, int32_t n_levels, const int32_t *level_index, int32_t start_dir,
                       const mgplr_step_out *out, void *stream);
 
+/* The same for n of the envs with one level each: env env_index[k] (i32 [n], device) gets level k of enc u8 [n][W][W][3];
+ * the other envs are untouched.  For environments that regenerate their level on every reset with a host-side generator
+ * (the Kruskal perfect mazes, envs/multigrid/mst_maze.py:55-115: worker auto-reset, parallel_wrappers.py:20-25).
+ * Outputs are written at rows env_index[k]. */
+int mgplr_load_levels_at(mgplr_venv *v, const uint8_t *enc, const int32_t *env_index, int32_t n, int32_t start_dir,
+                         const mgplr_step_out *out, void *stream);
+
 /* Same, action-string form: locs i32 [n][len] (device), replayed through step_adversary. */
 int mgplr_reset_to_actions(mgplr_venv *v, const int32_t *locs, int32_t len, const int32_t *index, int32_t n,
                            const mgplr_step_out *out, void *stream);
