@@ -434,6 +434,42 @@ class CudaAdversarialVecEnv(object):
     def get_max_episode_steps(self):
         return self.spec['max_episode_steps']
 
+    def max_episode_steps(self):
+        """parallel_wrappers.py:200-203 (the TimeLimit's _max_episode_steps of env 0)."""
+        return self.get_max_episode_steps()
+
+    # baselines' two-phase VecEnv calls (parallel_wrappers.py:232-311): the work is a kernel launch, so *_async runs the call
+    # and *_wait hands the result over
+    def step_env_async(self, action):
+        self._pending_result = self.step_env(action, reset_random=False)
+
+    def step_env_reset_random_async(self, action):
+        self._pending_result = self.step_env(action, reset_random=True)
+
+    def step_adversary_async(self, action):
+        self._pending_result = self.step_adversary(action)
+
+    def step_async(self, action):
+        self._pending_result = self.step(action)
+
+    def step_wait(self):
+        res, self._pending_result = self._pending_result, None
+        return res
+
+    def level_seed(self, index):
+        """parallel_wrappers.py:272-285: the `level_seed` attribute of env `index`; MultiGrid envs have none."""
+        raise AttributeError("MultiGrid environments have no attribute 'level_seed'")
+
+    def get_level(self):
+        """parallel_wrappers.py:418-420 (`level` attribute): not defined by the MultiGrid envs either."""
+        raise AttributeError("MultiGrid environments have no attribute 'level'")
+
+    def get_complexity_info(self):
+        raise NotImplementedError('get_complexity_info is the Box2D envs\' (BipedalWalker / CarRacing), out of scope')
+
+    def render_to_screen(self):
+        raise NotImplementedError('RGB rendering is out of scope (SURVEY.md 8f rank 4)')
+
     def get_observation_space(self):
         return self.observation_space
 
