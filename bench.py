@@ -203,7 +203,7 @@ def run_ours(a):
     flags = torch.zeros(T, N, dtype=torch.uint8, device=dev)
     ep_r = torch.zeros(N, device=dev)
     ep_l = torch.zeros(N, dtype=torch.int32, device=dev)
-    max_eps = N * 4  # ~2.2 episodes per env per rollout here; the kernel drops records beyond the cap
+    max_eps = N * 3  # ~2.2 episodes per env per rollout here (checked below); the kernel drops records beyond the cap
     episodes = torch.zeros(max_eps, 10, dtype=torch.int32, device=dev)
     n_eps = torch.zeros(1, dtype=torch.int32, device=dev)
     gathered = torch.zeros(world * max_eps, 10, dtype=torch.int32, device=dev) if world > 1 else None
@@ -317,6 +317,7 @@ def run_ours(a):
     n_done = int((flags & 1).sum().item())
     n_goal = int(((flags & 8) > 0).sum().item())
     n_episodes = int(n_eps.item())
+    assert n_episodes <= max_eps, 'episode-record buffer too small: %d > %d' % (n_episodes, max_eps)
 
     # ---- e2e: the host-buffer C-ABI call every vector step (actions from pinned host memory, results to host)
     e2e = None
