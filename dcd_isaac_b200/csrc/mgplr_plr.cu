@@ -197,10 +197,11 @@ __device__ __forceinline__ float logit_score(const float *__restrict__ x, int A,
   return expf(m1 - lse) - expf(m2 - lse);
 }
 
+template <int strategy>  // compile-time: the common value-loss instances stay free of the logit / TD code
 __global__ void k_episode_scores(const float *__restrict__ masks, const float *__restrict__ cliff, const float *__restrict__ returns,
                                  const float *__restrict__ values, const float *__restrict__ rewards,
                                  const int32_t *__restrict__ seeds, const float *__restrict__ logits, int A, float gamma,
-                                 int T, int N, int strategy,
+                                 int T, int N,
                                  const int32_t *__restrict__ offsets, const int32_t *__restrict__ block_off,
                                  mgplr_episode *__restrict__ out, int max_out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,6 +214,7 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
   // The time loop is latency-bound if it issues one step's loads at a time (4 x 128 B in flight per warp): steps are
   // loaded kB at a time (4 kB independent loads in flight) and then consumed in order.
   constexpr int kB = 8;  // (16 was measured slower: 403 vs 235 us at 131 072 actors -- registers, occupancy)
+  // (loading batch k+1 while batch k is consumed was measured slower too: 297 us, 96 registers)
   for (int t0 = 0; t0 < T; t0 += kB) {
     float retb[kB], vb[kB], rb[kB], mb[kB];
 #pragma unroll
@@ -323,9 +325,20 @@ extern "C" int mgplr_plr_episode_scores_ex(const float *masks, const float *clif
   k_count_episodes<<<(N + 127) / 128, 128, 0, st>>>(masks, T, N, counts);
   k_scan_blocks<<<n_blocks, 1024, 0, st>>>(counts, N, offsets, block_off);
   k_scan_tops<<<1, 1024, 0, st>>>(block_off, n_blocks, n_episodes);
-  k_episode_scores<<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, (strategy <= MGPLR_SCORE_VALUE_L1) ? returns : nullptr,
-                                                    value_preds, rewards, level_seeds, action_log_dist, num_actions, (float)gamma, T, N,
-                                                    strategy, offsets, block_off, episodes, max_episodes);
+#define SCORES(S)                                                                                                          \
+  k_episode_scores<S><<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, (S <= MGPLR_SCORE_VALUE_L1) ? returns : nullptr, \
+                                                       value_preds, rewards, level_seeds, action_log_dist, num_actions, (float)gamma, \
+                                                       T, N, offsets, block_off, episodes, max_episodes)
+  switch (strategy) {
+    case MGPLR_SCORE_POSITIVE_VALUE_LOSS: SCORES(MGPLR_SCORE_POSITIVE_VALUE_LOSS); break;
+    case MGPLR_SCORE_SIGNED_VALUE_LOSS: SCORES(MGPLR_SCORE_SIGNED_VALUE_LOSS); break;
+    case MGPLR_SCORE_VALUE_L1: SCORES(MGPLR_SCORE_VALUE_L1); break;
+    case MGPLR_SCORE_MAX_MC: SCORES(MGPLR_SCORE_MAX_MC); break;
+    case MGPLR_SCORE_LEAST_CONFIDENCE: SCORES(MGPLR_SCORE_LEAST_CONFIDENCE); break;
+    case MGPLR_SCORE_MIN_MARGIN: SCORES(MGPLR_SCORE_MIN_MARGIN); break;
+    default: SCORES(MGPLR_SCORE_ONE_STEP_TD); break;
+  }
+#undef SCORES
   PCK(cudaGetLastError());
   return 0;
 }
