@@ -44,7 +44,8 @@ struct Dev {
   // speculative next-level generation of the DR auto-reset (step_env(reset_random=True)), see the "speculation" block
   uint32_t *spec;    // [N] bits 16+2p / 17+2p: candidate 0 (episode ended without a goal) / 1 (ended at the goal) built for a
                      //     level epoch of parity p is valid; bits 20-26: level epoch (bumped by every DR reset)
-  uint32_t *cand;    // [N][2 epochs][2][W + 8] candidate records: wall rows, packed goal/start, -, words consumed, error bits
+  uint32_t *cand;    // [N][2 epochs][2][W + 8 + 128] candidate records: wall rows, packed goal/start, -, words consumed, error
+                     //     bits, and the NEW MT state words of the consumed span (so that a commit copies, never recomputes)
   uint2 *rr_list;    // [2][2N] regeneration jobs {env << 8 | candidate << 7 | epoch, MT cursor}, one list per launch parity
   unsigned long long *prof;  // debug counters (MGPLR_RR_PROF), else NULL
   uint32_t *sched;   // [8] regeneration phase: [0..1] jobs appended to list p, [2..3] next ticket of list p, [4] warps exited,
@@ -67,7 +68,8 @@ __host__ __device__ inline uint32_t spec_valid_bit(uint32_t ep, int k) { return 
 constexpr uint32_t kSpecEpochMask = 127u << kSpecEpochShift;
 __host__ __device__ inline uint32_t spec_epoch(uint32_t sp) { return (sp & kSpecEpochMask) >> kSpecEpochShift; }
 constexpr int kSpecWindow = 224;   // MT words one regeneration job can look ahead (< 227: all computable from the present state)
-__host__ __device__ inline int cand_words(int W) { return W + 8; }
+constexpr int kSpecState = 128;     // new MT state words a candidate record carries (a record that consumed more is not published)
+__host__ __device__ inline int cand_words(int W) { return W + 8 + kSpecState; }
 
 // `pending` = goal respawns (multigrid.py:821-838) whose env-RNG draws have not been made yet.  A respawn draw
 // depends only on the level (walls + goal; the agent is off the grid while it is drawn) and its result is
@@ -491,43 +493,6 @@ __device__ __forceinline__ void reset_random(const Rows &R, Env &e, uint32_t &ad
 // 32-word batch (one memory round trip per 32 draws), lane y owns row y of the grid (gen_grid, wall count and the
 // flood fill become a handful of shuffles per iteration), and the (inherently serial) rejection sampling runs
 // warp-uniformly on broadcast values.  Draw order and count are exactly reset_random()'s.
-// Apply `a` (<= kSpecWindow < 227) logically consumed words to env e's MT state, all lanes of the warp together: every new
-// state word of the span only depends on PRESENT state words (j, j+1, j+397 mod 624), so all are loaded first, then stored.
-__device__ __forceinline__ void coop_mt_advance(const Dev &d, int e, int lane, uint32_t &idx, uint32_t &used, int a) {
-  // 96 words (3 per lane) per pass: one pass for a typical record (~85 words).  A later pass only reads words that
-  // earlier passes did not store (word j reads present words j, j+1 and j+397 mod 624, the latter outside the span).
-  constexpr int kPer = 3;
-#pragma unroll 1
-  for (int j0 = 0; j0 < a; j0 += 32 * kPer) {
-    uint32_t xs[kPer], bs[kPer], cs[kPer];
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {  // all loads first (lanes past `a` re-read word j0: no branch in the way)
-      const int j = (j0 + lane + 32 * i < a) ? j0 + lane + 32 * i : j0;
-      uint32_t p = idx + j, p1 = p + 1, pm = p + 397;
-      if (p >= 624) p -= 624;
-      if (p1 >= 624) p1 -= 624;
-      if (pm >= 624) pm -= 624;
-      if (pm >= 624) pm -= 624;
-      xs[i] = d.mt[mt_at(e, p)]; bs[i] = d.mt[mt_at(e, p1)]; cs[i] = d.mt[mt_at(e, pm)];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < kPer; i++) {
-      const int j = j0 + lane + 32 * i;
-      if (j < a) {
-        const uint32_t y = (xs[i] & 0x80000000u) | (bs[i] & 0x7fffffffu);
-        uint32_t p = idx + j;
-        if (p >= 624) p -= 624;
-        d.mt[mt_at(e, p)] = cs[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-    }
-    __syncwarp();
-  }
-  idx += a;
-  if (idx >= 624) idx -= 624;
-  used += a;
-}
-
 struct CoopRng {
   uint32_t *mt, *mti_p, *words_p;
   int N, e, lane;
@@ -927,6 +892,7 @@ __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *s
   const uint32_t cur_row = (k == 1 && lane < W) ? __ldcg(env_rows(d, e).p + lane * 32) : 0xffffffffu;
   // look-ahead window: tempered outputs idx .. idx + kSpecWindow - 1 of the present state (nothing is stored to mt).
   // All 21 loads per lane are issued before the first shared-memory store (which the compiler must order against them).
+  uint32_t nst[kSpecState / 32];  // untempered = new state words of positions lane + 32 i
   {
     constexpr int kPer = kSpecWindow / 32;
     uint32_t xs[kPer], bs[kPer], cs[kPer];
@@ -943,6 +909,7 @@ __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *s
     for (int i = 0; i < kPer; i++) {
       uint32_t y = (xs[i] & 0x80000000u) | (bs[i] & 0x7fffffffu);
       y = cs[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      if (i < kSpecState / 32) nst[i] = y;
       y ^= (y >> 11);
       y ^= (y << 7) & 0x9d2c5680u;
       y ^= (y << 15) & 0xefc60000u;
@@ -964,9 +931,11 @@ __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *s
   if (d.prof && lane == 0) {
     atomicAdd(&d.prof[6], (unsigned long long)(c2 - c1)); atomicAdd(&d.prof[7], (unsigned long long)(clock64() - c2));
   }
-  if (!ok) return;
+  if (!ok || consumed > kSpecState) return;
   uint32_t *rec = cand_record(d, e, ep, k);
   if (lane < W) rec[lane] = lvl[lane];
+#pragma unroll
+  for (int i = 0; i < kSpecState / 32; i++) rec[W + 8 + lane + 32 * i] = nst[i];  // coalesced; the commit copies them into mt
   if (lane == 0) {
     rec[W] = ((uint32_t)o.gx & 31u) | (((uint32_t)o.gy & 31u) << 5) | (1u << 10) | (((uint32_t)o.sx & 31u) << 11) |
              (((uint32_t)o.sy & 31u) << 16) | (1u << 21) | ((uint32_t)o.sdir << 22);

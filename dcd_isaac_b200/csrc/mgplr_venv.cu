@@ -992,7 +992,24 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         const uint32_t *rec = cand_record(d, env, spec_epoch(__shfl_sync(0xffffffffu, sp, le)), pick);
         if (lane < W) rows[lane * kWarpTile + le] = __ldcg(rec + lane);
         uint32_t idx = __shfl_sync(0xffffffffu, cand_idx, le), used = __shfl_sync(0xffffffffu, cand_words_used, le);
-        coop_mt_advance(d, env, lane, idx, used, used_w);
+        // the record carries the new MT state words of the span it consumed: coalesced reads, fire-and-forget stores
+        {
+          uint32_t nw[kSpecState / 32];
+#pragma unroll
+          for (int i = 0; i < kSpecState / 32; i++) nw[i] = __ldcg(rec + W + 8 + lane + 32 * i);
+#pragma unroll
+          for (int i = 0; i < kSpecState / 32; i++) {
+            const int j = lane + 32 * i;
+            if (j < used_w) {
+              uint32_t p = idx + j;
+              if (p >= 624) p -= 624;
+              d.mt[mt_at(env, p)] = nw[i];
+            }
+          }
+          idx += used_w;
+          if (idx >= 624) idx -= 624;
+          used += used_w;
+        }
         if (lane == 0) { d.mti[env] = idx; d.words[env] = used; }
         if (lane == le) new_idx = idx;
       }
