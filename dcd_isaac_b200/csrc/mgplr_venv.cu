@@ -1269,8 +1269,7 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(cudaMemset(d.sched, 0, 8 * sizeof(uint32_t)));
   CK(dalloc(&d.spec, N, total));
   CK(cudaMemset(d.spec, 0, N * sizeof(uint32_t)));
-  CK(dalloc(&d.cand, N * 4 * (size_t)cand_words(cfg->width), total));
-  CK(dalloc(&d.rr_list, 4 * N, total));  // uint2 entries
+  d.cand = nullptr; d.rr_list = nullptr;  // DR speculation buffers: allocated by the first DR step launch (rr_spec_alloc)
   v->rr_spec = getenv("MGPLR_RR_SPEC") ? atoi(getenv("MGPLR_RR_SPEC")) : 1;  // DR speculation; 0 = in-kernel rebuild only
   v->host_dma = getenv("MGPLR_HOST_DMA") ? atoi(getenv("MGPLR_HOST_DMA")) : 0;
   CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
@@ -1492,6 +1491,20 @@ static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_rando
   if (out) A.o = *out;
   return launch_step_args(v, A, reset_random, st);
 }
+// candidate records + job lists of the DR speculation (2.4 KB per env at 15x15): only DR users pay for them
+static int rr_spec_alloc(mgplr_venv *v) {
+  if (v->d.cand) return 0;
+  const size_t N = (size_t)v->d.N;
+  cudaError_t e = dalloc(&v->d.cand, N * 4 * (size_t)cand_words(v->d.c.W), v->bytes);
+  if (e == cudaSuccess) e = dalloc(&v->d.rr_list, 4 * N, v->bytes);  // uint2 entries
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    v->d.cand = nullptr;
+    return fail((int)e, "allocating the DR speculation buffers failed (the first reset_random step must run outside CUDA graph capture)");
+  }
+  return 0;
+}
+
 static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st, int tile0, int tile1) {
   // persistent grid: as many 4-warp CTAs as fit on the chip (shared-memory bound), capped by the tile count
   const int W = v->d.c.W, wpc = 4;
@@ -1503,6 +1516,7 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
   // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing job phase
   A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample && (v->d.N >= 16384 || v->rr_spec > 1);
+  if (A.spec) { if (int rc = rr_spec_alloc(v)) return rc; }
   const int need = (n_tiles - tile0 + wpc - 1) / wpc;
   if (grid > need) grid = need;
   if (grid < 1) return 0;
