@@ -5,107 +5,84 @@ Host bookkeeping is a dict keyed by the level's bytes / action string exactly as
 handed out from 1, duplicates return the existing seed).  Byte-encoded levels are additionally mirrored in ONE
 uint8 tensor in HBM ([capacity, *shape], slot = seed's row), so that replaying a batch of levels is a device
 gather + mgplr_reset_to_encoding without touching the host (`get_levels_device`)."""
-from collections import defaultdict
-
 import numpy as np
 
 INT32_MAX = 2147483647
 
 
 class LevelStore(object):
+    """Public surface as consumed by envs/runners/adversarial_runner.py (:101-128, 371-376, 402-437): `insert`,
+    `get_level`, `reconcile_seeds`, `remove`, `len()`, and the maps `seed2level`, `level2seed`, `seed2parent`."""
+
     def __init__(self, max_size=None, data_info={}, device=None):
-        self.max_size = max_size
-        self.seed2level = defaultdict()
-        self.level2seed = defaultdict()
-        self.seed2parent = defaultdict()
-        self.next_seed = 1
-        self.levels = set()
-        self.data_info = data_info
-        self.device = device
-        self._mirror = None       # device tensor [capacity, *shape] (not pickled)
-        self._seed2slot = {}
-        self._free_slots = []
+        self.max_size, self.data_info, self.device = max_size, data_info, device
+        self.next_seed = 1                      # seeds are handed out from 1, never reused
+        self.seed2level, self.level2seed, self.seed2parent = {}, {}, {}
+        self._mirror, self._seed2slot, self._free_slots = None, {}, []   # HBM mirror (not pickled)
+
+    @property
+    def levels(self):
+        return self.level2seed.keys()
 
     def __len__(self):
-        return len(self.levels)
+        return len(self.level2seed)
 
     def __getstate__(self):
-        st = dict(self.__dict__)
-        st['_mirror'] = None
-        st['_seed2slot'] = {}
-        st['_free_slots'] = []
-        if st.get('device') is not None:
-            st['device'] = str(st['device'])
-        return st
+        state = {k: v for k, v in self.__dict__.items() if k not in ('_mirror', '_seed2slot', '_free_slots')}
+        state.update(_mirror=None, _seed2slot={}, _free_slots=[])
+        if state['device'] is not None:
+            state['device'] = str(state['device'])
+        return state
 
-    def __setstate__(self, st):
-        self.__dict__.update(st)
+    def __setstate__(self, state):
+        self.__dict__.update(state)
 
+    # -- insertion: content dedupe, lineage = parent's lineage + the parent level, FIFO eviction under max_size
     def _insert(self, level, parent_seed=None):
         if level is None:
             return None
-        if level not in self.levels:
-            if self.max_size is not None:  # FIFO if max size constraint
-                while len(self.levels) >= self.max_size:
-                    first_idx = list(self.seed2level)[0]
-                    self._remove(first_idx)
-            seed = self.next_seed
-            self.seed2level[seed] = level
-            if parent_seed is not None:
-                self.seed2parent[seed] = self.seed2parent[parent_seed] + [self.seed2level[parent_seed]]
-            else:
-                self.seed2parent[seed] = []
-            self.level2seed[level] = seed
-            self.levels.add(level)
-            self.next_seed += 1
-            return seed
-        return self.level2seed[level]
+        known = self.level2seed.get(level)
+        if known is not None:
+            return known
+        while self.max_size is not None and len(self.level2seed) >= self.max_size:
+            self._remove(next(iter(self.seed2level)))   # oldest surviving seed (dicts keep insertion order)
+        seed, self.next_seed = self.next_seed, self.next_seed + 1
+        lineage = [] if parent_seed is None else self.seed2parent[parent_seed] + [self.seed2level[parent_seed]]
+        self.seed2level[seed], self.level2seed[level], self.seed2parent[seed] = level, seed, lineage
+        return seed
 
     def insert(self, level, parent_seeds=None):
-        if hasattr(level, '__iter__') and not isinstance(level, (bytes, str)):
-            idx = []
-            for i, l in enumerate(level):
-                ps = None
-                if parent_seeds is not None:
-                    ps = parent_seeds[i]
-                idx.append(self._insert(l, ps))
-            return idx
-        return self._insert(level)
+        if isinstance(level, (bytes, str)) or not hasattr(level, '__iter__'):
+            return self._insert(level)
+        parents = parent_seeds if parent_seeds is not None else [None] * len(level)
+        return [self._insert(l, p) for l, p in zip(level, parents)]
 
     def _remove(self, level_seed):
         if level_seed is None or level_seed < 0:
             return
-        level = self.seed2level[level_seed]
-        self.levels.remove(level)
-        del self.seed2level[level_seed]
-        del self.level2seed[level]
-        del self.seed2parent[level_seed]
+        self.level2seed.pop(self.seed2level.pop(level_seed))
+        self.seed2parent.pop(level_seed)
         slot = self._seed2slot.pop(level_seed, None)
         if slot is not None:
             self._free_slots.append(slot)
 
     def remove(self, level_seed):
-        if hasattr(level_seed, '__iter__'):
-            for i in level_seed:
-                self._remove(i)
-        else:
-            self._remove(level_seed)
+        for seed in (level_seed if hasattr(level_seed, '__iter__') else (level_seed,)):
+            self._remove(seed)
 
     def reconcile_seeds(self, level_seeds):
-        old_seeds = set(self.seed2level)
-        new_seeds = set(level_seeds)
-        if len(new_seeds) == 1 and -1 in new_seeds:  # don't update if empty seeds
+        """Drop everything the sampler's working buffer no longer holds; an all-empty buffer ({-1}) changes nothing."""
+        keep = set(level_seeds)
+        if keep == {-1}:
             return
-        for seed in old_seeds - new_seeds:
+        for seed in [s for s in self.seed2level if s not in keep]:
             self._remove(seed)
 
     def get_level(self, level_seed):
         level = self.seed2level[level_seed]
-        if self.data_info:
-            if self.data_info.get('numpy', False):
-                dtype = self.data_info['dtype']
-                shape = self.data_info['shape']
-                level = np.frombuffer(level, dtype=dtype).reshape(*shape)
+        info = self.data_info
+        if info and info.get('numpy', False):
+            return np.frombuffer(level, dtype=info['dtype']).reshape(*info['shape'])
         return level
 
     # ------------------------------------------------------------------ device mirror
