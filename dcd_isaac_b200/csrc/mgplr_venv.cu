@@ -866,26 +866,70 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   asm volatile("griddepcontrol.launch_dependents;");
   if (!RR && tile >= n_tiles) return;  // (the DR variant's idle warps still serve the regeneration phase)
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
+  const bool use_spec = RR && A.spec;
+  const int rr_par = use_spec ? (int)(*(volatile uint32_t *)&d.sched[5] & 1u) : 0;  // stable for the whole launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
+  if (RR && use_spec) {
+    // ---- regeneration jobs FIRST: the jobs queued by the previous launch (list of the other parity; its length is
+    // final) are the long indivisible items of this launch (~15 us each), so warps take them before any tile; the warps
+    // that find the list empty start on the tiles at once, and because the tiles are handed out dynamically below, the
+    // job warps simply end up with fewer tiles.  Nothing waits on this launch's own progress.
+    const int q = rr_par ^ 1;
+    const uint32_t n_jobs = *(volatile uint32_t *)&d.sched[q];
+    const uint2 *list = d.rr_list + (size_t)q * 2 * N;
+    uint32_t *scr = reinterpret_cast<uint32_t *>(s_obs);  // the observation tile is not in use yet
+    for (;;) {
+      uint32_t j = 0;
+      if (lane == 0) j = atomicAdd(&d.sched[2 + q], 1u);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= n_jobs) break;
+      const long long c0 = d.prof ? clock64() : 0;
+      rr_regen_job(d, __ldcg(list + j), lane, scr);
+      __syncwarp();
+      if (d.prof && lane == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - c0);
+        atomicAdd(&d.prof[3], dt); atomicAdd(&d.prof[4], 1ull); atomicMax(&d.prof[5], dt);
+      }
+    }
+    if (d.prof && lane == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicMax(&d.prof[2], t1);               // end of this warp's job phase
+    }
+    __syncwarp();
+  }
   // the state plane of every observation is all zero: written once here, never touched by emit_packed_f32
 #pragma unroll
   for (int i = 0; i < kV * kV; i++) s_obs[lane * kObsFloats + 2 * kV * kV + i] = 0.0f;
   __syncwarp();
   const uint64_t pol_keep = l2_policy(d.l2_hints ? 1 : 0), pol_stream = l2_policy(d.l2_hints ? 2 : 0);
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
   if (A.done_count_next && blockIdx.x == 0 && threadIdx.x == 0) *A.done_count_next = 0;
+  // Tile assignment: static round-robin (tile = global_warp + k * total_warps) -- a dynamic scheduler on one global
+  // counter doubled the reset_agent variant's launch time -- EXCEPT in the speculative DR variant, where warps carry very
+  // different loads (jobs, commits): there the next tile is a ticket, requested one tile ahead so that the atomic's
+  // round trip hides behind a tile's work.
+  const bool dyn = RR && use_spec;
+  uint32_t ticket = 0;  // (lane 0) ticket of the tile after `next`
+  int next;
+  if (dyn) {
+    uint32_t t0 = 0, t1 = 0;
+    if (lane == 0) { t0 = atomicAdd(&d.sched[6], 1u); t1 = atomicAdd(&d.sched[6], 1u); }
+    tile = tile0 + (int)__shfl_sync(0xffffffffu, t0, 0);
+    next = tile0 + (int)__shfl_sync(0xffffffffu, t1, 0);
+  } else {
+    next = tile + total;
+  }
   // prologue: first tile's rows and scalars
   if (tile < n_tiles) warp_issue_rows(d, s_rows, &bars[0], tile, lane, pol_keep);
   uint4 nh = make_uint4(0, 0, 0, 0);
   int na = 6;
   uint32_t nsp = 0;  // speculation word of the env (DR variant)
-  const bool use_spec = RR && A.spec;
-  const int rr_par = use_spec ? (int)(*(volatile uint32_t *)&d.sched[5] & 1u) : 0;  // stable for the whole launch
   if (tile < n_tiles && tile * kWarpTile + lane < N) {
     nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep); na = (int)A.action[tile * kWarpTile + lane];
     if (use_spec) nsp = d.spec[tile * kWarpTile + lane];
   }
   uint32_t phase = 0;  // bit s = parity to wait for on bars[s]
-  for (int k = 0; tile < n_tiles; tile += total, k++) {
+  for (int k = 0; tile < n_tiles; k++) {
     const int st = k & 1, base = tile * kWarpTile, e = base + lane;
     const int n_tile = min(kWarpTile, N - base);
     const bool valid = lane < n_tile;
@@ -894,8 +938,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     const uint32_t sp = nsp;
     uint32_t *rows = s_rows + st * W * kWarpTile;
     // prefetch the next tile into the other stage (its last readers, the previous tile, are done: __syncwarp)
-    const int next = tile + total;
     __syncwarp();
+    if (dyn && lane == 0) ticket = atomicAdd(&d.sched[6], 1u);  // the tile after `next`: consumed at the end of this iteration
     if (next < n_tiles) {
       warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane, pol_keep);
       if (next * kWarpTile + lane < N) {
@@ -1099,6 +1143,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         pend_n += __popc(qm);
       }
     }
+    tile = next;
+    next = dyn ? tile0 + (int)__shfl_sync(0xffffffffu, ticket, 0) : next + total;
   }
   if (RR && use_spec) flush_pending_jobs(d, rr_par, s_pend, pend_n, lane);
   if (lane == 0) bulk_wait_read0();
@@ -1112,35 +1158,12 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     atomicAdd(&d.prof[cls], dur); atomicAdd(&d.prof[cls + 1], 1ull); atomicMax(&d.prof[cls + 2], dur);
   }
   if (RR && use_spec) {
-    // ---- regeneration phase: the jobs queued by the PREVIOUS launch (list of the other parity; its count is final)
-    // are drained by warps that are past their tiles -- no waiting on this launch's progress.
-    __syncwarp();
+    // last warp out: the list drained at the start of this launch becomes the next launch's append list
     const int q = rr_par ^ 1;
-    const uint32_t n_jobs = *(volatile uint32_t *)&d.sched[q];
-    const uint2 *list = d.rr_list + (size_t)q * 2 * N;
-    uint32_t *scr = reinterpret_cast<uint32_t *>(s_obs);  // the observation tile is free now
-    for (;;) {
-      uint32_t j = 0;
-      if (lane == 0) j = atomicAdd(&d.sched[2 + q], 1u);
-      j = __shfl_sync(0xffffffffu, j, 0);
-      if (j >= n_jobs) break;
-      const long long c0 = d.prof ? clock64() : 0;
-      rr_regen_job(d, __ldcg(list + j), lane, scr);
-      __syncwarp();
-      if (d.prof && lane == 0) {
-        const unsigned long long dt = (unsigned long long)(clock64() - c0);
-        atomicAdd(&d.prof[3], dt); atomicAdd(&d.prof[4], 1ull); atomicMax(&d.prof[5], dt);
-      }
-    }
-    if (d.prof && lane == 0) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      atomicMax(&d.prof[2], t1);               // end of the regeneration phase
-    }
     if (lane == 0) {
       __threadfence();
       if (atomicAdd(&d.sched[4], 1u) == (uint32_t)total - 1u) {  // last warp out: the drained list becomes the next append list
-        d.sched[q] = 0; d.sched[2 + q] = 0; d.sched[4] = 0;
+        d.sched[q] = 0; d.sched[2 + q] = 0; d.sched[4] = 0; d.sched[6] = 0;
         d.sched[5] = (uint32_t)q;
       }
     }
