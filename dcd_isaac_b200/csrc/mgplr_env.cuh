@@ -36,7 +36,7 @@ struct Dev {
   uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx5|gy5|hasgoal1|sx5|sy5|hasstart1|sdir2|pending8  z: elapsed16|eplen16  w: ep_ret bits
   uint32_t *adv;     // [N] adversary_step_count12 | adversary_max_steps12 | n_clutter_sampled1
   int4 *metrics;     // [N] n_clutter_placed, distance_to_goal, passable, shortest_path_length
-  uint32_t *mt;      // [ceil(N/32)][624][32] MT19937 state (numpy RandomState of each env), see mt_at()
+  uint32_t *mt;      // [ceil(N/32)][39][32][16] MT19937 state (numpy RandomState of each env), see mt_at()
   uint32_t *mti;     // [N] index of the next word to generate (incremental twist), 0..623
   uint32_t *limbs;   // [3][N] seed limbs lo, hi, count (re-seed of fixed_environment)
   uint32_t *words;   // [N] MT words consumed since seeding
@@ -51,13 +51,17 @@ struct Dev {
   uint32_t *sched;   // [8] regeneration phase: [0..1] jobs appended to list p, [2..3] next ticket of list p, [4] warps exited,
                      //     [5] parity of the running / next DR launch (device-side so that graph replays stay consistent)
 };
-// MT19937 state layout: tile-major like the wall plane -- the 624 words of 32 consecutive envs form one contiguous
-// 624*128-byte block (word i of env e at mt[((e/32)*624 + i)*32 + e%32]).  32 lanes stepping 32 consecutive envs read
-// 128 contiguous bytes per word index (coalesced), AND all 624 words of one env live in one 78 KB span: a warp that
-// walks ONE env's state (cooperative rebuild, MT advance at a commit, a regeneration job's look-ahead window) stays
-// inside one 2 MB page.  The earlier [624][N] layout put consecutive words of an env N*4 bytes apart -- a different page
-// for every few words, i.e. a TLB miss storm on exactly those paths.
-__host__ __device__ inline size_t mt_at(int e, uint32_t i) { return ((size_t)(e >> 5) * 624 + i) * 32 + (size_t)(e & 31); }
+// MT19937 state layout: tile-major AND chunked -- the 624 words of 32 consecutive envs form one 78 KB block laid out as
+// [39 chunks][32 envs][16 words]: word i of env e at ((e/32*39 + i/16)*32 + e%32)*16 + i%16.  Both access patterns of this
+// code stay sector-efficient: (a) lane-parallel code (32 lanes = 32 consecutive envs) generates 16-33 CONSECUTIVE words
+// per refill, i.e. each lane walks a few 64-byte chunks of its own; (b) warp-per-env code (cooperative rebuild, the
+// look-ahead window of a regeneration job) reads runs of 32-225 consecutive words of ONE env = a handful of 64-byte
+// chunks instead of one 128-byte line per word.  (History: [624][N] put consecutive words of an env N*4 bytes apart;
+// [tile][624][32] fixed the page locality but still cost one line per word on the warp-per-env paths.)
+constexpr int kMtChunk = 16, kMtChunks = 624 / kMtChunk;  // 39 chunks of 16 words
+__host__ __device__ inline size_t mt_at(int e, uint32_t i) {
+  return ((((size_t)(e >> 5) * kMtChunks + (i >> 4)) * 32 + (size_t)(e & 31)) << 4) + (i & 15u);
+}
 constexpr int kMetricsDirty = -2;  // metrics.z of an env whose level came from a candidate record: recomputed by the getter
 constexpr uint32_t kSpecValidMask = 15u << 16;
 constexpr int kSpecEpochShift = 20;

@@ -1718,8 +1718,8 @@ extern "C" int mgplr_peek_rng(mgplr_venv *v, int32_t index, uint32_t *words_host
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   uint32_t mt[624], idx = 0;
-  CK(cudaMemcpy2D(mt, sizeof(uint32_t), v->d.mt + mt_at(index, 0), 32 * sizeof(uint32_t), sizeof(uint32_t), 624,
-                  cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(mt, kMtChunk * sizeof(uint32_t), v->d.mt + mt_at(index, 0), 32 * kMtChunk * sizeof(uint32_t),
+                  kMtChunk * sizeof(uint32_t), kMtChunks, cudaMemcpyDeviceToHost));  // 39 chunks of 16 words
   CK(cudaMemcpy(&idx, v->d.mti + index, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   for (int k = 0; k < count; k++) {
     const uint32_t i = idx, i1 = (i + 1 == 624) ? 0 : i + 1, im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
