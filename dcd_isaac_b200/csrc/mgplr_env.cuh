@@ -953,6 +953,91 @@ __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *s
   }
 }
 
+// ---- lane-parallel regeneration for LONG job lists (a synchronized time-limit storm queues two jobs for nearly every
+// env) ------------------------------------------------------------------------------------------------------------
+// A warp-per-job build costs ~10 us per candidate whatever the list length; 32 candidates built side by side by the 32
+// lanes with the plain lane-serial code cost about as much as ONE of them (k_reset_random builds 131 072 levels in 0.23
+// ms).  The draws come straight from the present MT state, non-destructively: output j of the look-ahead span is a
+// function of present words j, j+1, j+397 for j < 227, so no window has to be stored, and the untempered value IS the new
+// state word the record carries.
+struct FlyRng {
+  const uint32_t *mt;
+  uint32_t *rec_state;  // record slots of the new state words (first kSpecState draws)
+  int e;
+  uint32_t idx;
+  int pos;
+  bool overflow;
+  __device__ __forceinline__ uint32_t next() {
+    if (pos >= kSpecWindow) { overflow = true; return 0u; }
+    uint32_t p = idx + pos, p1 = p + 1, pm = p + 397;
+    if (p >= 624) p -= 624;
+    if (p1 >= 624) p1 -= 624;
+    if (pm >= 624) pm -= 624;
+    if (pm >= 624) pm -= 624;
+    const uint32_t x = __ldcg(mt + mt_at(e, p)), b = __ldcg(mt + mt_at(e, p1)), c = __ldcg(mt + mt_at(e, pm));
+    uint32_t y = (x & 0x80000000u) | (b & 0x7fffffffu);
+    y = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    if (pos < kSpecState) rec_state[pos] = y;
+    pos++;
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+  }
+  __device__ __forceinline__ int randint(int lo, int hi) {
+    const uint32_t rng = (uint32_t)(hi - lo - 1);
+    if (rng == 0) return lo;
+    const uint32_t mask = 0xffffffffu >> __clz(rng);
+    uint32_t v;
+    do { v = next() & mask; } while (v > rng && !overflow);
+    return lo + (int)(v > rng ? 0u : v);
+  }
+  __device__ __forceinline__ bool ok() const { return !overflow; }
+};
+
+// one candidate per LANE; `col` = this lane's column of a [W][32] shared-memory scratch (the level under construction)
+__device__ __noinline__ void rr_regen_job_lane(Dev d, uint2 jb, uint32_t *col) {
+  const Cfg &c = d.c;
+  const uint32_t job = jb.x;
+  const int e = (int)(job >> 8), k = (int)((job >> 7) & 1u);
+  const uint32_t ep = job & 127u;
+  const int W = c.W;
+  if (spec_epoch(__ldcg(d.spec + e)) != ep) return;  // the level is gone already
+  const Env s = unpack(__ldcg(d.hot + e));
+  uint32_t *rec = cand_record(d, e, ep, k);
+  FlyRng rng{d.mt, rec + W + 8, e, jb.y % 624u, 0, false};
+  const Rows L{col, 32};
+  int x = 0, y = 0;
+  uint32_t err = 0;
+  if (k == 1) {  // the goal respawn's draws (multigrid.py:821-838) against the current level, agent off the grid
+    Env t{};
+    t.gx = s.gx; t.gy = s.gy; t.has_agent = 0;
+    place_random(env_rows(d, e), t, rng, W, -1, x, y);
+  }
+  Env n{};
+  n.gx = n.gy = n.sx = n.sy = kNone;
+  gen_grid(L, W);
+  if (!place_random(L, n, rng, W, 100, x, y)) err |= kErrRetries;
+  n.gx = x; n.gy = y;
+  n.sdir = rng.randint(0, 4);
+  place_random(L, n, rng, W, -1, x, y);
+  n.sx = x; n.sy = y; n.has_agent = 1; n.ax = x; n.ay = y;
+  const int n_walls = c.n_clutter / 2;
+  for (int i = 0; i < n_walls; i++) {
+    if (!place_random(L, n, rng, W, 100, x, y)) { err |= kErrRetries; break; }
+    L.set(y, L.get(y) | (1u << x));
+  }
+  if (!rng.ok() || rng.pos > kSpecState) return;
+  for (int r = 0; r < W; r++) rec[r] = L.get(r);
+  rec[W] = ((uint32_t)n.gx & 31u) | (((uint32_t)n.gy & 31u) << 5) | (1u << 10) | (((uint32_t)n.sx & 31u) << 11) |
+           (((uint32_t)n.sy & 31u) << 16) | (1u << 21) | ((uint32_t)n.sdir << 22);
+  rec[W + 5] = (uint32_t)rng.pos;
+  rec[W + 6] = err;
+  __threadfence();
+  atomicOr(d.spec + e, spec_valid_bit(ep, k));
+}
+
 // ---------------------------------------------------------------------------------------------
 // Egocentric view (multigrid.py:977-1055 gen_obs_grid/gen_agent_obs, 320-338 slice, 300-318
 // rotate_left, 749-782 get_view_exts; gym_minigrid Grid.process_vis / encode).

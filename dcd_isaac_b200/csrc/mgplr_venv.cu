@@ -878,6 +878,17 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     const uint32_t n_jobs = *(volatile uint32_t *)&d.sched[q];
     const uint2 *list = d.rr_list + (size_t)q * 2 * N;
     uint32_t *scr = reinterpret_cast<uint32_t *>(s_obs);  // the observation tile is not in use yet
+    if (n_jobs >= 8u * (uint32_t)total) {
+      // a storm's worth of jobs: 32 candidates per warp side by side (rr_regen_job_lane), tickets in units of 32
+      for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(&d.sched[2 + q], 32u);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= n_jobs) break;
+        if (j + lane < n_jobs) rr_regen_job_lane(d, __ldcg(list + j + lane), scr + lane);
+        __syncwarp();
+      }
+    } else
     for (;;) {
       uint32_t j = 0;
       if (lane == 0) j = atomicAdd(&d.sched[2 + q], 1u);
