@@ -1549,7 +1549,9 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   int grid = v->sm_count * per_sm;
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
   // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing job phase
-  A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample && (v->d.N >= 16384 || v->rr_spec > 1);
+  // ... and a level with many walls does not fit the 224-word look-ahead window (2-3 words per try): no point in queueing jobs
+  A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample && (v->d.N >= 16384 || v->rr_spec > 1) &&
+           v->d.c.n_clutter / 2 <= 48;
   if (A.spec) { if (int rc = rr_spec_alloc(v)) return rc; }
   const int need = (n_tiles - tile0 + wpc - 1) / wpc;
   if (grid > need) grid = need;
