@@ -44,7 +44,7 @@ struct Dev {
   // speculative next-level generation of the DR auto-reset (step_env(reset_random=True)), see the "speculation" block
   uint32_t *spec;    // [N] bits 16+2p / 17+2p: candidate 0 (episode ended without a goal) / 1 (ended at the goal) built for a
                      //     level epoch of parity p is valid; bits 20-26: level epoch (bumped by every DR reset)
-  uint32_t *cand;    // [N][2 epochs][2][W + 8 + 128] candidate records: wall rows, packed goal/start, -, words consumed, error
+  uint32_t *cand;    // [N][2 epochs][2][W + 8 + 192] candidate records: wall rows, packed goal/start, -, words consumed, error
                      //     bits, and the NEW MT state words of the consumed span (so that a commit copies, never recomputes)
   uint2 *rr_list;    // [2][2N] regeneration jobs {env << 8 | candidate << 7 | epoch, MT cursor}, one list per launch parity
   unsigned long long *prof;  // debug counters (MGPLR_RR_PROF), else NULL
@@ -72,7 +72,7 @@ __host__ __device__ inline uint32_t spec_valid_bit(uint32_t ep, int k) { return 
 constexpr uint32_t kSpecEpochMask = 127u << kSpecEpochShift;
 __host__ __device__ inline uint32_t spec_epoch(uint32_t sp) { return (sp & kSpecEpochMask) >> kSpecEpochShift; }
 constexpr int kSpecWindow = 224;   // MT words one regeneration job can look ahead (< 227: all computable from the present state)
-constexpr int kSpecState = 128;     // new MT state words a candidate record carries (a record that consumed more is not published)
+constexpr int kSpecState = 192;     // new MT state words a candidate record carries (a record that consumed more is not published)
 __host__ __device__ inline int cand_words(int W) { return W + 8 + kSpecState; }
 
 // `pending` = goal respawns (multigrid.py:821-838) whose env-RNG draws have not been made yet.  A respawn draw

@@ -1525,7 +1525,7 @@ static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_rando
   if (out) A.o = *out;
   return launch_step_args(v, A, reset_random, st);
 }
-// candidate records + job lists of the DR speculation (2.4 KB per env at 15x15): only DR users pay for them
+// candidate records + job lists of the DR speculation (3.5 KB per env at 15x15): only DR users pay for them
 static int rr_spec_alloc(mgplr_venv *v) {
   if (v->d.cand) return 0;
   const size_t N = (size_t)v->d.N;
@@ -1551,7 +1551,7 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing job phase
   // ... and a level with many walls does not fit the 224-word look-ahead window (2-3 words per try): no point in queueing jobs
   A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample && (v->d.N >= 16384 || v->rr_spec > 1) &&
-           v->d.c.n_clutter / 2 <= 48;
+           v->d.c.n_clutter / 2 <= 56;
   if (A.spec) { if (int rc = rr_spec_alloc(v)) return rc; }
   const int need = (n_tiles - tile0 + wpc - 1) / wpc;
   if (grid > need) grid = need;
