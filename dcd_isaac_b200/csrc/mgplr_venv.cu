@@ -785,15 +785,17 @@ __device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, 
 }
 
 // ---- hot kernel: persistent, warp-pipelined step_env -------------------------------------------------------
-// Each WARP owns tiles of 32 consecutive envs (tile = global_warp + k * total_warps) and runs a software
-// pipeline with no CTA-level synchronisation:
-//   * the wall rows of tile k+1 are prefetched by W bulk asynchronous copies (TMA, 128 B each) into the other
+// Each WARP owns tiles of 32 consecutive envs (tile = global_warp + k * total_warps; handed out by tickets in the
+// speculative DR variant) and runs a software pipeline with no CTA-level synchronisation:
+//   * the wall rows of tile k+1 are prefetched by ONE bulk asynchronous copy (TMA, W*128 B) into the other
 //     half of a double buffer while tile k computes; completion is signalled on a per-warp mbarrier;
 //   * the hot record / action of tile k+1 are prefetched into registers;
 //   * the 32x75 float32 observations of tile k leave shared memory as one 9600-byte bulk asynchronous store
 //     that drains while tile k+1 steps and renders; the single obs buffer is only re-acquired
 //     (cp.async.bulk.wait_group.read) right before tile k+1 emits.
-// per warp: obs tile | two row buffers | two mbarriers | (DR variant) batched-RNG scratch [32][32]
+// The DR variant (RR) additionally resets finished envs -- by copying a pre-built candidate level, or by rebuilding in
+// the kernel -- and runs the regeneration jobs queued by the previous launch.
+// per warp: obs tile | two row buffers | two mbarriers | (DR variant) batched-RNG scratch [32][32] | job queue
 constexpr int kPendCap = 96;  // DR variant: regeneration jobs a warp collects before it appends them to the global list
 __host__ __device__ inline size_t warp_smem_bytes(int W, bool rr) {
   return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + (rr ? 32 * kWarpTile * 4 + kPendCap * 8 : 0) + 127) &
