@@ -327,14 +327,17 @@ def run_ours(a):
         h_done = torch.zeros(N * 16, dtype=torch.uint8).pin_memory()
         h_nd = torch.zeros(1, dtype=torch.int32).pin_memory()
         hp = [ptr(h_act[t]) for t in range(T)]
+        nd_np = h_nd.numpy()  # (reading the count through numpy: no tensor indexing in the per-step loop)
+        p_flg, p_done, p_nd = ptr(h_flg), ptr(h_done), ptr(h_nd)
+        step_host = L.mgplr_step_env_host
+        out_refs = [C.byref(o) for o in outs]
         done_seen = [0]
 
         def rollout_host():
             check(L.mgplr_reset_agent(venv.h, C.byref(venv._out({'image': obs_img[0], 'direction': obs_dir[0]})), stream))
             for t in range(T):
-                check(L.mgplr_step_env_host(venv.h, hp[t], rr, 3 if t == T - 1 else 0, C.byref(outs[t]), ptr(h_flg), ptr(h_done),
-                                            N, ptr(h_nd), stream))
-                done_seen[0] += int(h_nd[0])
+                check(step_host(venv.h, hp[t], rr, 3 if t == T - 1 else 0, out_refs[t], p_flg, p_done, N, p_nd, stream))
+                done_seen[0] += int(nd_np[0])
             check(L.mgplr_gae(ptr(rewards), ptr(values), ptr(masks), ptr(returns), T, N, 0.995, 0.95, stream))
             check(L.mgplr_plr_episode_scores(ptr(masks), ptr(cliff), ptr(returns), ptr(values), ptr(rewards), ptr(level_seeds),
                                              T, N, 0, ptr(episodes), max_eps, ptr(n_eps), stream))
