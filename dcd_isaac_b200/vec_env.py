@@ -275,26 +275,43 @@ class CudaAdversarialVecEnv(object):
         self._assert_not_closed()
         N = self.num_envs
         num_tiles = (self.W - 2) ** 2
-        if edits is None:
-            locs_l, ops_l = [], []
-            for _ in range(N):
-                edit_locs = list(set(np.random.randint(0, num_tiles, num_edits)))
-                action_idx = np.random.randint(0, len(self.editor_actions), len(edit_locs))
-                locs_l.append(edit_locs)
-                ops_l.append(action_idx)
+        n_ops = len(self.editor_actions)
+        if edits is None and N > 256:
+            # In the reference every env subprocess makes these draws from its OWN unseeded global numpy stream, so only the
+            # per-env semantics are defined (DESIGN.md deviation 2): large batches draw all envs' numbers in two calls and
+            # keep the per-env rule -- distinct locations in set-iteration order, one op per kept location.
+            raw = np.random.randint(0, num_tiles, (N, num_edits)).tolist()
+            ops_raw = np.random.randint(0, n_ops, (N, num_edits))
+            mx = max(1, num_edits)
+            locs = np.zeros((N, mx), np.int32)
+            n_ed = np.zeros(N, np.int32)
+            for i, row in enumerate(raw):
+                u = list(set(row))
+                n_ed[i] = len(u)
+                locs[i, :len(u)] = u
+            ops = np.ascontiguousarray(ops_raw[:, :mx], dtype=np.int32)
             choice = None
         else:
-            locs_l, ops_l, n_l, choice = edits
-            locs_l = [list(l[:n]) for l, n in zip(locs_l, n_l)]
-            ops_l = [list(o[:n]) for o, n in zip(ops_l, n_l)]
-        mx = max(1, max(len(l) for l in locs_l))
-        locs = np.zeros((N, mx), np.int32)
-        ops = np.zeros((N, mx), np.int32)
-        n_ed = np.zeros(N, np.int32)
-        for i in range(N):
-            n_ed[i] = len(locs_l[i])
-            locs[i, :n_ed[i]] = locs_l[i]
-            ops[i, :n_ed[i]] = ops_l[i]
+            if edits is None:
+                locs_l, ops_l = [], []
+                for _ in range(N):
+                    edit_locs = list(set(np.random.randint(0, num_tiles, num_edits)))
+                    action_idx = np.random.randint(0, n_ops, len(edit_locs))
+                    locs_l.append(edit_locs)
+                    ops_l.append(action_idx)
+                choice = None
+            else:
+                locs_l, ops_l, n_l, choice = edits
+                locs_l = [list(l[:n]) for l, n in zip(locs_l, n_l)]
+                ops_l = [list(o[:n]) for o, n in zip(ops_l, n_l)]
+            mx = max(1, max(len(l) for l in locs_l))
+            locs = np.zeros((N, mx), np.int32)
+            ops = np.zeros((N, mx), np.int32)
+            n_ed = np.zeros(N, np.int32)
+            for i in range(N):
+                n_ed[i] = len(locs_l[i])
+                locs[i, :n_ed[i]] = locs_l[i]
+                ops[i, :n_ed[i]] = ops_l[i]
         d_locs, d_ops, d_n = (torch.from_numpy(a).to(self.device) for a in (locs, ops, n_ed))
         need = torch.zeros(N, 2, dtype=torch.uint8, device=self.device)
         nfree = torch.zeros(N, 2, dtype=torch.int32, device=self.device)
@@ -303,12 +320,10 @@ class CudaAdversarialVecEnv(object):
         if choice is None:
             need_h, nfree_h = need.cpu().numpy(), nfree.cpu().numpy()
             choice = np.zeros((N, 2), np.int32)
-            for i in range(N):  # np.random.choice(free_idx) (adversarial.py:308-315), goal first then agent
-                for k in range(2):
-                    if need_h[i, k]:
-                        if nfree_h[i, k] <= 0:
-                            raise ValueError("'a' cannot be empty unless no samples are taken")
-                        choice[i, k] = np.random.choice(int(nfree_h[i, k]))
+            for i, k in zip(*np.nonzero(need_h)):  # np.random.choice(free_idx) (adversarial.py:308-315), env order, goal first then agent
+                if nfree_h[i, k] <= 0:
+                    raise ValueError("'a' cannot be empty unless no samples are taken")
+                choice[i, k] = np.random.choice(int(nfree_h[i, k]))
         d_choice = torch.from_numpy(np.ascontiguousarray(choice, dtype=np.int32)).to(self.device)
         obs = self._new_obs()
         o = self._out(obs)
