@@ -95,6 +95,10 @@ class CudaAdversarialVecEnv(object):
         self._h_flags = torch.zeros(N, dtype=torch.uint8).pin_memory()
         self._h_done = torch.zeros(N * 16, dtype=torch.uint8).pin_memory()  # mgplr_done_record [N]
         self._h_ndone = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._h_done_np = self._h_done.numpy()
+        self._done_dtype = np.dtype(_lib.DONE_DTYPE)
+        self._step_out = None   # StepOut with the persistent destinations of step_env (built on first use)
+        self._tr = None
         if seed is not None:
             self.set_seed([seed] * N)
 
@@ -338,14 +342,24 @@ class CudaAdversarialVecEnv(object):
         (vec_env.py:113-118; folded wrappers: time_limit.py:24-33, vec_monitor.py:60-85, obs_wrappers.py:168-181)."""
         self._assert_not_closed()
         N = self.num_envs
-        obs = self._new_obs()
-        tr = self._new_obs()
-        rew = torch.empty(N, 1, dtype=torch.float32, device=self.device)
-        o = self._out(obs, reward=rew, flags=self._flags, ep_return=self._ep_r, ep_length=self._ep_l,
-                      trunc_image=tr['image'], trunc_direction=tr['direction'])
-        if self.full_obs:
-            tr['full_obs'] = torch.empty(N, 3, self.W, self.W, dtype=torch.float32, device=self.device)
-            o.trunc_full_obs = ptr(tr['full_obs'])
+        # one allocation for the step's outputs (image | direction | reward are contiguous slices of it); the truncated-
+        # observation buffers and the StepOut with the persistent pointers live across calls
+        o_dir = (N * 75 + 63) & ~63        # slice starts kept 256-byte aligned (the kernel's bulk / vector stores)
+        o_rew = o_dir + ((N + 63) & ~63)
+        flat = torch.empty(o_rew + N, dtype=torch.float32, device=self.device)
+        obs = {'image': flat[:N * 75].view(N, 3, 5, 5), 'direction': flat[o_dir:o_dir + N].view(N, 1)}
+        rew = flat[o_rew:].view(N, 1)
+        if self._step_out is None:
+            self._tr = self._new_obs()
+            if self.full_obs:
+                self._tr['full_obs'] = torch.empty(N, 3, self.W, self.W, dtype=torch.float32, device=self.device)
+            self._step_out = self._out(None, flags=self._flags, ep_return=self._ep_r, ep_length=self._ep_l,
+                                       trunc_image=self._tr['image'], trunc_direction=self._tr['direction'])
+            if self.full_obs:
+                self._step_out.trunc_full_obs = ptr(self._tr['full_obs'])
+        tr, o = self._tr, self._step_out
+        base = flat.data_ptr()
+        o.image, o.direction, o.reward = base, base + o_dir * 4, base + o_rew * 4
         a = torch.as_tensor(action)
         if reset_random and self.resample_n_clutter:
             raise NotImplementedError('step_env(reset_random=True) with resample_n_clutter: use step_env_device')
@@ -363,11 +377,13 @@ class CudaAdversarialVecEnv(object):
                                              self._stream()), 'mgplr_step_env_host')
             flags = self._h_flags.numpy().copy()
             nd = int(self._h_ndone[0])
-            rec = self._h_done.numpy()[:nd * 16].view(np.dtype(_lib.DONE_DTYPE))
-            ep_r = np.zeros(N, np.float32)
-            ep_l = np.zeros(N, np.int32)
-            ep_r[rec['env']] = rec['ep_return']
-            ep_l[rec['env']] = rec['ep_length']
+            ep_r = ep_l = None
+            if nd:
+                rec = self._h_done_np[:nd * 16].view(self._done_dtype)
+                ep_r = np.zeros(N, np.float32)
+                ep_l = np.zeros(N, np.int32)
+                ep_r[rec['env']] = rec['ep_return']
+                ep_l[rec['env']] = rec['ep_length']
         done = (flags & F_DONE) != 0
         infos = [{} for _ in range(N)]
         if flags.any():
@@ -377,6 +393,7 @@ class CudaAdversarialVecEnv(object):
                 if flags[i] & F_TRUNC_KEY:
                     info['truncated'] = bool(flags[i] & F_TRUNC_VAL)
                     info['truncated_obs'] = {k: v[i] for k, v in tr.items()}
+                    self._step_out = None   # the infos now own these buffers: take fresh ones next step
                 if flags[i] & F_DONE:
                     info['episode'] = {'r': ep_r[i], 'l': ep_l[i], 't': t_now}
             if (flags & F_DONE).any():
