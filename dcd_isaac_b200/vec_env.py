@@ -367,9 +367,11 @@ class CudaAdversarialVecEnv(object):
             a = a.reshape(-1).to(torch.int64).contiguous()
             check(self.L.mgplr_step_env(self.h, ptr(a), int(bool(reset_random)), None, 0, C.byref(o), self._stream()),
                   'mgplr_step_env')
-            flags = self._flags.cpu().numpy().copy()
-            ep_r = self._ep_r.cpu().numpy().copy()
-            ep_l = self._ep_l.cpu().numpy().copy()
+            flags = self._flags.cpu().numpy()
+            ep_r = ep_l = None
+            if (flags & F_DONE).any():      # episode statistics cross only on the steps that end an episode
+                ep_r = self._ep_r.cpu().numpy()
+                ep_l = self._ep_l.cpu().numpy()
         else:
             self._h_action.copy_(a.reshape(-1))
             check(self.L.mgplr_step_env_host(self.h, ptr(self._h_action), int(bool(reset_random)), 0, C.byref(o),

@@ -7,3 +7,4 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/check_bench_r
 python bench.py --steps 5 > gpurun_out/check_bench_main.json 2>> gpurun_out/check_bench.err
 python profiles/summarize_bench.py gpurun_out/check_bench_reference.json gpurun_out/check_bench_main.json
 tail -3 gpurun_out/check_bench.err
+timeout 120 python tools/bench_dropin.py > gpurun_out/check_dropin.json 2>> gpurun_out/check_bench.err; grep -c step_env gpurun_out/check_dropin.json
