@@ -23,7 +23,7 @@ from dcd_isaac_b200.storage import gae_returns
 from dcd_isaac_b200.vec_env import CudaAdversarialVecEnv
 
 
-def timeit(fn, reps=5, warm=3):
+def timeit(fn, reps=int(os.environ.get('LEVELOPS_REPS', 5)), warm=int(os.environ.get('LEVELOPS_WARM', 3))):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
