@@ -285,6 +285,165 @@ __global__ void k_episode_scores(const float *__restrict__ masks, const float *_
   }
 }
 
+// ---- time-split variant: kSeg threads per actor.  One thread per actor leaves a B200 under-filled below ~300 000 actors (131 072
+// actors = 43 % of the thread slots) and the loop is latency-bound, so the rollout is cut into kSeg time segments: CTA = 32 actors x
+// kSeg segments (warp = segment, lane = actor: loads stay coalesced), every thread scores the episodes that END inside its segment.
+// The first of them may have begun in an earlier segment: its accumulators are completed after a CTA barrier from the "tail" parts
+// (steps after a segment's last done) the earlier segments left in shared memory.  Record order is unchanged because the episode
+// counts are taken per (actor, segment) and scanned in that order.
+constexpr int kSeg = 4;
+
+struct ScorePart {  // accumulators of a run of consecutive steps of one actor
+  double sum, vsum;
+  float mx, rsum, vmin;
+  int start;        // first step of the run
+};
+
+__device__ __forceinline__ void part_reset(ScorePart &p, int start) {
+  p.sum = 0.0; p.vsum = 0.0; p.mx = -INFINITY; p.rsum = 0.f; p.vmin = INFINITY; p.start = start;
+}
+
+// `a` precedes `b` in time
+__device__ __forceinline__ void part_prepend(ScorePart &b, const ScorePart &a) {
+  b.sum = a.sum + b.sum; b.vsum = a.vsum + b.vsum; b.mx = fmaxf(a.mx, b.mx); b.rsum = a.rsum + b.rsum; b.vmin = fminf(a.vmin, b.vmin);
+  b.start = a.start;
+}
+
+template <int strategy>
+__device__ __forceinline__ void part_emit(const ScorePart &p, int e, int t_end, float r_last, float v_last, int cliffhanger,
+                                          const int32_t *__restrict__ seeds, int N, mgplr_episode *__restrict__ out) {
+  mgplr_episode ep;
+  ep.actor = e; ep.t_start = p.start; ep.t_end = t_end; ep.seed = seeds ? seeds[(size_t)p.start * N + e] : -1;
+  const int n = t_end - p.start;
+  ep.mean_score = (float)(p.sum / (double)n); ep.max_score = p.mx; ep.reward_sum = p.rsum;
+  if (strategy == MGPLR_SCORE_MIN_MARGIN) { ep.mean_score = (float)(1.0 + p.sum / (double)n); ep.max_score = 1.0f + p.mx; }
+  if (strategy == MGPLR_SCORE_ONE_STEP_TD) {
+    if (n > 1) ep.mean_score = (float)(p.sum / (double)(n - 1));
+    else { ep.mean_score = __fsub_rn(r_last, v_last); ep.max_score = ep.mean_score; }
+  }
+  ep.value_sum = (float)p.vsum; ep.value_min = p.vmin; ep.cliffhanger = cliffhanger;
+  *out = ep;
+}
+
+// counts[e * kSeg + s] = episodes of actor e that end inside segment s (+ the not-done tail in the last segment)
+__global__ void __launch_bounds__(32 * kSeg) k_count_episodes_split(const float *__restrict__ masks, int T, int N, int L,
+                                                                    int32_t *__restrict__ counts) {
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31), s = threadIdx.x >> 5;
+  if (e >= N) return;
+  const int t0 = s * L, t1 = min(T, t0 + L);
+  int c = 0;
+#pragma unroll 8
+  for (int t = t0; t < t1; t++) c += !(masks[(size_t)(t + 1) * N + e] > 0.f);
+  if (s == kSeg - 1) c += (masks[(size_t)T * N + e] > 0.f);
+  counts[(size_t)e * kSeg + s] = c;
+}
+
+template <int strategy>
+__global__ void __launch_bounds__(32 * kSeg, 6) k_episode_scores_split(
+    const float *__restrict__ masks, const float *__restrict__ cliff, const float *__restrict__ returns,
+    const float *__restrict__ values, const float *__restrict__ rewards, const int32_t *__restrict__ seeds,
+    const float *__restrict__ logits, int A, float gamma, int T, int N, int L, const int32_t *__restrict__ offsets,
+    const int32_t *__restrict__ block_off, mgplr_episode *__restrict__ out, int max_out) {
+  __shared__ ScorePart s_tail[kSeg][32], s_head[kSeg][32];  // head: the run up to the segment's first done (kept out of registers)
+  __shared__ int s_head_end[kSeg][32];
+  __shared__ float s_head_r[kSeg][32], s_head_v[kSeg][32];
+  __shared__ uint8_t s_closed[kSeg][32];  // the segment saw a done (its tail does not reach further back)
+  const int lane = threadIdx.x & 31, s = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const bool valid = e < N;
+  const int t0 = s * L, t1 = min(T, t0 + L);
+  int k = 0;
+  if (valid) {
+    const size_t ci = (size_t)e * kSeg + s;
+    k = offsets[ci] + block_off[ci >> 10];
+  }
+  ScorePart acc;
+  part_reset(acc, t0);
+  bool has_head = false;
+  float r_prev = 0.f, v_prev = 0.f;
+  bool have_prev = false;  // ONE_STEP_TD: step t-1 belongs to the same episode
+  if (strategy == MGPLR_SCORE_ONE_STEP_TD && valid && s > 0 && t0 < T && masks[(size_t)t0 * N + e] > 0.f) {
+    have_prev = true; r_prev = rewards[(size_t)(t0 - 1) * N + e]; v_prev = values[(size_t)(t0 - 1) * N + e];
+  }
+  constexpr int kB = 8;
+  if (valid)
+    for (int tb = t0; tb < t1; tb += kB) {
+      float retb[kB], vb[kB], rb[kB], mb[kB];
+#pragma unroll
+      for (int u = 0; u < kB; u++) {
+        const int t = tb + u;
+        const bool in = t < t1;
+        retb[u] = (in && returns) ? returns[(size_t)t * N + e] : 0.f;
+        vb[u] = in ? values[(size_t)t * N + e] : 0.f;
+        rb[u] = in ? rewards[(size_t)t * N + e] : 0.f;
+        mb[u] = in ? masks[(size_t)(t + 1) * N + e] : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kB; u++) {
+        const int t = tb + u;
+        if (t >= t1) break;
+        const float v = vb[u], r = rb[u];
+        float a = retb[u] - v;
+        if (strategy == MGPLR_SCORE_POSITIVE_VALUE_LOSS) a = fmaxf(a, 0.f);
+        else if (strategy == MGPLR_SCORE_VALUE_L1) a = fabsf(a);
+        else if (strategy == MGPLR_SCORE_LEAST_CONFIDENCE) a = logit_score(logits + ((size_t)t * N + e) * A, A, strategy);
+        else if (strategy == MGPLR_SCORE_MIN_MARGIN) a = -logit_score(logits + ((size_t)t * N + e) * A, A, strategy);
+        if (strategy == MGPLR_SCORE_ONE_STEP_TD) {
+          if (have_prev) {
+            a = fabsf(__fsub_rn(__fadd_rn(r_prev, __fmul_rn(gamma, v)), v_prev));
+            acc.sum += (double)a; acc.mx = fmaxf(acc.mx, a);
+          }
+          r_prev = r; v_prev = v; have_prev = true;
+        } else {
+          acc.sum += (double)a; acc.mx = fmaxf(acc.mx, a);
+        }
+        acc.rsum += r;
+        acc.vsum += (double)v; acc.vmin = fminf(acc.vmin, v);
+        if (!(mb[u] > 0.f)) {  // done at t+1 closes the running episode
+          const int t_end = t + 1;
+          if (!has_head) {     // the first one may have begun before this segment: finished after the barrier
+            has_head = true;
+            s_head[s][lane] = acc; s_head_end[s][lane] = t_end; s_head_r[s][lane] = r_prev; s_head_v[s][lane] = v_prev;
+          } else if (k < max_out) {
+            part_emit<strategy>(acc, e, t_end, r_prev, v_prev, cliff ? !(cliff[(size_t)t_end * N + e] > 0.f) : 0, seeds, N, out + k);
+          }
+          k++;
+          part_reset(acc, t_end);
+          have_prev = false;
+        }
+      }
+    }
+  s_tail[s][lane] = acc;
+  s_closed[s][lane] = has_head;
+  __syncthreads();
+  if (!valid) return;
+  if (has_head) {
+    ScorePart head = s_head[s][lane];
+    const int head_end = s_head_end[s][lane];
+    const size_t ci = (size_t)e * kSeg + s;
+    const int head_k = offsets[ci] + block_off[ci >> 10];  // the segment's first record
+    for (int j = s - 1; j >= 0; j--) {
+      part_prepend(head, s_tail[j][lane]);
+      if (s_closed[j][lane]) break;
+    }
+    if (head_k < max_out)
+      part_emit<strategy>(head, e, head_end, s_head_r[s][lane], s_head_v[s][lane], cliff ? !(cliff[(size_t)head_end * N + e] > 0.f) : 0, seeds, N,
+                          out + head_k);
+  }
+  if (s == kSeg - 1) {  // not-done tail: a partial record (cliffhanger field = 2)
+    if (!has_head)
+      for (int j = s - 1; j >= 0; j--) {
+        part_prepend(acc, s_tail[j][lane]);
+        if (s_closed[j][lane]) break;
+      }
+    if (acc.start < T && k < max_out) {
+      // r_last / v_last of a one-step TD tail: the last step of the rollout
+      const float r_l = rewards[(size_t)(T - 1) * N + e], v_l = values[(size_t)(T - 1) * N + e];
+      part_emit<strategy>(acc, e, T, r_l, v_l, 2, seeds, N, out + k);
+    }
+  }
+}
+
 // scan scratch of the episode-score launcher: one grow-only buffer PER DEVICE (a process may drive several GPUs); growing
 // synchronises that device first so that no in-flight launch still uses the old buffer
 constexpr int kMaxDevices = 64;
@@ -311,8 +470,14 @@ extern "C" int mgplr_plr_episode_scores_ex(const float *masks, const float *clif
   if (strategy <= MGPLR_SCORE_VALUE_L1 && !returns) return pfail(MGPLR_E_BADARG, "returns required for this strategy");
   int dev = 0;
   PCK(cudaGetDevice(&dev));
-  const int n_blocks = (N + 1023) / 1024;
-  const size_t need = 2 * (size_t)N + (size_t)n_blocks;
+  // one thread per actor fills the machine only for large batches: below that, kSeg time segments per actor (knob MGPLR_SCORE_SPLIT:
+  // unset = by size, 0 = never, 1 = always).  Measured (T = 256, whole pass, us): 32 actors 87 -> 39, 4 096 100 -> 44,
+  // 32 768 174 -> 98, 131 072 235 -> 236, 262 144 418 -> 439, 524 288 791 -> 824 (80 registers against 64).
+  static const int split_knob = [] { const char *s = getenv("MGPLR_SCORE_SPLIT"); return s ? atoi(s) : -1; }();
+  const bool split = T >= 4 * kSeg && (split_knob > 0 || (split_knob < 0 && N <= 65536));
+  const size_t n_counts = split ? (size_t)N * kSeg : (size_t)N;
+  const int n_blocks = (int)((n_counts + 1023) / 1024);
+  const size_t need = 2 * n_counts + (size_t)n_blocks;
   if (dev < 0 || dev >= kMaxDevices) return pfail(MGPLR_E_UNSUPPORTED, "device index out of range");
   if (g_scratch_n[dev] < need) {
     if (g_scratch[dev]) { PCK(cudaDeviceSynchronize()); cudaFree(g_scratch[dev]); }
@@ -321,14 +486,21 @@ extern "C" int mgplr_plr_episode_scores_ex(const float *masks, const float *clif
     g_scratch_n[dev] = need;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  int32_t *counts = g_scratch[dev], *offsets = counts + N, *block_off = counts + 2 * (size_t)N;
-  k_count_episodes<<<(N + 127) / 128, 128, 0, st>>>(masks, T, N, counts);
-  k_scan_blocks<<<n_blocks, 1024, 0, st>>>(counts, N, offsets, block_off);
+  int32_t *counts = g_scratch[dev], *offsets = counts + n_counts, *block_off = counts + 2 * n_counts;
+  const int L = (T + kSeg - 1) / kSeg;
+  if (split) k_count_episodes_split<<<(N + 31) / 32, 32 * kSeg, 0, st>>>(masks, T, N, L, counts);
+  else k_count_episodes<<<(N + 127) / 128, 128, 0, st>>>(masks, T, N, counts);
+  k_scan_blocks<<<n_blocks, 1024, 0, st>>>(counts, (int)n_counts, offsets, block_off);
   k_scan_tops<<<1, 1024, 0, st>>>(block_off, n_blocks, n_episodes);
 #define SCORES(S)                                                                                                          \
-  k_episode_scores<S><<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, (S <= MGPLR_SCORE_VALUE_L1) ? returns : nullptr, \
-                                                       value_preds, rewards, level_seeds, action_log_dist, num_actions, (float)gamma, \
-                                                       T, N, offsets, block_off, episodes, max_episodes)
+  if (split)                                                                                                               \
+    k_episode_scores_split<S><<<(N + 31) / 32, 32 * kSeg, 0, st>>>(                                                        \
+        masks, cliffhanger_masks, (S <= MGPLR_SCORE_VALUE_L1) ? returns : nullptr, value_preds, rewards, level_seeds,      \
+        action_log_dist, num_actions, (float)gamma, T, N, L, offsets, block_off, episodes, max_episodes);                  \
+  else                                                                                                                     \
+    k_episode_scores<S><<<(N + 127) / 128, 128, 0, st>>>(masks, cliffhanger_masks, (S <= MGPLR_SCORE_VALUE_L1) ? returns : nullptr, \
+                                                         value_preds, rewards, level_seeds, action_log_dist, num_actions, (float)gamma, \
+                                                         T, N, offsets, block_off, episodes, max_episodes)
   switch (strategy) {
     case MGPLR_SCORE_POSITIVE_VALUE_LOSS: SCORES(MGPLR_SCORE_POSITIVE_VALUE_LOSS); break;
     case MGPLR_SCORE_SIGNED_VALUE_LOSS: SCORES(MGPLR_SCORE_SIGNED_VALUE_LOSS); break;

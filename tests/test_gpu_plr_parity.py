@@ -86,6 +86,53 @@ def test_episode_scores_vs_oracle(strategy):
     assert np.allclose(got['value_min'], [w['value_min'] for w in want], rtol=0, atol=0)
 
 
+@pytest.mark.parametrize('knob', ['0', '1'])
+def test_episode_scores_both_kernels(knob):
+    """The score pass has two kernels (one thread per actor; four time segments per actor, chosen by batch size; the knob
+    MGPLR_SCORE_SPLIT is read once per process): run the oracle comparison and a recorded sampler session with each forced."""
+    import subprocess
+    import sys
+    if os.environ.get('MGPLR_SCORE_SPLIT_CHILD'):
+        pytest.skip('child run')
+    env = dict(os.environ, MGPLR_SCORE_SPLIT=knob, MGPLR_SCORE_SPLIT_CHILD='1')
+    out = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-x', '-q', '-m', 'gpu', '-k',
+                          'episode_scores_vs_oracle or partial_tails'], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_episode_scores_partial_tails():
+    """Not-done tails (masks[T] != 0) and episodes spanning the time segments: the records of the kernel equal a plain
+    sequential walk over each actor (t_start / t_end / seed exact, sums to 1e-5)."""
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    rs = np.random.RandomState(11)
+    for T, N, p_done in ((256, 300, 0.01), (64, 130, 0.2), (17, 70, 0.3), (16, 33, 0.0)):
+        rec = dict(rewards=rs.rand(T, N).astype(np.float32), value_preds=rs.randn(T + 1, N).astype(np.float32),
+                   returns=rs.randn(T + 1, N).astype(np.float32), level_seeds=rs.randint(1, 100, size=(T, N)).astype(np.int32))
+        masks = (rs.rand(T + 1, N) > p_done).astype(np.float32)
+        masks[-1, ::3] = 0
+        rec['masks'] = masks
+        rec['cliffhanger_masks'] = np.ones_like(masks)
+        s = LevelSampler([], None, None, num_actors=N, strategy='positive_value_loss', sample_full_distribution=True, seed_buffer_size=64)
+        got = s.episode_records(_rollouts_from(rec))
+        want = []
+        for e in range(N):
+            start = 0
+            for t in range(T):
+                if masks[t + 1, e] == 0 or t == T - 1:
+                    adv = np.maximum(rec['returns'][start:t + 1, e] - rec['value_preds'][start:t + 1, e], 0)
+                    want.append((e, start, t + 1, rec['level_seeds'][start, e], adv.astype(np.float64).mean(), adv.max(),
+                                 np.cumsum(rec['rewards'][start:t + 1, e], dtype=np.float32)[-1], rec['value_preds'][start:t + 1, e].min(),
+                                 0 if masks[t + 1, e] == 0 else 2))
+                    start = t + 1
+        assert len(got) == len(want), (T, N)
+        w = list(zip(*want))
+        for k, col in zip(('actor', 't_start', 't_end', 'seed'), w[:4]):
+            assert np.array_equal(got[k], np.array(col)), (k, T, N)
+        assert np.allclose(got['mean_score'], w[4], rtol=RTOL, atol=1e-7) and np.allclose(got['max_score'], w[5], rtol=0, atol=0)
+        assert np.allclose(got['reward_sum'], w[6], rtol=2e-5, atol=1e-6) and np.array_equal(got['value_min'], np.array(w[7], np.float32))
+        assert np.array_equal(got['cliffhanger'], np.array(w[8]))
+
+
 def test_sample_weights_and_replay_golden():
     from dcd_isaac_b200.level_sampler import LevelSampler
     g = golden('plr_weights.npz')
