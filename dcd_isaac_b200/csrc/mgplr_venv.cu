@@ -1661,13 +1661,14 @@ extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, in
   return 0;
 }
 
-extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random,
-                             const mgplr_step_out *out_t0, void *stream) {
+extern "C" int mgplr_rollout_ex(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random, int32_t last_step,
+                                const mgplr_step_out *out_t0, void *stream) {
   NEED(v);
   if (!actions || T < 1) return fail(MGPLR_E_BADARG, "mgplr_rollout: bad arguments");
   StepArgs A;
   memset(&A, 0, sizeof(A));
   if (out_t0) A.o = *out_t0;
+  A.last_step = last_step;  // applied to step T-1 only (k_rollout)
   const int tile = 64;
   const int grid = grid_for(v->d.N, tile);
   const size_t smem = step_smem_bytes(v->d.c.W, tile, 2, reset_random != 0);
@@ -1685,6 +1686,11 @@ extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, i
 #undef LAUNCH
   CK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random,
+                             const mgplr_step_out *out_t0, void *stream) {
+  return mgplr_rollout_ex(v, actions, T, reset_random, 0, out_t0, stream);
 }
 
 extern "C" int mgplr_full_obs(mgplr_venv *v, float *full_obs, void *stream) {

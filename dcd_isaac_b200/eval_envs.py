@@ -5,6 +5,11 @@ from .mst_maze import MST_MAZES, CudaMSTMazeVecEnv
 from .vec_env import CudaMazeVecEnv
 
 
+def is_eval_env(env_name):
+    """True for the env ids make_eval_venv builds (the drop-in routes only these away from the reference's subprocess envs)."""
+    return env_name in MAZES or env_name in MST_MAZES
+
+
 def make_eval_venv(env_name, num_processes, device='cuda:0', full_obs=False):
     """env_name: one of the fixed-bitmap mazes of envs/multigrid/maze.py (MultiGrid-SixteenRooms-v0, -Labyrinth-v0,
     -Maze-v0, ...) or a Kruskal perfect maze of envs/multigrid/mst_maze.py (Small / Medium)."""

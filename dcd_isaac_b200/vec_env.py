@@ -38,7 +38,7 @@ def seed_limbs(seed):
 
 class CudaAdversarialVecEnv(object):
     def __init__(self, env_name, num_envs, device='cuda:0', seed=None, fixed_environment=None, spec=None, full_obs=False,
-                 **overrides):
+                 host_rng_seed=None, **overrides):
         if spec is None:
             spec = env_spec(env_name, fixed_environment=fixed_environment, **overrides)
         self.env_name = env_name
@@ -67,6 +67,12 @@ class CudaAdversarialVecEnv(object):
         self.h = h
         self.closed = False
         self.tstart = time.time()
+        # The env-side draws the reference makes from numpy's GLOBAL stream (random_z, adversarial.py:449-450; mutate_level,
+        # :317-397; _resample_n_clutter, :151-156; the corridor mazes' goal, maze.py:153-156) happen inside its env
+        # SUBPROCESSES, each with its own unseeded stream -- they never touch the trainer process's np.random, which the
+        # level sampler's decisions and draws consume (level_sampler.py:611,616,674).  The drop-in keeps that separation: one
+        # venv-owned RandomState, unseeded unless `host_rng_seed` / `host_rng.seed()` asks for repeatability.
+        self.host_rng = np.random.RandomState(host_rng_seed)
         self.seed_values = [seed] * self.num_envs
         # spaces (multigrid.py:407-440, adversarial.py:126-145, obs_wrappers.py:118-155 transposes 'image')
         N = self.num_envs
@@ -148,10 +154,10 @@ class CudaAdversarialVecEnv(object):
     def _adv_obs(self, image, time_step):
         # random_z: np.random.uniform(size=(50,)).astype(float32) per env (adversarial.py:449-450).  In the reference every
         # env subprocess draws it from its own, unseeded global numpy stream, so only the distribution is defined: small
-        # batches keep the host draw (np.random.seed then makes runs repeatable), large ones draw on the device (the host
-        # draw of N x 50 doubles was 66 of the 82 ms of a 4 096-env PAIRED cycle).
+        # batches draw from the venv's host_rng (seedable), large ones on the device (the host draw of N x 50 doubles was
+        # 66 of the 82 ms of a 4 096-env PAIRED cycle).
         if self.num_envs <= 256:
-            z = torch.from_numpy(np.random.uniform(size=(self.num_envs, self.random_z_dim)).astype(np.float32)).to(self.device)
+            z = torch.from_numpy(self.host_rng.uniform(size=(self.num_envs, self.random_z_dim)).astype(np.float32)).to(self.device)
         else:
             z = torch.rand(self.num_envs, self.random_z_dim, dtype=torch.float32, device=self.device)
         return {'image': image, 'time_step': time_step, 'random_z': z}
@@ -229,10 +235,14 @@ class CudaAdversarialVecEnv(object):
         o = self._out(obs)
         nw = None
         if self.resample_n_clutter:  # _resample_n_clutter: np.random.randint(0, n_clutter) per env (adversarial.py:151-156)
-            nw = torch.from_numpy(np.random.randint(0, self.n_clutter, size=self.num_envs).astype(np.int32)).to(self.device)
+            nw = self._draw_n_walls()
         check(self.L.mgplr_reset_random(self.h, ptr(nw), C.byref(o), self._stream()), 'mgplr_reset_random')
         self._raise_errors()
         return self._add_full_obs(obs)
+
+    def _draw_n_walls(self):
+        """One _resample_n_clutter draw per env: np.random.randint(0, n_clutter) (adversarial.py:151-156)."""
+        return torch.from_numpy(self.host_rng.randint(0, self.n_clutter, size=self.num_envs).astype(np.int32)).to(self.device)
 
     def _levels_to_device(self, levels):
         """list of levels -> ('bytes', u8 [n,W,W,3]) or ('str', i32 [n,len])."""
@@ -273,8 +283,8 @@ class CudaAdversarialVecEnv(object):
     def mutate_level(self, num_edits, edits=None):
         """venv.mutate_level(num_edits) (parallel_wrappers.py:352-359 -> adversarial.py:317-397).
 
-        The GLOBAL np.random draws are made here on the host, per env in env order, exactly as the reference
-        makes them; `edits` = (locs[N][k], ops[N][k], n_edits[N], choice[N][2]) replays recorded draws.
+        The draws the reference's env processes make from their global np.random are made here on the host from
+        `self.host_rng`, per env in env order and in the reference's order within an env; `edits` = (locs[N][k], ops[N][k], n_edits[N], choice[N][2]) replays recorded draws.
         Returns the agent observation (not used by the runner)."""
         self._assert_not_closed()
         N = self.num_envs
@@ -284,8 +294,8 @@ class CudaAdversarialVecEnv(object):
             # In the reference every env subprocess makes these draws from its OWN unseeded global numpy stream, so only the
             # per-env semantics are defined (DESIGN.md deviation 2): large batches draw all envs' numbers in two calls and
             # keep the per-env rule -- distinct locations in set-iteration order, one op per kept location.
-            raw = np.random.randint(0, num_tiles, (N, num_edits)).tolist()
-            ops_raw = np.random.randint(0, n_ops, (N, num_edits))
+            raw = self.host_rng.randint(0, num_tiles, (N, num_edits)).tolist()
+            ops_raw = self.host_rng.randint(0, n_ops, (N, num_edits))
             mx = max(1, num_edits)
             locs = np.zeros((N, mx), np.int32)
             n_ed = np.zeros(N, np.int32)
@@ -299,8 +309,8 @@ class CudaAdversarialVecEnv(object):
             if edits is None:
                 locs_l, ops_l = [], []
                 for _ in range(N):
-                    edit_locs = list(set(np.random.randint(0, num_tiles, num_edits)))
-                    action_idx = np.random.randint(0, n_ops, len(edit_locs))
+                    edit_locs = list(set(self.host_rng.randint(0, num_tiles, num_edits)))
+                    action_idx = self.host_rng.randint(0, n_ops, len(edit_locs))
                     locs_l.append(edit_locs)
                     ops_l.append(action_idx)
                 choice = None
@@ -327,7 +337,7 @@ class CudaAdversarialVecEnv(object):
             for i, k in zip(*np.nonzero(need_h)):  # np.random.choice(free_idx) (adversarial.py:308-315), env order, goal first then agent
                 if nfree_h[i, k] <= 0:
                     raise ValueError("'a' cannot be empty unless no samples are taken")
-                choice[i, k] = np.random.choice(int(nfree_h[i, k]))
+                choice[i, k] = self.host_rng.choice(int(nfree_h[i, k]))
         d_choice = torch.from_numpy(np.ascontiguousarray(choice, dtype=np.int32)).to(self.device)
         obs = self._new_obs()
         o = self._out(obs)
@@ -361,11 +371,13 @@ class CudaAdversarialVecEnv(object):
         base = flat.data_ptr()
         o.image, o.direction, o.reward = base, base + o_dir * 4, base + o_rew * 4
         a = torch.as_tensor(action)
-        if reset_random and self.resample_n_clutter:
-            raise NotImplementedError('step_env(reset_random=True) with resample_n_clutter: use step_env_device')
-        if a.device.type == 'cuda':
-            a = a.reshape(-1).to(torch.int64).contiguous()
-            check(self.L.mgplr_step_env(self.h, ptr(a), int(bool(reset_random)), None, 0, C.byref(o), self._stream()),
+        # DR auto-reset of a resample_n_clutter env (MultiGrid-GoalLastVariableBlocksAdversarialEnv-v0, the shipped
+        # mg_60b_uni_dr config): every env that finishes this step draws its own wall count (adversarial.py:151-156,574);
+        # one draw per env per step is made up front and only the finished envs consume theirs
+        n_walls = self._draw_n_walls() if (reset_random and self.resample_n_clutter) else None
+        if a.device.type == 'cuda' or n_walls is not None:
+            a = a.reshape(-1).to(torch.int64).to(self.device).contiguous()
+            check(self.L.mgplr_step_env(self.h, ptr(a), int(bool(reset_random)), ptr(n_walls), 0, C.byref(o), self._stream()),
                   'mgplr_step_env')
             flags = self._flags.cpu().numpy()
             ep_r = ep_l = None
@@ -414,15 +426,20 @@ class CudaAdversarialVecEnv(object):
     def rollout_device(self, actions_u8, out, reset_random=False, last_step=0):
         """T transitions in one launch from a recorded u8 [T, N] action stream (mgplr_rollout)."""
         T = int(actions_u8.shape[0])
-        o = out
-        if last_step:
-            raise NotImplementedError
-        check(self.L.mgplr_rollout(self.h, ptr(actions_u8), T, int(bool(reset_random)), C.byref(o), self._stream()),
-              'mgplr_rollout')
+        check(self.L.mgplr_rollout_ex(self.h, ptr(actions_u8), T, int(bool(reset_random)), int(last_step), C.byref(out),
+                                      self._stream()), 'mgplr_rollout_ex')
 
     def step(self, action):
-        raise NotImplementedError('step() auto-reset()s to an EMPTY adversarial grid in the reference '
-                                  '(parallel_wrappers.py:20-25); evaluation envs are not part of this build yet')
+        """venv.step(action) on the ADVERSARIAL env (parallel_wrappers.py:20-25,243-266).  The reference's worker answers
+        a finished env with `env.reset()`, i.e. the EMPTY adversary grid and the ADVERSARY observation dict (image [W,W,3],
+        time_step, random_z), which `_flatten_obs` (parallel_wrappers.py:208-216) then cannot stack with the other envs'
+        agent observations: it fails with KeyError('direction').  Until an episode ends, step() is the same transition as
+        step_env(); the step that ends one raises the reference's error.  Evaluation uses the non-adversarial test envs
+        (`CudaMazeVecEnv.step`, eval_envs.make_eval_venv), whose auto-reset is well defined."""
+        obs, rew, done, infos = self.step_env(action, reset_random=False)
+        if done.any():
+            raise KeyError('direction')
+        return obs, rew, done, infos
 
     # ------------------------------------------------------------------ getters
     def get_encodings(self, index=None):
@@ -549,7 +566,7 @@ class CudaMazeVecEnv(CudaAdversarialVecEnv):
     auto-`reset()` on done (parallel_wrappers.py:20-25), VecMonitor episode infos, preprocessed float32 observations.
     Same step / render kernels as the adversarial env; the level is loaded once with mgplr_load_levels."""
 
-    def __init__(self, env_name, num_envs, device='cuda:0', full_obs=False):
+    def __init__(self, env_name, num_envs, device='cuda:0', full_obs=False, host_rng_seed=None):
         from .mazes import MAZES
         if env_name not in MAZES:
             raise KeyError('No registered env with id: %s' % env_name)
@@ -557,7 +574,7 @@ class CudaMazeVecEnv(CudaAdversarialVecEnv):
         spec = dict(n_clutter=0, size=m['size'], choose_goal_last=True, see_through_walls=True, max_steps=m['max_steps'],
                     max_episode_steps=32767, resample_n_clutter=False, editor_actions='walls_none_agent_goal',
                     fixed_environment=False)
-        super().__init__(env_name, num_envs, device=device, spec=spec, full_obs=full_obs)  # eval.py:200-202
+        super().__init__(env_name, num_envs, device=device, spec=spec, full_obs=full_obs, host_rng_seed=host_rng_seed)  # eval.py:200-202
         self.maze = m
         W = m['size']
         if 'goal' in m:
@@ -565,8 +582,8 @@ class CudaMazeVecEnv(CudaAdversarialVecEnv):
         else:  # corridor mazes: row then col drawn per env at construction (maze.py:153-156,180-183)
             goals = []
             for _ in range(num_envs):
-                row = np.random.choice(m['goal_rows'])
-                col = np.random.choice(m['goal_cols'])
+                row = self.host_rng.choice(m['goal_rows'])
+                col = self.host_rng.choice(m['goal_cols'])
                 goals.append((int(col), int(row)))
         distinct = sorted(set(goals))
         enc = np.zeros((len(distinct), W, W, 3), np.uint8)
@@ -608,6 +625,10 @@ def create_parallel_env(args, adversary=True, device='cuda:0'):
     ued_venv is venv for MultiGrid, seeded [0..N-1] (or [args.seed]*N for singleton_env)."""
     if not args.env_name.startswith('MultiGrid'):
         raise NotImplementedError('only the MultiGrid adversarial environments are built (SURVEY.md 8)')
+    if getattr(args, 'normalize_returns', False):
+        # VecNormalize(ret=True) (util/__init__.py:192, vec_normalize.py:37-45) rescales rewards by a running return std;
+        # no shipped MultiGrid config sets it and the step kernel writes raw rewards, so refuse instead of ignoring it
+        raise NotImplementedError('--normalize_returns (VecNormalize ret=True) is not part of the B200 MultiGrid path')
     singleton = bool(getattr(args, 'singleton_env', False))
     venv = CudaAdversarialVecEnv(args.env_name, args.num_processes, device=device,
                                  fixed_environment=True if singleton else None,

@@ -143,8 +143,10 @@ int mgplr_mutate_finalize(mgplr_venv *v, const int32_t *choice, const mgplr_step
 
 /* venv.step_env(action, reset_random) (vec_env.py:113-118, parallel_wrappers.py:27-37,299-311) with the
  * wrapper chain folded in (time_limit.py:24-33, vec_monitor.py:60-85, obs_wrappers.py:168-181).
- * action i64 [N] (device).  last_step != 0 additionally applies adversarial_runner.py:521-530 to the
- * mask outputs (done forced, cliffhanger for not-done envs).  n_walls as in mgplr_reset_random. */
+ * action i64 [N] (device).  last_step bit 0: this is the rollout's last step -- adversarial_runner.py:530 forces
+ * done, so masks = 0 for every env; bit 1: use_proper_time_limits -- envs that are not done at that step are
+ * cliffhangers (adversarial_runner.py:521-528): cliffhanger_masks = 0, bad_masks = 0, and their observation is also
+ * written to trunc_image / trunc_direction.  n_walls as in mgplr_reset_random. */
 int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls,
                    int32_t last_step, const mgplr_step_out *out, void *stream);
 
@@ -174,6 +176,10 @@ int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset
  * [T][N][1], reward [T][N][1], flags u8 [T][N]; masks f32 [T][N][1] etc.  Any may be NULL. */
 int mgplr_rollout(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random,
                   const mgplr_step_out *out_t0, void *stream);
+/* Same, with the runner's last-step rule (adversarial_runner.py:521-530; `last_step` as in mgplr_step_env: bit 0 = this is a
+ * rollout's last step, bit 1 = use_proper_time_limits) applied to the mask outputs of step T-1. */
+int mgplr_rollout_ex(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random, int32_t last_step,
+                     const mgplr_step_out *out_t0, void *stream);
 
 /* obs['full_obs'] of MultiGridFullyObsWrapper (envs/wrappers/multigrid_wrappers.py:14-51; used with
  * --use_global_critic / --use_global_policy, util/__init__.py:175-178): the whole grid's encoding with the agent cell

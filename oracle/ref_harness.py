@@ -3,15 +3,20 @@
 Puts `oracle/shim` (stand-ins for the un-installed third-party gym / gym_minigrid /
 baselines) and `/root/reference` on sys.path so that envs/multigrid/*.py,
 envs/wrappers/*.py, level_replay/*.py and algos/storage.py import UNMODIFIED.  Only
-`oracle/gen_golden.py` and the `-m "not gpu"` reference-diff tests use it; it needs
-/root/reference and therefore never runs on the GPU box.
+`oracle/gen_golden*.py`, the `-m "not gpu"` reference-diff tests, the GPU tests that run the reference's own runner /
+train.py against the drop-in, and bench.py's Python CPU-baseline leg use it.  The tree is /root/reference in the
+authoring container and the unmodified staged copy baseline/_ref/reference (oracle/stage_reference.py; git-ignored,
+travels with the gpurun snapshot) on the GPU box.
 """
 import os
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SHIM = os.path.join(HERE, 'shim')
+STAGED = os.path.join(os.path.dirname(HERE), 'baseline', '_ref', 'reference')
 REFERENCE = os.environ.get('DCD_REFERENCE', '/root/reference')
+if not os.path.isdir(os.path.join(REFERENCE, 'envs', 'multigrid')) and os.path.isdir(os.path.join(STAGED, 'envs', 'multigrid')):
+    REFERENCE = STAGED
 
 
 def available():

@@ -9,3 +9,7 @@ import numpy as np
 for _n, _v in (("float", float), ("int", int), ("bool", bool), ("NINF", -np.inf)):
     if not hasattr(np, _n):
         setattr(np, _n, _v)
+
+import _stubs  # noqa: E402  permissive stand-ins for the Box2D / plotting / display packages (never used on the MultiGrid path)
+
+_stubs.install()

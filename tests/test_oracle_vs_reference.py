@@ -61,3 +61,32 @@ def test_random_dense_levels(W, see):
             assert np.array_equal(res['obs'], np.array(o['image'], np.uint8)), i
             assert res['rew'] == np.float32(r) and bool(res['flags'] & 1) == bool(d)
     assert n_impassable > 3  # the unreachable branch was exercised
+
+
+def test_runner_fixture_reproducible():
+    """The runner-level fixtures are outputs of the reference's own AdversarialRunner.run() over its spawn-subprocess
+    vector env (oracle/gen_golden_runner.py): re-executing one case here must reproduce the committed file exactly."""
+    import gzip
+    import os
+    import pickle
+    from conftest import GOLDEN
+    rh.activate()
+    import oracle.gen_golden_runner as gr
+    import util
+    from algos.storage import RolloutStorage
+    from envs.runners.adversarial_runner import AdversarialRunner
+    name = 'runner_dr_mini_nohtl'
+    with gzip.open(os.path.join(GOLDEN, name + '.pkl.gz'), 'rb') as f:
+        g = pickle.load(f)
+    args = gr.parse_args(g['argv'])
+    venv, ued_venv = util.create_parallel_env(args)
+    try:
+        runner, agent, _ = gr.build_runner(args, venv, ued_venv, RolloutStorage, AdversarialRunner, None)
+        runs = gr.run_case(name, runner, agent, g['n_runs'], g['np_seed'])
+    finally:
+        venv.close()
+    for got, want in zip(runs, g['runs']):
+        for k, v in want['storage'].items():
+            assert np.array_equal(got['storage'][k], v), k
+        assert np.array_equal(got['encodings'], want['encodings'])
+        assert got['total_episodes'] == want['total_episodes']
