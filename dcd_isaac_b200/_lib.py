@@ -50,7 +50,7 @@ SYMBOLS = (
     'mgplr_last_error', 'mgplr_abi_version', 'mgplr_venv_create', 'mgplr_venv_destroy', 'mgplr_venv_num_envs',
     'mgplr_venv_state_bytes', 'mgplr_seed', 'mgplr_reset', 'mgplr_step_adversary', 'mgplr_reset_agent',
     'mgplr_reset_random', 'mgplr_reset_to_encoding', 'mgplr_load_levels', 'mgplr_load_levels_at', 'mgplr_reset_to_actions', 'mgplr_mutate_edits',
-    'mgplr_mutate_finalize', 'mgplr_step_env', 'mgplr_step_env_host', 'mgplr_rollout', 'mgplr_rollout_ex', 'mgplr_full_obs', 'mgplr_get_encodings',
+    'mgplr_mutate_finalize', 'mgplr_step_env', 'mgplr_step_env_u8', 'mgplr_step_env_host', 'mgplr_step_env_host_u8', 'mgplr_rollout', 'mgplr_rollout_ex', 'mgplr_full_obs', 'mgplr_render_images', 'mgplr_get_encodings',
     'mgplr_get_metrics', 'mgplr_get_agent_state', 'mgplr_get_errors', 'mgplr_peek_rng', 'mgplr_gae',
     'mgplr_discounted_returns', 'mgplr_batched_value_loss',
     'mgplr_plr_episode_scores', 'mgplr_plr_episode_scores_ex', 'mgplr_plr_sample_weights', 'mgplr_plr_score_weights', 'mgplr_plr_sample_replay',
@@ -97,9 +97,12 @@ def load():
     L.mgplr_mutate_finalize.argtypes = [vp, vp, C.POINTER(StepOut), vp]
     L.mgplr_step_env.argtypes = [vp, vp, i32, vp, i32, C.POINTER(StepOut), vp]
     L.mgplr_step_env_host.argtypes = [vp, vp, i32, i32, C.POINTER(StepOut), vp, vp, i32, vp, vp]
+    L.mgplr_step_env_host_u8.argtypes = [vp, vp, i32, i32, C.POINTER(StepOut), vp, vp, i32, vp, vp]
+    L.mgplr_step_env_u8.argtypes = [vp, vp, i32, vp, i32, C.POINTER(StepOut), vp]
     L.mgplr_rollout.argtypes = [vp, vp, i32, i32, C.POINTER(StepOut), vp]
     L.mgplr_rollout_ex.argtypes = [vp, vp, i32, i32, i32, C.POINTER(StepOut), vp]
     L.mgplr_full_obs.argtypes = [vp, vp, vp]
+    L.mgplr_render_images.argtypes = [vp, vp, vp, i32, vp, vp]
     L.mgplr_get_encodings.argtypes = [vp, vp, vp]
     L.mgplr_get_metrics.argtypes = [vp, vp, vp]
     L.mgplr_get_agent_state.argtypes = [vp, vp, vp]

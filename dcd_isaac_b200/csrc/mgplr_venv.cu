@@ -54,6 +54,7 @@ struct mgplr_venv {
   int pdl;                 // launch the step kernel with programmatic stream serialization
   int rr_spec;             // DR auto-reset: speculative next-level candidates (MGPLR_RR_SPEC=0 disables)
   int sm_count;
+  int steps_since_sweep;   // reset_agent-mode step launches since the last deferred-respawn sweep (kSweepEvery)
 };
 
 // dynamic shared memory: `bufs` obs tiles [TILE][75] f32 then wall rows [W][TILE] u32
@@ -493,13 +494,56 @@ __global__ void k_encode(Dev d, uint8_t *enc) {
   o[0] = t; o[1] = c; o[2] = st;
 }
 
+// venv.get_images() (parallel_wrappers.py:187-193 -> MultiGridEnv.render(mode='level'), multigrid.py:1105-1140 ->
+// Grid.render, :216-261): the level as an RGB mosaic of 32x32 tiles, out u8 [n][W*32][W*32][3].  A maze cell is empty, wall,
+// goal or the agent (4 directions), highlighted or not (compute_agent_visibility_mask, multigrid.py:1071-1103: the cells of
+// the agent's view that process_vis leaves visible; walls are never highlighted, render_tile :190): 14 tiles, rendered once on
+// the host (dcd_isaac_b200/tiles.py) and pasted here.  One CTA per (cell row, image): the 32 pixel rows of a cell row are
+// contiguous in the output, written as coalesced 32-bit words.
+__global__ void __launch_bounds__(256) k_render_images(Dev d, const uint32_t *tiles /* [14][32][24] words */, const int32_t *index,
+                                                       int n, uint8_t *out) {
+  __shared__ int s_tile[32];
+  const int W = d.c.W, y = blockIdx.x, k = blockIdx.y;
+  const int e = index ? index[k] : k;
+  if (e < 0 || e >= d.N) return;
+  if ((int)threadIdx.x < W) {
+    const int x = threadIdx.x;
+    const Env s = unpack(d.hot[e]);
+    const Rows R = env_rows(d, e);
+    int code = 0;
+    if (s.has_agent && x == s.ax && y == s.ay) code = 3 + s.adir;
+    else if ((R.get(y) >> x) & 1u) code = 1;
+    else if (x == s.gx && y == s.gy) code = 2;
+    int hl = 0;
+    if (s.has_agent && code != 1) {
+      const uint32_t vis = d.c.see_through ? render_packed<true, uint64_t>(R, s, W).vis : render_packed<false, uint64_t>(R, s, W).vis;
+      const int dd = s.adir, dx = x - s.ax, dy = y - s.ay;
+      const bool vertical = dd & 1;
+      const int p = vertical ? dy : dx, q = vertical ? dx : dy;
+      const int fd = (dd == 0 || dd == 1) ? p : -p, lt = (dd == 0 || dd == 3) ? q : -q;
+      const int vy = kV - 1 - fd, vx = lt + kV / 2;
+      if ((unsigned)vx < (unsigned)kV && (unsigned)vy < (unsigned)kV) hl = (vis >> (vy * kV + vx)) & 1u;
+    }
+    s_tile[x] = 2 * code + hl;
+  }
+  __syncthreads();
+  const int row_words = W * 24;                      // one pixel row of the image: W tiles x 96 bytes
+  const size_t img_words = (size_t)W * 32 * row_words;
+  uint32_t *o = reinterpret_cast<uint32_t *>(out) + (size_t)k * img_words + (size_t)y * 32 * row_words;
+  for (int w = threadIdx.x; w < 32 * row_words; w += blockDim.x) {
+    const int py = w / row_words, rem = w - py * row_words, x = rem / 24, off = rem - x * 24;
+    o[w] = tiles[(s_tile[x] * 32 + py) * 24 + off];
+  }
+}
+
 // replay deferred respawn draws so that the RNG state seen by the host is the reference's
-__global__ void k_flush(Dev d) {
+// (min_pending > 1: the periodic sweep that keeps the 8-bit counter of very easy levels far from saturation)
+__global__ void k_flush(Dev d, int min_pending) {
   RNG_SCRATCH();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= d.N) return;
   Env s = unpack(d.hot[e]);
-  if (!s.pending) return;
+  if (s.pending < min_pending) return;
   const Rows R = env_rows(d, e);
   Rng rng = RNG_OF(d, e);
   flush_pending(R, s, rng, d.c.W);
@@ -536,6 +580,7 @@ __global__ void k_get_errors(Dev d, uint32_t *o, int clear) {
 // ------------------------------------------------------------------------------------------ hot kernel: step_env
 struct StepArgs {
   const int64_t *action;
+  const uint8_t *action_u8;      // narrow action stream (one byte per env) used instead of `action` when not NULL
   const int32_t *n_walls;
   int last_step;  // bit0: last rollout step (adversarial_runner.py:521-530), bit1: use_proper_time_limits
   mgplr_step_out o;
@@ -938,7 +983,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   int na = 6;
   uint32_t nsp = 0;  // speculation word of the env (DR variant)
   if (tile < n_tiles && tile * kWarpTile + lane < N) {
-    nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep); na = (int)A.action[tile * kWarpTile + lane];
+    nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep);
+    na = A.action_u8 ? (int)A.action_u8[tile * kWarpTile + lane] : (int)A.action[tile * kWarpTile + lane];
     if (use_spec) nsp = d.spec[tile * kWarpTile + lane];
   }
   uint32_t phase = 0;  // bit s = parity to wait for on bars[s]
@@ -956,7 +1002,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     if (next < n_tiles) {
       warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane, pol_keep);
       if (next * kWarpTile + lane < N) {
-        nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_keep); na = (int)A.action[next * kWarpTile + lane];
+        nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_keep);
+        na = A.action_u8 ? (int)A.action_u8[next * kWarpTile + lane] : (int)A.action[next * kWarpTile + lane];
         if (use_spec) nsp = d.spec[next * kWarpTile + lane];
       }
     }
@@ -1453,6 +1500,7 @@ static OutPtrs outptrs(const mgplr_step_out *o) {
 
 extern "C" int mgplr_reset_agent(mgplr_venv *v, const mgplr_step_out *out, void *stream) {
   NEED(v);
+  v->steps_since_sweep = 0;  // k_reset_agent replays every deferred respawn
   k_reset_agent<<<grid_for(v->d.N, 128), 128, 4 * 32 * kObsFloats * sizeof(float), st>>>(v->d, outptrs(out));
   CK(cudaGetLastError());
   return 0;
@@ -1478,7 +1526,7 @@ extern "C" int mgplr_load_levels(mgplr_venv *v, const uint8_t *enc, int32_t n_le
                                  int32_t start_dir, const mgplr_step_out *out, void *stream) {
   NEED(v);
   if (!enc || n_levels < 1) return fail(MGPLR_E_BADARG, "mgplr_load_levels: bad arguments");
-  k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d);  // the RNG stream keeps its reference position
+  k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, 1);  // the RNG stream keeps its reference position
   k_load_levels<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, enc, n_levels, level_index, start_dir, outptrs(out));
   CK(cudaGetLastError());
   return 0;
@@ -1541,7 +1589,19 @@ static int rr_spec_alloc(mgplr_venv *v) {
   return 0;
 }
 
+// Deferred goal respawns are counted in 8 bits per env (Env::pending); a level whose goal sits next to the start can finish an
+// episode every step or two, and a saturated counter is flushed INSIDE the step kernel, one serial MT draw at a time (~0.5 ms
+// for one warp).  Every kSweepEvery-th reset_agent-mode step launch is therefore preceded by a sweep that replays the draws of
+// the (rare) envs that have accumulated kSweepMin or more -- at full speed, with the batched generator -- so that no env
+// comes near 255 however long the caller goes without a reset_agent().  8 MB of hot records per sweep at 524 288 envs.
+constexpr int kSweepEvery = 64, kSweepMin = 96;
+
 static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cudaStream_t st, int tile0, int tile1) {
+  if (!reset_random && tile0 == 0 && ++v->steps_since_sweep >= kSweepEvery) {
+    v->steps_since_sweep = 0;
+    k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, kSweepMin);
+    CK(cudaGetLastError());
+  }
   // persistent grid: as many 4-warp CTAs as fit on the chip (shared-memory bound), capped by the tile count
   const int W = v->d.c.W, wpc = 4;
   const size_t smem = wpc * warp_smem_bytes(W, reset_random != 0);
@@ -1587,6 +1647,17 @@ extern "C" int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t rese
   return launch_step(v, action, reset_random, n_walls, last_step, out, st);
 }
 
+extern "C" int mgplr_step_env_u8(mgplr_venv *v, const uint8_t *action, int32_t reset_random, const int32_t *n_walls,
+                                 int32_t last_step, const mgplr_step_out *out, void *stream) {
+  NEED(v);
+  if (!action) return fail(MGPLR_E_BADARG, "action is NULL");
+  StepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.action_u8 = action; A.n_walls = n_walls; A.last_step = last_step;
+  if (out) A.o = *out;
+  return launch_step_args(v, A, reset_random, st);
+}
+
 constexpr int kHostChunks = 8;
 // Device view of a host pointer when it is pinned (cudaHostAlloc / cudaHostRegister) memory, else NULL.
 static void *mapped_view(const void *host) {
@@ -1601,26 +1672,28 @@ static void *mapped_view(const void *host) {
 // writes the flags straight into the caller's pinned flags buffer and appends the done records to a device-mapped pinned
 // list (dense prefix of an env = -1 sentinel-filled array, so no count has to come back).  Pageable buffers take staged
 // copies around the same launch.
-extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
-                                   const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
-                                   int32_t done_capacity, int32_t *n_done_host, void *stream) {
+static int step_env_host_impl(mgplr_venv *v, const void *action_host_any, size_t act_size, int32_t reset_random, int32_t last_step,
+                              const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
+                              int32_t done_capacity, int32_t *n_done_host, void *stream) {
   NEED(v);
-  if (!action_host) return fail(MGPLR_E_BADARG, "action_host is NULL");
+  if (!action_host_any) return fail(MGPLR_E_BADARG, "action_host is NULL");
   const size_t N = (size_t)v->d.N;
   mgplr_done_record *list_h = (mgplr_done_record *)v->res_pin;
   uint8_t *flags_pin = v->res_pin + 16 * N;
-  const int64_t *act = (const int64_t *)mapped_view(action_host);
+  const bool narrow = act_size == 1;
+  const int64_t *action_host = (const int64_t *)action_host_any;  // (the chunked-DMA A/B path below is int64-only)
+  const int64_t *act = (const int64_t *)mapped_view(action_host_any);
   // A/B knob (MGPLR_HOST_DMA=1, off): stage the pinned actions with the copy engine in chunks on a side stream and run
   // the step as one sub-launch per chunk behind its copy.  Measured slower than the zero-copy read on both sizes
   // (524 288 envs: 3.2 vs 4.4 G env-steps/s; 131 072: 2.2 vs 2.8): the event hand-offs cost more than the PCIe gain.
   int chunks = 1;
-  if (act && v->host_dma && N >= 65536) {
+  if (act && v->host_dma && N >= 65536 && !narrow) {
     chunks = (int)(N / 65536);
     if (chunks > kHostChunks) chunks = kHostChunks;
     act = v->act_dev;
   }
   if (!act) {
-    CK(cudaMemcpyAsync(v->act_dev, action_host, N * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(v->act_dev, action_host_any, N * act_size, cudaMemcpyHostToDevice, st));
     act = v->act_dev;
   }
   uint8_t *flags_map = flags_host ? (uint8_t *)mapped_view(flags_host) : nullptr;
@@ -1628,7 +1701,8 @@ extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, in
   StepArgs A;
   memset(&A, 0, sizeof(A));
   if (out_dev) A.o = *out_dev;
-  A.action = act; A.last_step = last_step;
+  if (narrow) A.action_u8 = (const uint8_t *)act; else A.action = act;
+  A.last_step = last_step;
   A.done_count = v->cnt_dev + (v->host_steps & 1u);
   A.done_count_next = v->cnt_dev + ((v->host_steps + 1u) & 1u);
   A.done_list = (mgplr_done_record *)v->res_pin_dev;
@@ -1659,6 +1733,19 @@ extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, in
   }
   for (size_t k = 0; k < n_done; k++) list_h[k].env = -1;
   return 0;
+}
+
+extern "C" int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset_random, int32_t last_step,
+                                   const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
+                                   int32_t done_capacity, int32_t *n_done_host, void *stream) {
+  return step_env_host_impl(v, action_host, sizeof(int64_t), reset_random, last_step, out_dev, flags_host, done_host, done_capacity,
+                            n_done_host, stream);
+}
+extern "C" int mgplr_step_env_host_u8(mgplr_venv *v, const uint8_t *action_host, int32_t reset_random, int32_t last_step,
+                                      const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
+                                      int32_t done_capacity, int32_t *n_done_host, void *stream) {
+  return step_env_host_impl(v, action_host, 1, reset_random, last_step, out_dev, flags_host, done_host, done_capacity, n_done_host,
+                            stream);
 }
 
 extern "C" int mgplr_rollout_ex(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t reset_random, int32_t last_step,
@@ -1699,6 +1786,16 @@ extern "C" int mgplr_full_obs(mgplr_venv *v, float *full_obs, void *stream) {
   return launch_adv_image(v, full_obs, nullptr, 0, nullptr, nullptr, st, 1);
 }
 
+extern "C" int mgplr_render_images(mgplr_venv *v, const uint8_t *tiles, const int32_t *index, int32_t n, uint8_t *images,
+                                   void *stream) {
+  NEED(v);
+  if (!tiles || !images || n < 1 || (!index && n > v->d.N)) return fail(MGPLR_E_BADARG, "mgplr_render_images: bad arguments");
+  if ((((uintptr_t)tiles) & 3u) || (((uintptr_t)images) & 3u)) return fail(MGPLR_E_BADARG, "mgplr_render_images: pointers must be 4-byte aligned");
+  k_render_images<<<dim3(v->d.c.W, n), 256, 0, st>>>(v->d, reinterpret_cast<const uint32_t *>(tiles), index, n, images);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mgplr_get_encodings(mgplr_venv *v, uint8_t *enc, void *stream) {
   NEED(v);
   if (!enc) return fail(MGPLR_E_BADARG, "enc is NULL");
@@ -1717,7 +1814,7 @@ extern "C" int mgplr_get_metrics(mgplr_venv *v, int32_t *metrics, void *stream) 
 extern "C" int mgplr_get_agent_state(mgplr_venv *v, int32_t *state, void *stream) {
   NEED(v);
   if (!state) return fail(MGPLR_E_BADARG, "state is NULL");
-  k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d);
+  k_flush<<<grid_for(v->d.N, 128), 128, 0, st>>>(v->d, 1);
   k_get_agent_state<<<grid_for(v->d.N, 256), 256, 0, st>>>(v->d, state);
   CK(cudaGetLastError());
   return 0;
@@ -1735,7 +1832,7 @@ extern "C" int mgplr_peek_rng(mgplr_venv *v, int32_t index, uint32_t *words_host
   if (!v) return fail(MGPLR_E_BADARG, "venv handle is NULL");
   CK(cudaSetDevice(v->device));
   if (index < 0 || index >= v->d.N || !words_host || count < 0) return fail(MGPLR_E_BADARG, "mgplr_peek_rng: bad arguments");
-  k_flush<<<grid_for(v->d.N, 128), 128>>>(v->d);
+  k_flush<<<grid_for(v->d.N, 128), 128>>>(v->d, 1);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   uint32_t mt[624], idx = 0;

@@ -14,6 +14,7 @@ import ctypes as C
 import hashlib
 import struct
 import time
+import types
 
 import numpy as np
 import torch
@@ -24,6 +25,23 @@ from .registry import EDITOR_ACTION_SPACES, env_spec
 from .spaces import Box, Discrete
 
 F_DONE, F_TRUNC_KEY, F_TRUNC_VAL, F_GOAL = 1, 2, 4, 8
+
+_NO_INFO = types.MappingProxyType({})   # read-only stand-in for the `{}` info of an env to which nothing happened
+
+
+class LazyInfos(list):
+    """The `infos` list of one vector step.  Almost every env's info is `{}` on almost every step, so the untouched
+    entries all hold ONE read-only empty mapping and a real dict is only created for an env that finished / was truncated,
+    or the first time the caller indexes an entry to write into it (`infos[i]['cliffhanger'] = True`,
+    adversarial_runner.py:526-528).  Nothing mutable is shared: writing through the read-only mapping raises."""
+    __slots__ = ()
+
+    def __getitem__(self, i):
+        v = list.__getitem__(self, i)
+        if v is _NO_INFO:
+            v = {}
+            list.__setitem__(self, i, v)
+        return v
 
 
 def seed_limbs(seed):
@@ -98,6 +116,7 @@ class CudaAdversarialVecEnv(object):
         self._errors = torch.zeros(N, dtype=torch.int32, device=dev)
         # pinned host staging for the host-driven step (actions in; flags + done records out)
         self._h_action = torch.zeros(N, dtype=torch.int64).pin_memory()
+        self._h_action_u8 = torch.zeros(N, dtype=torch.uint8).pin_memory()
         self._h_flags = torch.zeros(N, dtype=torch.uint8).pin_memory()
         self._h_done = torch.zeros(N * 16, dtype=torch.uint8).pin_memory()  # mgplr_done_record [N]
         self._h_ndone = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -218,7 +237,7 @@ class CudaAdversarialVecEnv(object):
               'mgplr_step_adversary')
         done = self._done_adv.cpu().numpy().astype(bool)
         rew = torch.zeros(N, 1, dtype=torch.float32, device=self.device)
-        return self._adv_obs(image, ts), rew, done, [{} for _ in range(N)]
+        return self._adv_obs(image, ts), rew, done, LazyInfos([_NO_INFO] * N)
 
     # ------------------------------------------------------------------ level resets
     def reset_agent(self):
@@ -385,10 +404,16 @@ class CudaAdversarialVecEnv(object):
                 ep_r = self._ep_r.cpu().numpy()
                 ep_l = self._ep_l.cpu().numpy()
         else:
-            self._h_action.copy_(a.reshape(-1))
-            check(self.L.mgplr_step_env_host(self.h, ptr(self._h_action), int(bool(reset_random)), 0, C.byref(o),
-                                             ptr(self._h_flags), ptr(self._h_done), N, ptr(self._h_ndone),
-                                             self._stream()), 'mgplr_step_env_host')
+            if N <= 65536:   # narrow to one byte per action on the way into pinned memory (8x less PCIe traffic)
+                self._h_action_u8.copy_(a.reshape(-1))
+                check(self.L.mgplr_step_env_host_u8(self.h, self._h_action_u8.data_ptr(), int(bool(reset_random)), 0, C.byref(o),
+                                                    self._h_flags.data_ptr(), self._h_done.data_ptr(), N, self._h_ndone.data_ptr(),
+                                                    self._stream()), 'mgplr_step_env_host_u8')
+            else:            # (a host-side narrowing pass over millions of int64 would cost more than the transfer)
+                self._h_action.copy_(a.reshape(-1))
+                check(self.L.mgplr_step_env_host(self.h, self._h_action.data_ptr(), int(bool(reset_random)), 0, C.byref(o),
+                                                 self._h_flags.data_ptr(), self._h_done.data_ptr(), N, self._h_ndone.data_ptr(),
+                                                 self._stream()), 'mgplr_step_env_host')
             flags = self._h_flags.numpy().copy()
             nd = int(self._h_ndone[0])
             ep_r = ep_l = None
@@ -399,7 +424,7 @@ class CudaAdversarialVecEnv(object):
                 ep_r[rec['env']] = rec['ep_return']
                 ep_l[rec['env']] = rec['ep_length']
         done = (flags & F_DONE) != 0
-        infos = [{} for _ in range(N)]
+        infos = LazyInfos([_NO_INFO] * N)
         if flags.any():
             t_now = round(time.time() - self.tstart, 6)
             for i in np.nonzero(flags & (F_DONE | F_TRUNC_KEY))[0]:
@@ -519,7 +544,8 @@ class CudaAdversarialVecEnv(object):
         raise NotImplementedError('get_complexity_info is the Box2D envs\' (BipedalWalker / CarRacing), out of scope')
 
     def render_to_screen(self):
-        raise NotImplementedError('RGB rendering is out of scope (SURVEY.md 8f rank 4)')
+        raise NotImplementedError('render_to_screen opens a matplotlib window in env process 0 (parallel_wrappers.py:195-198, '
+                                  '--render); use get_images() for RGB frames')
 
     def get_observation_space(self):
         return self.observation_space
@@ -541,8 +567,28 @@ class CudaAdversarialVecEnv(object):
             res = [res[i] for i in index]
         return res if flatten else [[r] for r in res]
 
-    def get_images(self):
-        raise NotImplementedError('RGB screenshots are out of scope (SURVEY.md 8f rank 4)')
+    def get_images(self, index=None):
+        """venv.get_images() (parallel_wrappers.py:187-193): list of np.uint8 [W*32, W*32, 3] level screenshots, one per env
+        (or per env in `index`) -- MultiGridEnv.render(mode='level') with the agent's view highlighted (multigrid.py:1105-1140).
+        train.py:204-232 saves the first `screenshot_batch_size` of them.  Large batches are rendered in chunks so that the
+        staging buffer stays below ~1 GB."""
+        from . import tiles
+        self._assert_not_closed()
+        if getattr(self, '_tile_table', None) is None:
+            self._tile_table = torch.from_numpy(tiles.tile_table()).to(self.device)
+        idx = list(range(self.num_envs)) if index is None else [int(i) for i in index]
+        side = self.W * tiles.TILE
+        per = side * side * 3
+        chunk = max(1, (1 << 30) // per)
+        out = []
+        for lo in range(0, len(idx), chunk):
+            sub = idx[lo:lo + chunk]
+            d_idx = torch.tensor(sub, dtype=torch.int32, device=self.device)
+            img = torch.empty(len(sub), side, side, 3, dtype=torch.uint8, device=self.device)
+            check(self.L.mgplr_render_images(self.h, ptr(self._tile_table), ptr(d_idx), len(sub), ptr(img), self._stream()),
+                  'mgplr_render_images')
+            out.extend(img.cpu().numpy())
+        return out
 
     def state_bytes(self):
         return int(self.L.mgplr_venv_state_bytes(self.h))

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MGPLR_ABI_VERSION 2
+#define MGPLR_ABI_VERSION 3
 
 #define MGPLR_E_BADARG (-1)
 #define MGPLR_E_UNSUPPORTED (-2)
@@ -150,6 +150,10 @@ int mgplr_mutate_finalize(mgplr_venv *v, const int32_t *choice, const mgplr_step
 int mgplr_step_env(mgplr_venv *v, const int64_t *action, int32_t reset_random, const int32_t *n_walls,
                    int32_t last_step, const mgplr_step_out *out, void *stream);
 
+/* The same with a narrow action stream: action u8 [N] (device), values 0..6 -- 1 byte per env instead of 8. */
+int mgplr_step_env_u8(mgplr_venv *v, const uint8_t *action, int32_t reset_random, const int32_t *n_walls, int32_t last_step,
+                      const mgplr_step_out *out, void *stream);
+
 /* One finished episode, as the host needs it to build info['episode'] (vec_monitor.py:66-74). */
 typedef struct mgplr_done_record {
   int32_t env;        /* env index */
@@ -170,6 +174,12 @@ int mgplr_step_env_host(mgplr_venv *v, const int64_t *action_host, int32_t reset
                         const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
                         int32_t done_capacity, int32_t *n_done_host, void *stream);
 
+/* mgplr_step_env_host with uint8 actions (MultiGrid has 7 actions): 8x less PCIe traffic per vector step; the caller narrows
+ * `action.cpu()` (adversarial_runner.py:512) once.  Everything else as above. */
+int mgplr_step_env_host_u8(mgplr_venv *v, const uint8_t *action_host, int32_t reset_random, int32_t last_step,
+                           const mgplr_step_out *out_dev, uint8_t *flags_host, mgplr_done_record *done_host,
+                           int32_t done_capacity, int32_t *n_done_host, void *stream);
+
 /* T consecutive step_env transitions in ONE launch from a recorded action stream u8 [T][N]: env state
  * stays in shared memory / registers across steps (replayed-seed evaluation, random-policy rollouts).
  * Outputs are the [T]-leading versions of mgplr_step_out fields: image f32 [T][N][3][5][5], direction
@@ -185,6 +195,12 @@ int mgplr_rollout_ex(mgplr_venv *v, const uint8_t *actions, int32_t T, int32_t r
  * --use_global_critic / --use_global_policy, util/__init__.py:175-178): the whole grid's encoding with the agent cell
  * (10, 0, dir), channels first and NOT scaled (obs_wrappers.py:108-110 only transposes it): f32 [N][3][W][W]. */
 int mgplr_full_obs(mgplr_venv *v, float *full_obs, void *stream);
+
+/* venv.get_images() (parallel_wrappers.py:187-193 -> MultiGridEnv.render(mode='level'), multigrid.py:1105-1140,159-261): RGB
+ * screenshots of n levels, images u8 [n][W*32][W*32][3] (device).  tiles u8 [14][32][32][3] (device) is the tile table --
+ * index 2*code + highlighted, code 0 empty / 1 wall / 2 goal / 3+dir agent (dcd_isaac_b200/tiles.py renders it from the
+ * published gym-minigrid tile algorithm).  index i32 [n] (device) selects the envs, NULL = envs 0..n-1. */
+int mgplr_render_images(mgplr_venv *v, const uint8_t *tiles, const int32_t *index, int32_t n, uint8_t *images, void *stream);
 
 /* Getters (parallel_wrappers.py:422-448): encodings u8 [N][W][W][3] = AdversarialEnv.encoding;
  * metrics i32 [N][4] = n_clutter_placed, distance_to_goal, passable, shortest_path_length. */

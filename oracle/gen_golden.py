@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz by EXECUTING the reference's own Python modules (TEST INFRASTRUCTURE ONLY).
 
-Run here (needs /root/reference):   python oracle/gen_golden.py [--only env|venv|adv|mutate|plr]
+Run here (needs /root/reference):   python oracle/gen_golden.py [--only env|venv|fullobs|adv|mutate|images|plr|runner]
 
 The reference ships no tests or golden vectors, so these fixtures are the
 pinning: every array below is an output of the unmodified reference files
@@ -333,16 +333,54 @@ def gen_mutate():
         print('mutate', tag, 'fallbacks', np.array(rec['need']).sum(0))
 
 
+def gen_images():
+    """venv.get_images() (parallel_wrappers.py:187-193 -> render(mode='level')) of the REAL vectorised env: RGB level
+    screenshots with the agent's view highlighted, after reset_random / reset_agent and after a few steps (so that agents
+    face every direction), see-through and occluded; plus the adversary phase (empty grid, no agent -> no highlight)."""
+    import numpy as np
+    import torch
+    from types import SimpleNamespace
+    import util
+    out = {}
+    for tag, env_name in (('gl15', 'MultiGrid-GoalLastAdversarial-v0'),
+                          ('fb15_opaque', 'MultiGrid-GoalLastFewerBlocksOpaqueWallsAdversarial-v0')):
+        N = 4
+        args = SimpleNamespace(env_name=env_name, seed=1, singleton_env=False, use_global_critic=False,
+                               use_global_policy=False, num_processes=N, normalize_returns=False)
+        venv, _ = util.create_parallel_env(args)
+        venv.set_seed(list(range(N)))
+        venv.reset_random()
+        venv.reset_agent()
+        out[tag + '_env_name'] = env_name
+        out[tag + '_enc0'] = np.stack(venv.get_encodings())
+        out[tag + '_img0'] = np.stack(venv.get_images())
+        rs = np.random.RandomState(5)
+        acts = np.stack([_biased_actions(rs, N) for _ in range(9)])
+        for t in range(9):
+            venv.step_env(torch.from_numpy(acts[t].astype(np.int64)).view(N, 1), reset_random=False)
+        out[tag + '_actions'] = acts
+        out[tag + '_img1'] = np.stack(venv.get_images())
+        venv.reset()
+        venv.step_adversary(torch.tensor([[3], [20], [77], [100]]))
+        out[tag + '_img_adv'] = np.stack(venv.get_images())
+        venv.close()
+        print('images', tag, out[tag + '_img0'].shape)
+    np.savez_compressed(os.path.join(GOLDEN, 'level_images.npz'), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default=None)
     a = ap.parse_args()
     rh.activate()
     os.makedirs(GOLDEN, exist_ok=True)
-    todo = {'env': gen_env_traces, 'venv': gen_venv, 'fullobs': gen_fullobs, 'adv': gen_adversary, 'mutate': gen_mutate}
+    todo = {'env': gen_env_traces, 'venv': gen_venv, 'fullobs': gen_fullobs, 'adv': gen_adversary, 'mutate': gen_mutate,
+            'images': gen_images}
     try:
         from gen_golden_plr import gen_plr
         todo['plr'] = gen_plr
+        from gen_golden_runner import gen_runner
+        todo['runner'] = gen_runner
     except ImportError:
         pass
     for k, fn in todo.items():

@@ -74,6 +74,10 @@ class Goal(WorldObj):
     def can_overlap(self):
         return True
 
+    def render(self, img):
+        from gym_minigrid.rendering import fill_coords, point_in_rect
+        fill_coords(img, point_in_rect(0, 1, 0, 1), COLORS[self.color])
+
 
 class Floor(WorldObj):
     def __init__(self, color='blue'):
@@ -97,6 +101,10 @@ class Wall(WorldObj):
 
     def see_behind(self):
         return False
+
+    def render(self, img):
+        from gym_minigrid.rendering import fill_coords, point_in_rect
+        fill_coords(img, point_in_rect(0, 1, 0, 1), COLORS[self.color])
 
 
 class Door(WorldObj):

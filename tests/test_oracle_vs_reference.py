@@ -90,3 +90,21 @@ def test_runner_fixture_reproducible():
             assert np.array_equal(got['storage'][k], v), k
         assert np.array_equal(got['encodings'], want['encodings'])
         assert got['total_episodes'] == want['total_episodes']
+
+
+def test_tile_table_matches_reference_render_tile():
+    """dcd_isaac_b200.tiles (the 14-tile table behind venv.get_images) == the reference's Grid.render_tile
+    (multigrid.py:159-214) over the restated gym-minigrid rendering helpers, pixel for pixel."""
+    rh.activate()
+    from envs.multigrid import multigrid as mg
+    from gym_minigrid import minigrid
+    from dcd_isaac_b200 import tiles
+    table = tiles.tile_table()
+    objs = [None, minigrid.Wall(), minigrid.Goal()] + [mg.Agent(0, d) for d in range(4)]
+    for code, obj in enumerate(objs):
+        for hl in (False, True):
+            mg.Grid.tile_cache = {}
+            ref = mg.Grid.render_tile(obj, highlight=[np.bool_(hl)], tile_size=32, cell_type=(obj.type if obj else None))
+            img = np.zeros((32, 32, 3), np.uint8)
+            img[:] = ref
+            assert np.array_equal(img, table[2 * code + int(hl)]), (code, hl)
