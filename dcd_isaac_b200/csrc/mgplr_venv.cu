@@ -695,6 +695,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
   const PackedView v = render_packed<SEE, EXT>(R, s, c.W);
   emit_packed_f32<SEE, false>(v, s_obs);
   if (A.o.image_u8) rare_emit_u8(rows, stride, pack(s), c.W, c.see_through, A.o.image_u8, e);
+  if ((flags & MGPLR_F_DONE) && d.err[e]) flags |= MGPLR_F_ERROR;
   rew_out = (float)rew;
   return flags;
 }
@@ -1180,6 +1181,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     const long long pc3 = (RR && d.prof) ? clock64() : 0;
     if (valid) {
       st_hint_u4(&d.hot[e], pack(s), pol_keep);
+      if ((flags & MGPLR_F_DONE) && d.err[e]) flags |= MGPLR_F_ERROR;  // an auto-reset failed: the host raises (mgplr_get_errors)
       write_step_scalars(A, e, s, flags, (float)rew, fin_ret, fin_len);
       if (A.o.image_u8) rare_emit_u8(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.image_u8, e);
       if (RR && dirty) {

@@ -24,7 +24,7 @@ from ._lib import EnvConfig, StepOut, check, ptr
 from .registry import EDITOR_ACTION_SPACES, env_spec
 from .spaces import Box, Discrete
 
-F_DONE, F_TRUNC_KEY, F_TRUNC_VAL, F_GOAL = 1, 2, 4, 8
+F_DONE, F_TRUNC_KEY, F_TRUNC_VAL, F_GOAL, F_ERROR = 1, 2, 4, 8, 16
 
 _NO_INFO = types.MappingProxyType({})   # read-only stand-in for the `{}` info of an env to which nothing happened
 
@@ -121,6 +121,8 @@ class CudaAdversarialVecEnv(object):
         self._h_done = torch.zeros(N * 16, dtype=torch.uint8).pin_memory()  # mgplr_done_record [N]
         self._h_ndone = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._h_done_np = self._h_done.numpy()
+        self._h_flags_np = self._h_flags.numpy()
+        self._h_ndone_np = self._h_ndone.numpy()
         self._done_dtype = np.dtype(_lib.DONE_DTYPE)
         self._step_out = None   # StepOut with the persistent destinations of step_env (built on first use)
         self._tr = None
@@ -414,33 +416,28 @@ class CudaAdversarialVecEnv(object):
                 check(self.L.mgplr_step_env_host(self.h, self._h_action.data_ptr(), int(bool(reset_random)), 0, C.byref(o),
                                                  self._h_flags.data_ptr(), self._h_done.data_ptr(), N, self._h_ndone.data_ptr(),
                                                  self._stream()), 'mgplr_step_env_host')
-            flags = self._h_flags.numpy().copy()
-            nd = int(self._h_ndone[0])
+            flags = self._h_flags_np.copy()
+            nd = int(self._h_ndone_np[0])
             ep_r = ep_l = None
-            if nd:
+            if nd:   # the finished episodes arrive as compact records: scatter them by env
                 rec = self._h_done_np[:nd * 16].view(self._done_dtype)
-                ep_r = np.zeros(N, np.float32)
-                ep_l = np.zeros(N, np.int32)
-                ep_r[rec['env']] = rec['ep_return']
-                ep_l[rec['env']] = rec['ep_length']
+                ep_r, ep_l = dict(zip(rec['env'].tolist(), rec['ep_return'])), dict(zip(rec['env'].tolist(), rec['ep_length']))
         done = (flags & F_DONE) != 0
         infos = LazyInfos([_NO_INFO] * N)
-        if flags.any():
+        if ep_r is not None or flags.any():
             t_now = round(time.time() - self.tstart, 6)
-            for i in np.nonzero(flags & (F_DONE | F_TRUNC_KEY))[0]:
+            for i in np.nonzero(flags & (F_DONE | F_TRUNC_KEY))[0].tolist():
                 info = infos[i]
-                if flags[i] & F_TRUNC_KEY:
-                    info['truncated'] = bool(flags[i] & F_TRUNC_VAL)
+                f = flags[i]
+                if f & F_TRUNC_KEY:
+                    info['truncated'] = bool(f & F_TRUNC_VAL)
                     info['truncated_obs'] = {k: v[i] for k, v in tr.items()}
                     self._step_out = None   # the infos now own these buffers: take fresh ones next step
-                if flags[i] & F_DONE:
+                if f & F_DONE:
                     info['episode'] = {'r': ep_r[i], 'l': ep_l[i], 't': t_now}
-            if (flags & F_DONE).any():
-                self._check_errors_lazily()
+            if (flags & F_ERROR).any():   # an auto-reset failed on the device (the kernel flags it: no extra launch otherwise)
+                self._raise_errors()
         return self._add_full_obs(obs), rew, done, infos
-
-    def _check_errors_lazily(self):
-        self._raise_errors()
 
     def step_env_device(self, action, out, reset_random=False, last_step=0, n_walls=None):
         """Device-resident step: `action` i64 [N] CUDA tensor, `out` a StepOut of raw pointers into rollout storage.

@@ -33,6 +33,7 @@ extern "C" {
 #define MGPLR_F_TRUNC_KEY 2u /* 'truncated' in info (envs/wrappers/time_limit.py:28-31) */
 #define MGPLR_F_TRUNC_VAL 4u /* info['truncated'] is True */
 #define MGPLR_F_GOAL 8u      /* goal reached this step (reward != 0) */
+#define MGPLR_F_ERROR 16u    /* the env finished and has a pending error bit (mgplr_get_errors): the auto-reset failed */
 
 /* AdversarialEnv constructor arguments (envs/multigrid/adversarial.py:67-79) + the registered
  * TimeLimit (envs/registration.py:118-120, envs/wrappers/time_limit.py:15-22). */
