@@ -53,7 +53,7 @@ SYMBOLS = (
     'mgplr_mutate_finalize', 'mgplr_step_env', 'mgplr_step_env_u8', 'mgplr_step_env_host', 'mgplr_step_env_host_u8', 'mgplr_rollout', 'mgplr_rollout_ex', 'mgplr_full_obs', 'mgplr_render_images', 'mgplr_get_encodings',
     'mgplr_get_metrics', 'mgplr_get_agent_state', 'mgplr_get_errors', 'mgplr_peek_rng', 'mgplr_gae',
     'mgplr_discounted_returns', 'mgplr_batched_value_loss',
-    'mgplr_plr_episode_scores', 'mgplr_plr_episode_scores_ex', 'mgplr_plr_sample_weights', 'mgplr_plr_score_weights', 'mgplr_plr_sample_replay',
+    'mgplr_plr_episode_scores', 'mgplr_plr_episode_scores_ex', 'mgplr_plr_sample_weights', 'mgplr_plr_score_weights', 'mgplr_plr_sample_replay', 'mgplr_plr_apply_records',
 )
 
 
@@ -116,6 +116,8 @@ def load():
     L.mgplr_plr_sample_weights.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, i32, f64, vp, vp, vp]
     L.mgplr_plr_score_weights.argtypes = [vp, vp, i32, i32, f64, f64, vp, vp]
     L.mgplr_plr_sample_replay.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, i32, f64, vp, vp, i32, vp, vp]
+    L.mgplr_plr_apply_records.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, f64, f64,
+                                          i32, i32, i32, f64, f64, f64, i32, f64, vp, vp, vp]
     _lib = L
     return L
 

@@ -777,3 +777,272 @@ extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, 
   PCK(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------ sampler bookkeeping
+// LevelSampler.update_with_rollouts after the score reductions: the walk over the episode records in canonical (actor-major,
+// time-minor) order that applies the EWA score update to working seeds and admits staging seeds into the working buffer
+// (level_sampler.py:185-273: update_seed_score, _partial_update_seed_score(_buffer), _next_buffer_index), on the HBM
+// resident buffer arrays.  The walk is order dependent (an admission changes which slot the next one may evict), so it is ONE
+// CTA: thread 0 interprets the record stream from a shared-memory chunk; when a staging seed meets a FULL buffer the whole CTA
+// evaluates argmin(sample_weights()) on the current state (the same device functions as k_sample_weights, so the weights are
+// the bits the host API would get) and hands the slot back.  The rank transform does not re-sort per admission: ranks are
+// kept incrementally -- a slot whose score changed is "dirty" and one pass fixes every rank against the old and new keys of the
+// dirty slots (rank_i = 1 + #{k : key_k before key_i}) -- with a full bitonic sort only when more than kMaxDirty slots changed.
+// Seeds are addressed through a small table of the rollout's distinct seeds (sorted; built by the host from its dict / set
+// views): cur_idx = seed2index entry or -1 (entries are never deleted, level_sampler.py:250), stamp = staging timestamp or -1.
+constexpr int kMaxDirty = 32, kRecChunk = 128;
+
+struct ApplyArgs {
+  const mgplr_episode *rec;
+  const int32_t *n_rec_dev;   // record count on the device (written by the score kernel) or NULL
+  int32_t n_rec, max_rec;
+  const double *pre;          // optional [n_rec][4]: partial score, partial max, partial steps, unused (not-done tails merged by the host)
+  const int64_t *useeds;      // [n_u] sorted distinct seeds
+  int32_t n_u;
+  int32_t *uid;               // [max_rec] scratch: index into useeds or -1
+  int32_t *cur_idx;           // [n_u] in/out
+  const double *stamp;        // [n_u] staging timestamp (seed2timestamp_buffer) or -1
+  int32_t *status;            // [n_u] out: 0 untouched, 1 admitted, 2 rejected (left the staging set either way)
+  int32_t *adm_log;           // [n_u][2] out: (table index, slot) of the admissions, in order
+  int32_t *counters;          // [4]: n admissions, working_seed_buffer_size (in/out), not-done tails seen, records walked
+  double *scores, *stale, *unseen, *grounded;
+  int64_t *seeds;
+  int32_t n_buf;
+  double running_count, alpha, max_coef;
+  int32_t kind;               // 0: record scores, 1: uniform, 2: grounded (MaxMC)
+  int32_t priority;           // 0: replay_support (argmin of sample_weights), 1: lowest score
+  WeightArgs wa;
+  double *w_score, *weights, *table, *rank_score;
+  int32_t *rank;
+};
+
+__global__ void k_record_uid(ApplyArgs a) {
+  const int n = a.n_rec_dev ? min(*a.n_rec_dev, a.max_rec) : a.n_rec;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int64_t s = a.rec[r].seed;
+  int lo = 0, hi = a.n_u;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a.useeds[mid] < s) lo = mid + 1; else hi = mid;
+  }
+  a.uid[r] = (lo < a.n_u && a.useeds[lo] == s) ? lo : -1;
+}
+
+__device__ __forceinline__ bool key_before(double sa, int ia, double sb, int ib) { return sa > sb || (sa == sb && ia > ib); }
+
+__global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  Key *keys = reinterpret_cast<Key *>(sm);
+  __shared__ double red[33];
+  __shared__ mgplr_episode s_rec[kRecChunk];
+  __shared__ int s_uid[kRecChunk];
+  __shared__ int s_req, s_next, s_slot, s_chunk_lo, s_have_slot, s_rank_valid, s_ndirty;
+  __shared__ int s_dirty[kMaxDirty], s_cnt[kMaxDirty];
+  __shared__ double s_old[kMaxDirty], s_new[kMaxDirty];
+  __shared__ double s_min[32];
+  __shared__ int s_arg[32];
+  const int tid = threadIdx.x, N = a.n_buf;
+  const int n = a.n_rec_dev ? min(*a.n_rec_dev, a.max_rec) : a.n_rec;
+  const bool ranked = a.wa.score_transform == 1 && a.priority == 0;
+  if (tid == 0) { s_next = 0; s_chunk_lo = -kRecChunk; s_have_slot = 0; s_rank_valid = 0; s_ndirty = 0; }
+  if (ranked) {
+    const double inv_t = 1.0 / a.wa.temperature;
+    for (int r = tid; r < N; r += blockDim.x) a.table[r] = 1.0 / pow((double)(r + 1), inv_t);
+  }
+  __syncthreads();
+  int n_adm = a.counters[0], filled = a.counters[1], n_tail = 0;   // (meaningful in thread 0)
+  for (;;) {
+    if (tid == 0) {
+      int r = s_next, req = 0;
+      while (r < n) {
+        if (r < s_chunk_lo || r >= s_chunk_lo + kRecChunk) { req = 2; break; }
+        const mgplr_episode e = s_rec[r - s_chunk_lo];
+        const int u = s_uid[r - s_chunk_lo];
+        if (e.cliffhanger == 1 || u < 0) { r++; continue; }                 // cliffhangers are skipped (level_sampler.py:527-528)
+        if (e.cliffhanger == 2) { n_tail++; r++; continue; }                // not-done tail: host bookkeeping (never under the runner)
+        const int steps = e.t_end - e.t_start;
+        const double dn = (double)steps;
+        int idx = a.cur_idx[u];
+        double score = (double)e.mean_score, mx = (double)e.max_score, gv = 0.0;
+        double p_score = 0.0, p_max = -INFINITY, p_steps = 0.0;
+        bool flush = false;  // after_update: what is left of an unfinished episode, scored as it stands (level_sampler.py:580-599)
+        if (a.pre) {
+          p_score = a.pre[4 * (size_t)r]; p_max = a.pre[4 * (size_t)r + 1]; p_steps = a.pre[4 * (size_t)r + 2];
+          flush = a.pre[4 * (size_t)r + 3] != 0.0;
+        }
+        if (flush) { score = 0.0; mx = -INFINITY; }
+        else if (a.kind == 1) { score = 1.0; mx = 1.0; }
+        else if (a.kind == 2) {  // _average_grounded_signed_value_loss (level_sampler.py:351-386) from the episode sums
+          gv = (double)e.reward_sum;
+          if (idx >= 0) gv = fmax(a.grounded[idx], gv);
+          score = ((p_steps + dn) / dn) * (gv - (double)e.value_sum / dn);
+          mx = gv - (double)e.value_min;
+        }
+        const double merged = p_score + (score - p_score) * dn / (p_steps + dn);
+        const bool staged = a.stamp[u] >= 0.0 && a.status[u] == 0;
+        if (staged) {   // _partial_update_seed_score_buffer(done=True), level_sampler.py:228-273
+          int slot;
+          if (filled < N) slot = filled;
+          else if (s_have_slot) { slot = s_slot; s_have_slot = 0; }
+          else { req = 1; break; }
+          if (a.scores[slot] <= merged || a.unseen[slot] > 0.0) {
+            a.unseen[slot] = 0.0;
+            a.seeds[slot] = a.useeds[u];
+            a.cur_idx[u] = slot;
+            a.scores[slot] = merged;
+            a.stale[slot] = a.running_count - a.stamp[u];
+            filled = min(filled + 1, N);
+            if (a.kind == 2 && !flush) a.grounded[slot] = gv;
+            a.status[u] = 1;
+            a.adm_log[2 * n_adm] = u; a.adm_log[2 * n_adm + 1] = slot;
+            n_adm++;
+            idx = slot;
+          } else { a.status[u] = 2; idx = -1; }
+        } else if (idx >= 0) {   // _partial_update_seed_score(done=True), level_sampler.py:193-216
+          a.unseen[idx] = 0.0;
+          const double total = a.max_coef * fmax(p_max, mx) + (1.0 - a.max_coef) * merged;
+          a.scores[idx] = (1.0 - a.alpha) * a.scores[idx] + a.alpha * total;
+          if (a.kind == 2 && !flush) a.grounded[idx] = gv;
+        }
+        if (idx >= 0 && ranked && s_rank_valid) {   // the slot's rank key changed
+          int k = 0;
+          while (k < s_ndirty && s_dirty[k] != idx) k++;
+          if (k == s_ndirty) {
+            if (s_ndirty < kMaxDirty) s_dirty[s_ndirty++] = idx;
+            else s_rank_valid = 0;                   // too many: full sort at the next admission
+          }
+        }
+        r++;
+      }
+      s_next = r; s_req = req;
+    }
+    __syncthreads();
+    const int req = s_req;
+    if (req == 0) break;
+    if (req == 2) {   // next chunk of records into shared memory
+      const int lo = s_next;
+      for (int i = tid; i < kRecChunk; i += blockDim.x)
+        if (lo + i < n) { s_rec[i] = a.rec[lo + i]; s_uid[i] = a.uid[lo + i]; }
+      __syncthreads();
+      if (tid == 0) s_chunk_lo = lo;
+      __syncthreads();
+      continue;
+    }
+    // ---- req == 1: slot = _next_buffer_index on a full buffer (level_sampler.py:218-226), all threads
+    if (a.priority == 0) {
+      if (ranked) {
+        if (!s_rank_valid) {   // full sort (same key order as transform_vals)
+          int n2 = 1;
+          while (n2 < N) n2 <<= 1;
+          for (int i = tid; i < n2; i += blockDim.x) {
+            Key k;
+            k.s = (i < N) ? a.scores[i] : -INFINITY; k.i = (i < N) ? i : -1 - i;
+            keys[i] = k;
+          }
+          __syncthreads();
+          block_sort_desc(keys, n2);
+          for (int r = tid; r < N; r += blockDim.x) { a.rank[keys[r].i] = r + 1; }
+          for (int i = tid; i < N; i += blockDim.x) a.rank_score[i] = a.scores[i];
+          __syncthreads();
+          if (tid == 0) { s_rank_valid = 1; s_ndirty = 0; }
+          __syncthreads();
+        } else if (s_ndirty) {
+          const int D = s_ndirty;
+          if (tid < D) { s_old[tid] = a.rank_score[s_dirty[tid]]; s_new[tid] = a.scores[s_dirty[tid]]; s_cnt[tid] = 0; }
+          __syncthreads();
+          for (int i = tid; i < N; i += blockDim.x) {
+            bool dirty = false;
+            for (int d = 0; d < D; d++) dirty |= (s_dirty[d] == i);
+            const double si = dirty ? a.scores[i] : a.rank_score[i];   // the slot's FINAL key
+            if (!dirty) {
+              int delta = 0;
+              for (int d = 0; d < D; d++)
+                delta += (int)key_before(s_new[d], s_dirty[d], si, i) - (int)key_before(s_old[d], s_dirty[d], si, i);
+              if (delta) a.rank[i] += delta;
+            }
+            for (int d = 0; d < D; d++)   // slots ahead of dirty slot d under the final keys
+              if (s_dirty[d] != i && key_before(si, i, s_new[d], s_dirty[d])) atomicAdd(&s_cnt[d], 1);
+          }
+          __syncthreads();
+          if (tid < D) { a.rank[s_dirty[tid]] = 1 + s_cnt[tid]; a.rank_score[s_dirty[tid]] = s_new[tid]; }
+          __syncthreads();
+          if (tid == 0) s_ndirty = 0;
+          __syncthreads();
+        }
+        for (int i = tid; i < N; i += blockDim.x) a.w_score[i] = a.table[a.rank[i] - 1];
+        __syncthreads();
+        mask_normalise(a.w_score, a.unseen, N, true, red);
+      } else {
+        score_weights(a.scores, a.unseen, N, a.wa, a.w_score, keys, red);
+      }
+      mix_staleness(a.w_score, a.stale, a.unseen, N, a.wa, a.weights, keys, red);
+    }
+    {   // first index of the minimum (numpy argmin)
+      const double *v = a.priority == 0 ? a.weights : a.scores;
+      double best = INFINITY;
+      int arg = 0x7fffffff;
+      for (int i = tid; i < N; i += blockDim.x) {
+        const double x = v[i];
+        if (x < best || (x == best && i < arg)) { best = x; arg = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oa = __shfl_down_sync(0xffffffffu, arg, o);
+        if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+      }
+      if ((tid & 31) == 0) { s_min[tid >> 5] = best; s_arg[tid >> 5] = arg; }
+      __syncthreads();
+      if (tid < 32) {
+        best = (tid < (int)(blockDim.x >> 5)) ? s_min[tid] : INFINITY;
+        arg = (tid < (int)(blockDim.x >> 5)) ? s_arg[tid] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_down_sync(0xffffffffu, best, o);
+          const int oa = __shfl_down_sync(0xffffffffu, arg, o);
+          if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (tid == 0) { s_slot = arg; s_have_slot = 1; }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) { a.counters[0] = n_adm; a.counters[1] = filled; a.counters[2] = n_tail; a.counters[3] = n; }
+}
+
+// host launcher: every pointer is a device pointer; scratch = [4 * n_buf] doubles + [n_buf] int32 owned by the caller
+extern "C" int mgplr_plr_apply_records(const mgplr_episode *records, const int32_t *n_records_dev, int32_t n_records,
+                                       int32_t max_records, const double *pre, const int64_t *table_seeds, int32_t n_table,
+                                       int32_t *table_index, const double *table_stamp, int32_t *table_status,
+                                       int32_t *admission_log, int32_t *counters, int32_t *record_scratch, double *scores,
+                                       double *staleness, double *unseen, double *grounded, int64_t *seeds, int32_t n_buf,
+                                       double running_sample_count, double alpha, double max_score_coef, int32_t score_kind,
+                                       int32_t priority, int32_t score_transform, double temperature, double eps,
+                                       double staleness_coef, int32_t staleness_transform, double staleness_temperature,
+                                       double *scratch_f64, int32_t *scratch_i32, void *stream) {
+  if (!records || !table_seeds || !table_index || !table_stamp || !table_status || !admission_log || !counters || !record_scratch ||
+      !scores || !staleness || !unseen || !seeds || !scratch_f64 || !scratch_i32 || n_buf < 1 || n_buf > kMaxBuf || n_table < 0 ||
+      max_records < 0 || (score_kind == 2 && !grounded))
+    return pfail(MGPLR_E_BADARG, "mgplr_plr_apply_records: bad arguments (seed_buffer_size must be in [1, 8192])");
+  if (int rc = check_transform(score_transform)) return rc;
+  if (int rc = check_transform(staleness_transform)) return rc;
+  ApplyArgs a;
+  a.rec = records; a.n_rec_dev = n_records_dev; a.n_rec = n_records; a.max_rec = max_records; a.pre = pre;
+  a.useeds = table_seeds; a.n_u = n_table; a.uid = record_scratch; a.cur_idx = table_index; a.stamp = table_stamp;
+  a.status = table_status; a.adm_log = admission_log; a.counters = counters;
+  a.scores = scores; a.stale = staleness; a.unseen = unseen; a.grounded = grounded; a.seeds = seeds; a.n_buf = n_buf;
+  a.running_count = running_sample_count; a.alpha = alpha; a.max_coef = max_score_coef; a.kind = score_kind; a.priority = priority;
+  a.wa = WeightArgs{score_transform, staleness_transform, temperature, eps, staleness_coef, staleness_temperature};
+  a.w_score = scratch_f64; a.weights = scratch_f64 + n_buf; a.table = scratch_f64 + 2 * (size_t)n_buf;
+  a.rank_score = scratch_f64 + 3 * (size_t)n_buf; a.rank = scratch_i32;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int upper = n_records_dev ? max_records : n_records;
+  if (upper > 0 && n_table > 0) {
+    k_record_uid<<<(upper + 255) / 256, 256, 0, st>>>(a);
+    PCK(cudaGetLastError());
+  }
+  const size_t smem = sort_smem(n_buf);
+  PCK(cudaFuncSetAttribute(k_apply_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_apply_records<<<1, 1024, smem, st>>>(a);
+  PCK(cudaGetLastError());
+  return 0;
+}

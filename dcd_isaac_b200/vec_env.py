@@ -29,6 +29,41 @@ F_DONE, F_TRUNC_KEY, F_TRUNC_VAL, F_GOAL, F_ERROR = 1, 2, 4, 8, 16
 _NO_INFO = types.MappingProxyType({})   # read-only stand-in for the `{}` info of an env to which nothing happened
 
 
+class _ObsRow(object):
+    """`info['truncated_obs']`: the observation dict of ONE env, `{k: batch[k][i]}`, sliced out of the step's batched
+    truncated-observation tensors only when a key is read (a synchronized time-limit step would otherwise spend ~10 us per env
+    on tensor indexing whether or not anybody looks).  Read-only mapping with the dict methods the runner and
+    RolloutStorage.insert_truncated_obs use (adversarial_runner.py:546-549, algos/storage.py:188-193)."""
+    __slots__ = ('_batch', '_i')
+
+    def __init__(self, batch, i):
+        self._batch, self._i = batch, i
+
+    def __getitem__(self, k):
+        return self._batch[k][self._i]
+
+    def __iter__(self):
+        return iter(self._batch)
+
+    def __len__(self):
+        return len(self._batch)
+
+    def __contains__(self, k):
+        return k in self._batch
+
+    def keys(self):
+        return self._batch.keys()
+
+    def values(self):
+        return [self._batch[k][self._i] for k in self._batch]
+
+    def items(self):
+        return [(k, self._batch[k][self._i]) for k in self._batch]
+
+    def get(self, k, default=None):
+        return self._batch[k][self._i] if k in self._batch else default
+
+
 class LazyInfos(list):
     """The `infos` list of one vector step.  Almost every env's info is `{}` on almost every step, so the untouched
     entries all hold ONE read-only empty mapping and a real dict is only created for an env that finished / was truncated,
@@ -431,7 +466,7 @@ class CudaAdversarialVecEnv(object):
                 f = flags[i]
                 if f & F_TRUNC_KEY:
                     info['truncated'] = bool(f & F_TRUNC_VAL)
-                    info['truncated_obs'] = {k: v[i] for k, v in tr.items()}
+                    info['truncated_obs'] = _ObsRow(tr, i)
                     self._step_out = None   # the infos now own these buffers: take fresh ones next step
                 if f & F_DONE:
                     info['episode'] = {'r': ep_r[i], 'l': ep_l[i], 't': t_now}

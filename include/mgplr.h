@@ -304,6 +304,28 @@ int mgplr_plr_sample_replay(const double *scores, double *staleness, const doubl
                             int32_t staleness_transform, double staleness_temperature, const double *score_weights,
                             const double *u, int32_t n_draws, int32_t *out_index, void *stream);
 
+/* The order-dependent half of LevelSampler.update_with_rollouts (level_sampler.py:185-273: update_seed_score,
+ * _partial_update_seed_score, _partial_update_seed_score_buffer, _next_buffer_index) on the buffer arrays in HBM: one single-CTA
+ * kernel walks `records` (canonical order; n_records_dev = device count written by mgplr_plr_episode_scores, or NULL and
+ * n_records) and applies, per finished non-cliffhanger episode, the EWA update (1-alpha) old + alpha (c max + (1-c) mean) of a
+ * working seed, or the admission of a staging seed: next free slot, else the slot with the least replay support (argmin of
+ * sample_weights on the current state; priority 1: lowest score), replaced iff its score <= the new one, staleness =
+ * running_sample_count - staging timestamp.  score_kind 0: record mean / max, 1: uniform (1, 1), 2: MaxMC from reward_sum /
+ * value_sum / value_min with the per-slot grounded value (level_sampler.py:351-386,529-547).
+ * Seeds are addressed through a table of the rollout's distinct seeds: table_seeds i64 [n_table] sorted, table_index i32 in/out
+ * (seed2index entry or -1), table_stamp f64 (staging timestamp or -1 = not in the staging set), table_status i32 out (1 admitted,
+ * 2 rejected), admission_log i32 [n_table][2] out (table index, slot) in admission order, counters i32 [4] in/out: admissions,
+ * working_seed_buffer_size, not-done tails skipped (left to the host), records walked.  pre f64 [n][4] optional: partial score /
+ * max / steps of a stored tail to merge, flush flag.  record_scratch i32 [max_records], scratch_f64 [4 n_buf], scratch_i32 [n_buf]. */
+int mgplr_plr_apply_records(const mgplr_episode *records, const int32_t *n_records_dev, int32_t n_records, int32_t max_records,
+                            const double *pre, const int64_t *table_seeds, int32_t n_table, int32_t *table_index,
+                            const double *table_stamp, int32_t *table_status, int32_t *admission_log, int32_t *counters,
+                            int32_t *record_scratch, double *scores, double *staleness, double *unseen, double *grounded,
+                            int64_t *seeds, int32_t n_buf, double running_sample_count, double alpha, double max_score_coef,
+                            int32_t score_kind, int32_t priority, int32_t score_transform, double temperature, double eps,
+                            double staleness_coef, int32_t staleness_transform, double staleness_temperature, double *scratch_f64,
+                            int32_t *scratch_i32, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,3 +159,85 @@ def sample_replay(scores, staleness, unseen, u, **kw):
             staleness = staleness + 1
             staleness[i] = 0
     return np.array(idx), staleness
+
+
+class BufferOracle(object):
+    """Sequential restatement of the sampler's buffer bookkeeping for the full-distribution (robust PLR / ACCEL) mode:
+    observe_external_unseen_sample (level_sampler.py:645-659), the per-record score update with staging -> working
+    admission (update_seed_score / _partial_update_seed_score / _partial_update_seed_score_buffer / _next_buffer_index,
+    level_sampler.py:185-273) driven by episode records in the reference's actor-major / time-minor order
+    (_update_with_rollouts, :486-549), for finished episodes (the only kind the runner produces, adversarial_runner.py:530).
+    Test infrastructure: the CUDA kernel k_apply_records is compared with this walk, and this walk is pinned by the recorded
+    reference sessions (tests/test_plr_oracle.py)."""
+
+    def __init__(self, n_buf, strategy='positive_value_loss', alpha=1.0, max_score_coef=0.0, priority='replay_support',
+                 score_transform='rank', temperature=0.3, staleness_coef=0.3, staleness_transform='power',
+                 staleness_temperature=1.0):
+        self.n = n_buf
+        self.strategy, self.alpha, self.coef, self.priority = strategy, alpha, max_score_coef, priority
+        self.wkw = dict(score_transform=score_transform, temperature=temperature, staleness_coef=staleness_coef,
+                        staleness_transform=staleness_transform, staleness_temperature=staleness_temperature)
+        self.seeds = np.zeros(n_buf, np.int64) - 1
+        self.scores = np.zeros(n_buf)
+        self.stale = np.zeros(n_buf)
+        self.unseen = np.ones(n_buf)
+        self.grounded = np.full(n_buf, -np.inf) if strategy.startswith('grounded') else None
+        self.index_of = {}       # seed2index: entries are never deleted (an evicted seed keeps its stale slot, :250)
+        self.stamp = {}          # seed2timestamp_buffer: the staging set
+        self.count = 0           # running_sample_count
+        self.filled = 0          # working_seed_buffer_size
+
+    def observe(self, seeds):
+        for s in seeds:
+            s = int(s)
+            self.count += 1
+            if s in self.stamp or s in set(self.seeds[self.seeds >= 0].tolist()):
+                i = self.index_of.get(s)
+                if i is not None and self.wkw['staleness_coef'] > 0:   # _update_staleness (:601-604)
+                    self.stale = self.stale + 1
+                    self.stale[i] = 0
+            else:
+                self.stamp[s] = self.count
+
+    def _free_slot(self):
+        if self.filled < self.n:
+            return self.filled
+        if self.priority == 'replay_support':
+            return int(np.argmin(sample_weights(self.scores, self.stale, self.unseen, **self.wkw)))
+        return int(np.argmin(self.scores))
+
+    def apply(self, recs):
+        """recs: iterable of dicts with actor, t_start, t_end, seed, mean, max, reward_sum, value_sum, value_min, cliffhanger."""
+        for r in recs:
+            if r['cliffhanger']:
+                continue
+            seed, n = int(r['seed']), int(r['t_end'] - r['t_start'])
+            idx = self.index_of.get(seed)
+            score, mx, gv = float(r['mean']), float(r['max']), None
+            if self.strategy == 'uniform':
+                score = mx = 1.0
+            elif self.grounded is not None:      # _average_grounded_signed_value_loss (:351-386) from the episode sums
+                gv = float(r['reward_sum'])
+                if idx is not None:
+                    gv = max(self.grounded[idx], gv)
+                score = (n / n) * (gv - float(r['value_sum']) / n)
+                mx = gv - float(r['value_min'])
+            merged = 0.0 + (score - 0.0) * n / float(n)
+            if seed in self.stamp:               # staging seed: admission (:228-273)
+                slot = self._free_slot()
+                if self.scores[slot] <= merged or self.unseen[slot] > 0:
+                    self.unseen[slot] = 0.0
+                    self.seeds[slot] = seed
+                    self.index_of[seed] = slot
+                    self.scores[slot] = merged
+                    self.stale[slot] = self.count - self.stamp[seed]
+                    self.filled = min(self.filled + 1, self.n)
+                    if gv is not None:
+                        self.grounded[slot] = gv
+                del self.stamp[seed]
+            elif idx is not None:                # working (or stale-index) seed: EWA update (:193-216)
+                self.unseen[idx] = 0.0
+                total = self.coef * max(float('-inf'), mx) + (1 - self.coef) * merged
+                self.scores[idx] = (1 - self.alpha) * self.scores[idx] + self.alpha * total
+                if gv is not None:
+                    self.grounded[idx] = gv

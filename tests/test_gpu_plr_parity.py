@@ -114,6 +114,8 @@ def test_episode_scores_partial_tails():
         rec['cliffhanger_masks'] = np.ones_like(masks)
         s = LevelSampler([], None, None, num_actors=N, strategy='positive_value_loss', sample_full_distribution=True, seed_buffer_size=64)
         got = s.episode_records(_rollouts_from(rec))
+        if T == 17:   # the grow-only record buffer started smaller than this rollout's record count and was regrown
+            assert len(got) > 4 * N + 64
         want = []
         for e in range(N):
             start = 0
@@ -131,6 +133,132 @@ def test_episode_scores_partial_tails():
         assert np.allclose(got['mean_score'], w[4], rtol=RTOL, atol=1e-7) and np.allclose(got['max_score'], w[5], rtol=0, atol=0)
         assert np.allclose(got['reward_sum'], w[6], rtol=2e-5, atol=1e-6) and np.array_equal(got['value_min'], np.array(w[7], np.float32))
         assert np.array_equal(got['cliffhanger'], np.array(w[8]))
+
+
+def _rec_array(recs):
+    from dcd_isaac_b200._lib import EPISODE_DTYPE
+    a = np.zeros(len(recs), dtype=np.dtype(EPISODE_DTYPE))
+    for i, r in enumerate(recs):
+        a[i] = (r['actor'], r['t_start'], r['t_end'], r['seed'], r['mean'], r['max'], r['reward_sum'], r['value_sum'], r['value_min'],
+                r['cliffhanger'])
+    return a
+
+
+@pytest.mark.parametrize('strategy,alpha,coef,priority,transform', [
+    ('positive_value_loss', 1.0, 0.0, 'replay_support', 'rank'), ('positive_value_loss', 0.7, 0.3, 'replay_support', 'rank'),
+    ('grounded_signed_value_loss', 1.0, 0.0, 'replay_support', 'rank'), ('value_l1', 0.5, 0.0, 'score', 'rank'),
+    ('value_l1', 1.0, 0.0, 'replay_support', 'power'), ('uniform', 1.0, 0.0, 'replay_support', 'rank')])
+def test_device_record_walk_vs_oracle(strategy, alpha, coef, priority, transform):
+    """mgplr_plr_apply_records (the single-CTA walk over the episode records: EWA updates, staging -> working admission with
+    eviction by argmin of sample_weights, incremental ranks) against the sequential oracle that is pinned by the recorded
+    reference sessions (oracle.plr_oracle.BufferOracle): identical buffer after every cycle, bit for bit, incl. seed2index with
+    its stale entries, alpha < 1, max_score_coef > 0, the MaxMC grounded values, ties (scores rounded to 2 digits) and long
+    runs of score changes between admissions (rank refresh by full sort)."""
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    from oracle import plr_oracle as po
+    rs = np.random.RandomState(0)
+    A, T, NB = 96, 64, 48
+    s = LevelSampler([], None, None, num_actors=A, strategy=strategy, max_score_coef=coef, alpha=alpha, score_transform=transform,
+                     temperature=0.3, rho=0.5, staleness_coef=0.3, sample_full_distribution=True, seed_buffer_size=NB,
+                     seed_buffer_priority=priority)
+    o = po.BufferOracle(NB, strategy=strategy, alpha=alpha, max_score_coef=coef, priority=priority, score_transform=transform,
+                        temperature=0.3, staleness_coef=0.3)
+    next_seed = 1
+    for cyc in range(10):
+        new = list(range(next_seed, next_seed + 30))
+        next_seed += 30
+        if cyc % 2 == 0:
+            pool, obs = new, new
+        else:
+            pool, obs = [int(x) for x in o.seeds if x >= 0] + new[:5], new[:5]
+        if cyc == 7:   # evicted seeds come back: stale seed2index entries are exercised
+            pool = pool + [1, 2, 3, 31, 32]
+        s.observe_external_unseen_sample(obs)
+        o.observe(obs)
+        recs = []
+        for a in range(A):
+            t = 0
+            while t < T:
+                t2 = min(T, t + int(rs.randint(1, 25)))
+                recs.append(dict(actor=a, t_start=t, t_end=t2, seed=int(rs.choice(pool)), mean=np.float32(round(rs.rand(), 2)),
+                                 max=np.float32(rs.rand() + 1), reward_sum=np.float32(rs.rand() * (rs.rand() < 0.5)),
+                                 value_sum=np.float32(rs.randn()), value_min=np.float32(rs.randn() - 1),
+                                 cliffhanger=int(t2 == T and rs.rand() < 0.5)))
+                t = t2
+        o.apply(recs)
+        s._apply_episode_records(_rec_array(recs))
+        s.after_update()
+        assert np.array_equal(s.seeds, o.seeds), cyc
+        assert np.array_equal(s.seed_scores, o.scores), cyc
+        assert np.array_equal(s.unseen_seed_weights, o.unseen) and np.array_equal(s.seed_staleness, o.stale), cyc
+        assert s.staging_seed_set == set(o.stamp) and s.working_seed_set == set(int(x) for x in o.seeds if x >= 0), cyc
+        assert s.seed2index == o.index_of and s.working_seed_buffer_size == o.filled, cyc
+        if o.grounded is not None:
+            assert np.array_equal(s.grounded_values, o.grounded), cyc
+    assert o.filled == NB
+
+
+def test_large_actor_count_update_is_cheap():
+    """131 072 actors, a full 4 000-slot buffer, 300 000 finished episodes of working seeds: one upload + one kernel; the
+    last record of a slot wins (alpha = 1)."""
+    import time
+    from dcd_isaac_b200._lib import EPISODE_DTYPE
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    A, NB, n = 131072, 4000, 300000
+    s = LevelSampler([], None, None, num_actors=A, strategy='positive_value_loss', sample_full_distribution=True,
+                     seed_buffer_size=NB)
+    s.seeds[:] = np.arange(1, NB + 1)
+    s.seed2index = {int(k): i for i, k in enumerate(s.seeds)}
+    s.working_seed_set = set(s.seed2index)
+    s.working_seed_buffer_size = NB
+    s.unseen_seed_weights[:] = 0
+    rs = np.random.RandomState(1)
+    rec = np.zeros(n, dtype=np.dtype(EPISODE_DTYPE))
+    rec['actor'] = np.sort(rs.randint(0, A, n))
+    rec['t_end'] = rs.randint(1, 250, n)
+    rec['seed'] = rs.randint(1, NB + 1, n)
+    rec['mean_score'] = rs.rand(n)
+    rec['max_score'] = rs.rand(n)
+    s._apply_episode_records(rec[:10])   # (creates the device context)
+    t = time.time()
+    s._apply_episode_records(rec)
+    dt = time.time() - t
+    assert dt < 2.0, dt
+    last = {}
+    for i in range(n):
+        last[int(rec['seed'][i])] = i
+    for k in (int(rec['seed'][n - 1]), 17, 2000):
+        i = last[k]
+        want = 0.0 + (float(rec['mean_score'][i]) - 0.0) * float(rec['t_end'][i]) / float(rec['t_end'][i])
+        assert s.seed_scores[k - 1] == want
+
+
+def test_not_done_tails_are_carried_and_flushed():
+    """A rollout that does not end in `done` (never produced by the reference runner): the tail's score is carried per
+    (actor, seed) with its step count, merged step-weighted into that actor's next finished episode on the seed
+    (level_sampler.py:199-204), or -- after_update -- scored as it stands (:580-599)."""
+    from dcd_isaac_b200._lib import EPISODE_DTYPE
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    s = LevelSampler([11, 12], None, None, num_actors=2, strategy='value_l1', score_transform='rank', temperature=0.3)
+    rec = np.zeros(3, dtype=np.dtype(EPISODE_DTYPE))
+    rec[0] = (0, 0, 10, 11, 0.5, 0.9, 0, 0, 0, 0)    # actor 0 finishes an episode on seed 11
+    rec[1] = (0, 10, 16, 12, 0.25, 0.4, 0, 0, 0, 2)  # ... and leaves a 6-step tail on seed 12
+    rec[2] = (1, 0, 16, 11, 0.75, 0.8, 0, 0, 0, 2)   # actor 1: one 16-step tail on seed 11
+    s._apply_episode_records(rec)
+    assert s.seed_scores[0] == 0.5 and s.unseen_seed_weights.tolist() == [0.0, 1.0]
+    assert s._tails == {(0, 12): (0.25, np.float32(0.4), 6), (1, 11): (0.75, np.float32(0.8), 16)}
+    nxt = np.zeros(2, dtype=np.dtype(EPISODE_DTYPE))
+    nxt[0] = (0, 0, 4, 12, 1.0, 1.0, 0, 0, 0, 0)     # the 4 remaining steps of actor 0's episode on seed 12
+    nxt[1] = (1, 0, 8, 12, 0.125, 0.5, 0, 0, 0, 0)   # actor 1 plays seed 12: its tail on seed 11 stays
+    s._apply_episode_records(nxt)
+    assert s.seed_scores[1] == 0.125                 # last write wins (alpha = 1): actor 1's episode
+    assert (0, 12) not in s._tails and (1, 11) in s._tails
+    s2 = LevelSampler([11, 12], None, None, num_actors=2, strategy='value_l1', score_transform='rank', temperature=0.3)
+    s2._apply_episode_records(rec)
+    s2._apply_episode_records(nxt[:1])
+    assert s2.seed_scores[1] == 0.25 + (1.0 - 0.25) * 4 / 10.0   # merged over 6 + 4 steps
+    s2.after_update()                                # flushes actor 1's tail on seed 11 as it stands
+    assert s2.seed_scores[0] == 0.75 and s2._tails == {}
 
 
 def test_sample_weights_and_replay_golden():

@@ -61,3 +61,48 @@ def test_logit_and_td_score_functions():
             assert len(rec) == 1 and rec[0]['t_end'] == L
             want = g['%s_%d' % (tag, k)]
             assert np.allclose([rec[0]['mean'], rec[0]['max']], want, rtol=1e-5, atol=1e-6), (strategy, L, rec[0], want)
+
+
+def test_buffer_oracle_reproduces_reference_sessions():
+    """oracle.plr_oracle.BufferOracle (the sequential record walk the CUDA bookkeeping kernel is checked against) replayed
+    over the recorded sessions of the reference LevelSampler: same buffer contents, scores, staleness, staging set after
+    every cycle -- including staging -> working admissions with eviction by replay support."""
+    import glob
+    import gzip
+    import os
+    import pickle
+    from conftest import GOLDEN
+    n_adm = 0
+    for path in sorted(glob.glob(os.path.join(GOLDEN, 'plr_session_*.pkl.gz'))):
+        with gzip.open(path, 'rb') as f:
+            sess = pickle.load(f)
+        tag, strategy, buf, temp, sc, rp, rho, A, T = sess['case']
+        o = po.BufferOracle(buf, strategy=strategy, score_transform=sess['transform'], temperature=temp, staleness_coef=sc)
+        for cyc, rec in enumerate(sess['log']):
+            def drawn(seeds):
+                if sc > 0:
+                    for s in seeds:
+                        o.stale = o.stale + 1
+                        o.stale[o.index_of[int(s)]] = 0
+            if rec['replay']:
+                drawn(rec['sampled'])
+                drawn(rec['resampled'])
+            else:
+                o.observe(rec['inserted'])
+            sq = lambda x: None if x is None else np.asarray(x)[..., 0] if np.asarray(x).ndim == 3 else np.asarray(x)
+            logits = rec.get('action_log_dist')
+            recs = po.episode_scores(sq(rec['masks']), sq(rec['cliffhanger_masks']), sq(rec['returns']), sq(rec['value_preds']),
+                                     sq(rec['rewards']), sq(rec['level_seeds']), strategy,
+                                     logits=None if logits is None else np.asarray(logits), gamma=0.995)
+            before = o.filled
+            o.apply(recs)
+            n_adm += int(o.filled > before)
+            assert np.array_equal(o.seeds, rec['seeds']), (tag, cyc)
+            assert np.array_equal(o.unseen, rec['unseen']), (tag, cyc)
+            assert np.allclose(o.scores, rec['seed_scores'], rtol=1e-5, atol=1e-7), (tag, cyc)
+            assert np.array_equal(o.stale, rec['seed_staleness']), (tag, cyc)
+            assert o.filled == rec['working_size'] and sorted(o.stamp) == list(rec['staging']), (tag, cyc)
+            assert o.count == rec['running_sample_count']
+            if 'grounded_values' in rec:
+                assert np.allclose(o.grounded, rec['grounded_values'], rtol=1e-5)
+    assert n_adm > 5
