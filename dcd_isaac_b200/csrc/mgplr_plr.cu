@@ -558,6 +558,24 @@ __device__ double block_sum(double v, double *red) {
   return r;
 }
 
+// two independent block sums in one pass (each with exactly block_sum's reduction tree, so the bits are block_sum's)
+__device__ double block_sum2(double v, double w2, double *red, double &out2) {
+  __shared__ double red2[33];
+  for (int o = 16; o > 0; o >>= 1) { v += __shfl_down_sync(0xffffffffu, v, o); w2 += __shfl_down_sync(0xffffffffu, w2, o); }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = v; red2[threadIdx.x >> 5] = w2; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double a = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0, b = (threadIdx.x < (blockDim.x >> 5)) ? red2[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+    if (threadIdx.x == 0) { red[32] = a; red2[32] = b; }
+  }
+  __syncthreads();
+  const double r = red[32];
+  out2 = red2[32];
+  __syncthreads();
+  return r;
+}
+
 // _score_transform (level_sampler.py:752-785) for the transforms the shipped configs use:
 //   1 rank:     w = 1 / rank^(1/T), rank 1 = highest value, ties by index (see before())
 //   2 power:    w = (clip(v, 0) + eps)^(1/T)
@@ -577,7 +595,10 @@ __device__ void transform_vals(int transform, const double *vals, int n, double 
     block_sort_desc(keys, n2);
     for (int r = threadIdx.x; r < n; r += blockDim.x) out[keys[r].i] = 1.0 / pow((double)(r + 1), inv_t);
   } else if (transform == 2) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = pow(fmax(vals[i], 0.0) + eps, inv_t);
+    // pow(x, 1.0) == x exactly; the double-precision pow routine is ~300 instructions per element and was what a replay draw /
+    // an admission mostly consisted of with the default staleness temperature 1 (10.7 us per draw at 4 000 slots)
+    if (inv_t == 1.0) { for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = fmax(vals[i], 0.0) + eps; }
+    else for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = pow(fmax(vals[i], 0.0) + eps, inv_t);
   } else {
     for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = 1.0;
   }
@@ -591,8 +612,8 @@ __device__ void mask_normalise(double *w, const double *unseen, int n, bool unif
     const double v = w[i] * (1.0 - unseen[i]);
     w[i] = v; part += v; seen_part += (1.0 - unseen[i]);
   }
-  const double z = block_sum(part, red);
-  const double nseen = block_sum(seen_part, red);
+  double nseen;
+  const double z = block_sum2(part, seen_part, red, nseen);   // (one pass for both sums: same reduction trees, half the barriers)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     if (z > 0) w[i] = w[i] / z;
     else {
@@ -647,18 +668,16 @@ __global__ void __launch_bounds__(1024) k_score_weights(const double *scores, co
   score_weights(scores, unseen, n, a, w_score, keys, red);
 }
 
-static double *g_dscratch = nullptr;
-static size_t g_dscratch_n = 0;
-static int g_dscratch_dev = -1;
+// rank-weight / weight work arrays of the weight and draw kernels: one fixed-size buffer PER DEVICE, allocated on first use
+// (calls on one device are expected on one stream at a time, like every other use of a LevelSampler)
+static double *g_dscratch_dev[kMaxDevices] = {nullptr};
+static double *g_dscratch = nullptr;   // the current device's buffer, set by ensure_dscratch
 static int ensure_dscratch(size_t n) {
   int dev = 0;
   PCK(cudaGetDevice(&dev));
-  if (g_dscratch_dev != dev || g_dscratch_n < n) {
-    if (g_dscratch) cudaFree(g_dscratch);
-    g_dscratch = nullptr;
-    PCK(cudaMalloc((void **)&g_dscratch, n * sizeof(double)));
-    g_dscratch_n = n; g_dscratch_dev = dev;
-  }
+  if (dev < 0 || dev >= kMaxDevices || n > 2 * (size_t)kMaxBuf) return pfail(MGPLR_E_UNSUPPORTED, "device index out of range");
+  if (!g_dscratch_dev[dev]) PCK(cudaMalloc((void **)&g_dscratch_dev[dev], 2 * (size_t)kMaxBuf * sizeof(double)));
+  g_dscratch = g_dscratch_dev[dev];
   return 0;
 }
 static size_t sort_smem(int n) {
@@ -706,16 +725,33 @@ extern "C" int mgplr_plr_sample_weights(const double *scores, const double *stal
 // n_draws sequential draws.  The rank part is fixed across the batch (scores do not change); the staleness
 // part is recomputed after every draw ("all +1, chosen -> 0").  Inverse CDF: np.random.choice(p=w) =
 // cumsum -> /cdf[-1] -> searchsorted(u, side='right') = #{cdf <= u}.
-__global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, double *staleness, const double *unseen, int n,
+// Shared-memory staging of the per-draw working set: every draw is a dozen block-wide stages over the buffer arrays, and with
+// the arrays in HBM each stage pays a global-memory round trip (10.7 us per draw at 4 000 slots; 4 096 replay draws of an ACCEL
+// cycle: 44 ms).  For buffers up to kStageMax slots the staleness / seen-mask / rank-weight / weight arrays live in shared memory
+// for the whole launch (same code, same operation order, same bits) and staleness is written back once at the end.
+constexpr int kStageMax = 4096;
+__global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, double *staleness_g, const double *unseen_g, int n,
                                                         WeightArgs a, const double *u, int n_draws, int32_t *out_index,
-                                                        double *w_rank, double *weights, const double *cached) {
+                                                        double *w_rank_g, double *weights_g, const double *cached, int staged) {
   extern __shared__ __align__(16) uint8_t sm[];
   Key *keys = reinterpret_cast<Key *>(sm);
   __shared__ double red[33];
   __shared__ double wsum[32];
   __shared__ int s_pick;
+  double *w_rank = w_rank_g, *weights = weights_g, *staleness = staleness_g;
+  const double *unseen = unseen_g;
   if (cached) w_rank = const_cast<double *>(cached);
-  else score_weights(scores, unseen, n, a, w_rank, keys, red);
+  else score_weights(scores, unseen_g, n, a, w_rank_g, keys, red);
+  if (staged) {   // layout: [keys scratch (only used by a rank STALENESS transform) | w_rank | weights | staleness | unseen]
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    double *base = reinterpret_cast<double *>(sm + (a.stale_transform == 1 ? (size_t)n2 * sizeof(Key) : 0));
+    double *s_w = base, *s_wt = base + n, *s_st = base + 2 * (size_t)n, *s_un = base + 3 * (size_t)n;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { s_w[i] = w_rank[i]; s_st[i] = staleness_g[i]; s_un[i] = unseen_g[i]; }
+    __syncthreads();
+    w_rank = s_w; weights = s_wt; staleness = s_st; unseen = s_un;
+  }
   const double coef = a.coef;
   // contiguous chunk per thread so the scan is a per-thread serial cumsum + a block scan of chunk sums
   const int per = (n + blockDim.x - 1) / blockDim.x;
@@ -758,6 +794,8 @@ __global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, do
     }
     __syncthreads();
   }
+  if (staged && coef > 0)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) staleness_g[i] = staleness[i];
 }
 
 extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, const double *unseen, int32_t n,
@@ -769,11 +807,14 @@ extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, 
   if (int rc = check_transform(score_transform)) return rc;
   if (int rc = check_transform(staleness_transform)) return rc;
   if (int rc = ensure_dscratch(2 * (size_t)kMaxBuf)) return rc;
-  const size_t smem = sort_smem(n);
+  const int staged = n <= kStageMax;
+  size_t smem = sort_smem(n);
+  if (staged) smem = (staleness_transform == 1 ? smem : 0) + 4 * (size_t)n * sizeof(double);
+  if (!score_weights_in && smem < sort_smem(n)) smem = sort_smem(n);
   PCK(cudaFuncSetAttribute(k_sample_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const WeightArgs a{score_transform, staleness_transform, temperature, eps, staleness_coef, staleness_temperature};
   k_sample_replay<<<1, 1024, smem, (cudaStream_t)stream>>>(scores, staleness, unseen, n, a, u, n_draws, out_index, g_dscratch,
-                                                          g_dscratch + kMaxBuf, score_weights_in);
+                                                          g_dscratch + kMaxBuf, score_weights_in, staged);
   PCK(cudaGetLastError());
   return 0;
 }
@@ -831,7 +872,7 @@ __global__ void k_record_uid(ApplyArgs a) {
 
 __device__ __forceinline__ bool key_before(double sa, int ia, double sb, int ib) { return sa > sb || (sa == sb && ia > ib); }
 
-__global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
+__global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a, int staged) {
   extern __shared__ __align__(16) uint8_t sm[];
   Key *keys = reinterpret_cast<Key *>(sm);
   __shared__ double red[33];
@@ -846,9 +887,24 @@ __global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
   const int n = a.n_rec_dev ? min(*a.n_rec_dev, a.max_rec) : a.n_rec;
   const bool ranked = a.wa.score_transform == 1 && a.priority == 0;
   if (tid == 0) { s_next = 0; s_chunk_lo = -kRecChunk; s_have_slot = 0; s_rank_valid = 0; s_ndirty = 0; }
+  // working set of an admission (every one is a dozen block-wide stages): in shared memory when the buffer fits (kStageMax),
+  // laid out [sort keys, later w_score | weights] [staleness] [unseen] [rank-weight table] [ranks]; else in the HBM scratch
+  double *w_score = a.w_score, *weights = a.weights, *stale = a.stale, *unseen = a.unseen, *table = a.table;
+  int32_t *rank = a.rank;
+  if (staged) {
+    int n2 = 1;
+    while (n2 < N) n2 <<= 1;
+    w_score = reinterpret_cast<double *>(sm);
+    weights = w_score + N;
+    stale = reinterpret_cast<double *>(sm + (size_t)n2 * sizeof(Key));
+    unseen = stale + N;
+    table = unseen + N;
+    rank = reinterpret_cast<int32_t *>(table + N);
+    for (int i = tid; i < N; i += blockDim.x) { stale[i] = a.stale[i]; unseen[i] = a.unseen[i]; }
+  }
   if (ranked) {
     const double inv_t = 1.0 / a.wa.temperature;
-    for (int r = tid; r < N; r += blockDim.x) a.table[r] = 1.0 / pow((double)(r + 1), inv_t);
+    for (int r = tid; r < N; r += blockDim.x) table[r] = 1.0 / pow((double)(r + 1), inv_t);
   }
   __syncthreads();
   int n_adm = a.counters[0], filled = a.counters[1], n_tail = 0;   // (meaningful in thread 0)
@@ -876,22 +932,23 @@ __global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
         else if (a.kind == 2) {  // _average_grounded_signed_value_loss (level_sampler.py:351-386) from the episode sums
           gv = (double)e.reward_sum;
           if (idx >= 0) gv = fmax(a.grounded[idx], gv);
-          score = ((p_steps + dn) / dn) * (gv - (double)e.value_sum / dn);
-          mx = gv - (double)e.value_min;
+          score = __dmul_rn(__ddiv_rn(__dadd_rn(p_steps, dn), dn), __dsub_rn(gv, __ddiv_rn((double)e.value_sum, dn)));
+          mx = __dsub_rn(gv, (double)e.value_min);
         }
-        const double merged = p_score + (score - p_score) * dn / (p_steps + dn);
+        // (explicitly rounded operations: an FMA contraction would round differently from the reference's Python floats)
+        const double merged = __dadd_rn(p_score, __ddiv_rn(__dmul_rn(__dsub_rn(score, p_score), dn), __dadd_rn(p_steps, dn)));
         const bool staged = a.stamp[u] >= 0.0 && a.status[u] == 0;
         if (staged) {   // _partial_update_seed_score_buffer(done=True), level_sampler.py:228-273
           int slot;
           if (filled < N) slot = filled;
           else if (s_have_slot) { slot = s_slot; s_have_slot = 0; }
           else { req = 1; break; }
-          if (a.scores[slot] <= merged || a.unseen[slot] > 0.0) {
-            a.unseen[slot] = 0.0;
+          if (a.scores[slot] <= merged || unseen[slot] > 0.0) {
+            unseen[slot] = 0.0;
             a.seeds[slot] = a.useeds[u];
             a.cur_idx[u] = slot;
             a.scores[slot] = merged;
-            a.stale[slot] = a.running_count - a.stamp[u];
+            stale[slot] = __dsub_rn(a.running_count, a.stamp[u]);
             filled = min(filled + 1, N);
             if (a.kind == 2 && !flush) a.grounded[slot] = gv;
             a.status[u] = 1;
@@ -900,9 +957,9 @@ __global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
             idx = slot;
           } else { a.status[u] = 2; idx = -1; }
         } else if (idx >= 0) {   // _partial_update_seed_score(done=True), level_sampler.py:193-216
-          a.unseen[idx] = 0.0;
-          const double total = a.max_coef * fmax(p_max, mx) + (1.0 - a.max_coef) * merged;
-          a.scores[idx] = (1.0 - a.alpha) * a.scores[idx] + a.alpha * total;
+          unseen[idx] = 0.0;
+          const double total = __dadd_rn(__dmul_rn(a.max_coef, fmax(p_max, mx)), __dmul_rn(__dsub_rn(1.0, a.max_coef), merged));
+          a.scores[idx] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, a.alpha), a.scores[idx]), __dmul_rn(a.alpha, total));
           if (a.kind == 2 && !flush) a.grounded[idx] = gv;
         }
         if (idx >= 0 && ranked && s_rank_valid) {   // the slot's rank key changed
@@ -942,7 +999,7 @@ __global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
           }
           __syncthreads();
           block_sort_desc(keys, n2);
-          for (int r = tid; r < N; r += blockDim.x) { a.rank[keys[r].i] = r + 1; }
+          for (int r = tid; r < N; r += blockDim.x) { rank[keys[r].i] = r + 1; }
           for (int i = tid; i < N; i += blockDim.x) a.rank_score[i] = a.scores[i];
           __syncthreads();
           if (tid == 0) { s_rank_valid = 1; s_ndirty = 0; }
@@ -959,27 +1016,27 @@ __global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
               int delta = 0;
               for (int d = 0; d < D; d++)
                 delta += (int)key_before(s_new[d], s_dirty[d], si, i) - (int)key_before(s_old[d], s_dirty[d], si, i);
-              if (delta) a.rank[i] += delta;
+              if (delta) rank[i] += delta;
             }
             for (int d = 0; d < D; d++)   // slots ahead of dirty slot d under the final keys
               if (s_dirty[d] != i && key_before(si, i, s_new[d], s_dirty[d])) atomicAdd(&s_cnt[d], 1);
           }
           __syncthreads();
-          if (tid < D) { a.rank[s_dirty[tid]] = 1 + s_cnt[tid]; a.rank_score[s_dirty[tid]] = s_new[tid]; }
+          if (tid < D) { rank[s_dirty[tid]] = 1 + s_cnt[tid]; a.rank_score[s_dirty[tid]] = s_new[tid]; }
           __syncthreads();
           if (tid == 0) s_ndirty = 0;
           __syncthreads();
         }
-        for (int i = tid; i < N; i += blockDim.x) a.w_score[i] = a.table[a.rank[i] - 1];
+        for (int i = tid; i < N; i += blockDim.x) w_score[i] = table[rank[i] - 1];
         __syncthreads();
-        mask_normalise(a.w_score, a.unseen, N, true, red);
+        mask_normalise(w_score, unseen, N, true, red);
       } else {
-        score_weights(a.scores, a.unseen, N, a.wa, a.w_score, keys, red);
+        score_weights(a.scores, unseen, N, a.wa, w_score, keys, red);
       }
-      mix_staleness(a.w_score, a.stale, a.unseen, N, a.wa, a.weights, keys, red);
+      mix_staleness(w_score, stale, unseen, N, a.wa, weights, keys, red);
     }
     {   // first index of the minimum (numpy argmin)
-      const double *v = a.priority == 0 ? a.weights : a.scores;
+      const double *v = a.priority == 0 ? weights : a.scores;
       double best = INFINITY;
       int arg = 0x7fffffff;
       for (int i = tid; i < N; i += blockDim.x) {
@@ -1005,6 +1062,10 @@ __global__ void __launch_bounds__(1024) k_apply_records(ApplyArgs a) {
       }
       __syncthreads();
     }
+  }
+  if (staged) {
+    __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x) { a.stale[i] = stale[i]; a.unseen[i] = unseen[i]; }
   }
   if (tid == 0) { a.counters[0] = n_adm; a.counters[1] = filled; a.counters[2] = n_tail; a.counters[3] = n; }
 }
@@ -1040,9 +1101,10 @@ extern "C" int mgplr_plr_apply_records(const mgplr_episode *records, const int32
     k_record_uid<<<(upper + 255) / 256, 256, 0, st>>>(a);
     PCK(cudaGetLastError());
   }
-  const size_t smem = sort_smem(n_buf);
+  const int staged = n_buf <= kStageMax && staleness_transform != 1;  // (a rank STALENESS transform sorts in the aliased key region)
+  const size_t smem = sort_smem(n_buf) + (staged ? (size_t)n_buf * (3 * sizeof(double) + sizeof(int32_t)) : 0);
   PCK(cudaFuncSetAttribute(k_apply_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_apply_records<<<1, 1024, smem, st>>>(a);
+  k_apply_records<<<1, 1024, smem, st>>>(a, staged);
   PCK(cudaGetLastError());
   return 0;
 }

@@ -12,6 +12,7 @@ One JSON object per line.   python tools/bench_configs.py [--envs 4096]
 """
 import argparse
 import json
+import time
 import os
 import sys
 
@@ -117,25 +118,41 @@ def accel(N, T, NB=4000):
     st = DeviceRolloutStorage(T, N)
     st.value_preds.copy_(torch.rand(T + 1, N, 1, device='cuda', generator=g))
 
-    def cycle():
-        seeds = s.sample_replay_levels(N)
-        levels = [store.get_level(int(x)) for x in seeds]
-        v.reset_to_level_batch(levels)
+    phases = {}
+
+    def ph(name, fn, profile):
+        if not profile:
+            return fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        phases[name] = phases.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
+
+    def cycle(profile=False):
+        # replay: sample N levels, load them, roll out, update the sampler (adversarial_runner.py:462-466,497-622)
+        seeds = ph('sample_replay_levels', lambda: s.sample_replay_levels(N), profile)
+        levels = ph('store.get_level', lambda: [store.get_level(int(x)) for x in seeds], profile)
+        ph('reset_to_level_batch', lambda: v.reset_to_level_batch(levels), profile)
         st.level_seeds.copy_(torch.as_tensor(np.asarray(seeds, dtype=np.int32), device='cuda').view(1, N, 1).expand(T, N, 1))
-        student_rollout(v, st, acts)
-        s.update_with_rollouts(st)
-        s.after_update()
-        v.mutate_level(5)
-        child = store.insert([e.tobytes() for e in v.get_encodings()], parent_seeds=[int(x) for x in seeds])
+        ph('student_rollout', lambda: student_rollout(v, st, acts), profile)
+        ph('update_with_rollouts', lambda: (s.update_with_rollouts(st), s.after_update()), profile)
+        # ACCEL: mutate the replayed levels, insert the children, evaluate them (adversarial_runner.py:455-461,756-794)
+        ph('mutate_level', lambda: v.mutate_level(5), profile)
+        enc = ph('get_encodings', lambda: [e.tobytes() for e in v.get_encodings()], profile)
+        child = ph('store.insert', lambda: store.insert(enc, parent_seeds=[int(x) for x in seeds]), profile)
+        ph('observe_unseen', lambda: s.observe_external_unseen_sample(child), profile)
         st.level_seeds.copy_(torch.as_tensor(np.asarray(child, dtype=np.int32), device='cuda').view(1, N, 1).expand(T, N, 1))
-        student_rollout(v, st, acts)
-        s.update_with_rollouts(st)
-        s.after_update()
-        store.reconcile_seeds(s.working_seed_set)
+        ph('student_rollout', lambda: student_rollout(v, st, acts), profile)
+        ph('update_with_rollouts (admissions)', lambda: (s.update_with_rollouts(st), s.after_update()), profile)
+        ph('reconcile', lambda: store.reconcile_seeds(s.working_seed_set), profile)
 
     ms = timed(cycle, reps=2, warm=1)
+    cycle(True)
     print(json.dumps({'config': 'configs[3] ACCEL, MultiGrid-GoalLastVariableBlocksAdversarialEnv-Edit-v0, %d envs, buffer %d, replay + %d-edit mutation, 2 x T=%d rollouts' % (N, NB, 5, T),
-                      'ms_per_cycle': ms, 'agent_env_steps_per_s': 2 * T * N / (ms * 1e-3)}), flush=True)
+                      'ms_per_cycle': ms, 'agent_env_steps_per_s': 2 * T * N / (ms * 1e-3),
+                      'phase_ms': {k: round(x, 3) for k, x in phases.items()}}), flush=True)
     v.close()
 
 
