@@ -54,6 +54,7 @@ SYMBOLS = (
     'mgplr_get_metrics', 'mgplr_get_agent_state', 'mgplr_get_errors', 'mgplr_peek_rng', 'mgplr_gae',
     'mgplr_discounted_returns', 'mgplr_batched_value_loss',
     'mgplr_plr_episode_scores', 'mgplr_plr_episode_scores_ex', 'mgplr_plr_sample_weights', 'mgplr_plr_score_weights', 'mgplr_plr_sample_replay', 'mgplr_plr_apply_records',
+    'mgplr_wide_create', 'mgplr_wide_destroy', 'mgplr_wide_load_levels', 'mgplr_wide_step', 'mgplr_wide_get_encodings',
 )
 
 
@@ -118,6 +119,12 @@ def load():
     L.mgplr_plr_sample_replay.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, i32, f64, vp, vp, i32, vp, vp]
     L.mgplr_plr_apply_records.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f64, f64, f64,
                                           i32, i32, i32, f64, f64, f64, i32, f64, vp, vp, vp]
+    L.mgplr_wide_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
+    L.mgplr_wide_destroy.argtypes = [vp]
+    L.mgplr_wide_destroy.restype = None
+    L.mgplr_wide_load_levels.argtypes = [vp, vp, vp, i32, i32, C.POINTER(StepOut), vp]
+    L.mgplr_wide_step.argtypes = [vp, vp, C.POINTER(StepOut), vp]
+    L.mgplr_wide_get_encodings.argtypes = [vp, vp, vp]
     _lib = L
     return L
 

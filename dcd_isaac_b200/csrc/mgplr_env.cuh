@@ -263,7 +263,7 @@ struct RngSlow {
 };
 
 // MT19937 init_by_array for one env (RandomState.seed([lo, hi])), SoA state.
-__device__ __noinline__ void mt_seed(const Dev &d, int e, uint32_t k0, uint32_t k1, int klen) {
+static __device__ __noinline__ void mt_seed(const Dev &d, int e, uint32_t k0, uint32_t k1, int klen) {
   uint32_t *mt = d.mt;
   uint32_t prev = 19650218u;
   mt[mt_at(e, 0)] = prev;
@@ -308,7 +308,7 @@ __device__ __forceinline__ bool is_empty(const Rows &R, const Env &e, int x, int
 }
 
 // AdversarialEnv._gen_grid (adversarial.py:166-172): empty grid + wall_rect border.
-__device__ inline void gen_grid(const Rows &R, int W) {
+static __device__ inline void gen_grid(const Rows &R, int W) {
   const uint32_t full = (W >= 32) ? 0xffffffffu : ((1u << W) - 1u);
   const uint32_t mid = 1u | (1u << (W - 1));
   R.set(0, full);
@@ -377,7 +377,7 @@ __device__ __forceinline__ int flood_fill(const Rows &R, int W, int sx, int sy, 
 
 // reset_metrics + compute_metrics (adversarial.py:184-192,407-447): interior wall count, Manhattan
 // distance, and reachability / hop count by a bit-parallel flood fill over the interior rows.
-__device__ __noinline__ int4 compute_metrics(const Rows &R, const Env &e, int W, bool do_reset) {
+static __device__ __noinline__ int4 compute_metrics(const Rows &R, const Env &e, int W, bool do_reset) {
   int4 m;
   const int unreachable = (W - 2) * (W - 2) + 1;
   const uint32_t interior = ((W >= 32) ? 0xffffffffu : ((1u << W) - 1u)) & ~1u & ~(1u << (W - 1));
@@ -655,7 +655,7 @@ __device__ __forceinline__ bool coop_place_random(const Rows &R, int gx, int gy,
 
 // All 32 lanes call this with warp-uniform arguments; `R` is env `env`'s row column in shared memory.  Returns the
 // new hot record (uniform) and writes adv / metrics / error flags of the env from lane 0.
-__device__ __noinline__ uint4 coop_reset_random(Dev d, uint32_t *col, int stride, uint4 hot, int env, int n_walls, int lane) {
+static __device__ __noinline__ uint4 coop_reset_random(Dev d, uint32_t *col, int stride, uint4 hot, int env, int n_walls, int lane) {
   const Cfg &c = d.c;
   const int W = c.W;
   const Rows R{col, stride};
@@ -880,7 +880,7 @@ __device__ __forceinline__ uint32_t *cand_record(const Dev &d, int e, uint32_t e
 // applies a committed record's words to the MT state when it commits), every reset bumps the env's level epoch and
 // stores a fresh speculation word, records and validity bits are per epoch parity, and jobs live for one launch --
 // whatever a job computed from a torn state lands on the parity that is no longer consulted (spec_valid_bit).
-__device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *scr /* 1024 words of shared memory */) {
+static __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *scr /* 1024 words of shared memory */) {
   const Cfg &c = d.c;
   const uint32_t job = jb.x;
   const int e = (int)(job >> 8), k = (int)((job >> 7) & 1u);
@@ -997,7 +997,7 @@ struct FlyRng {
 };
 
 // one candidate per LANE; `col` = this lane's column of a [W][32] shared-memory scratch (the level under construction)
-__device__ __noinline__ void rr_regen_job_lane(Dev d, uint2 jb, uint32_t *col) {
+static __device__ __noinline__ void rr_regen_job_lane(Dev d, uint2 jb, uint32_t *col) {
   const Cfg &c = d.c;
   const uint32_t job = jb.x;
   const int e = (int)(job >> 8), k = (int)((job >> 7) & 1u);
@@ -1156,16 +1156,18 @@ struct PackedView {
   int goal;       // vx*5+vy of the goal if it is in view and visible, else -1
 };
 
+// (W = number of rows; Wc = number of columns a row word holds, W unless the caller hands in a window of a wider grid)
 template <bool SEE_THROUGH, typename EXT>
-__device__ __forceinline__ PackedView render_packed(const Rows &R, const Env &e, int W) {
+__device__ __forceinline__ PackedView render_packed(const Rows &R, const Env &e, int W, int Wc = -1) {
   constexpr int PAD = 4;
+  if (Wc < 0) Wc = W;
   const int d = e.adir;
   const bool vertical = d & 1, mirrored = d < 2;
   const int base = (d == 3) ? e.ay - 4 : (d == 1) ? e.ay : e.ay + 2;
   const int step = vertical ? 1 : -1;
   const int off = ((d == 0) ? e.ax : (d == 2) ? e.ax - 4 : e.ax - 2) + PAD;
   const EXT ones = ~(EXT)0;
-  const EXT border = ((EXT)15) | (ones << (W + PAD));
+  const EXT border = ((EXT)15) | (ones << (Wc + PAD));
   uint32_t X = 0;
 #pragma unroll
   for (int k = 0; k < kV; k++) {

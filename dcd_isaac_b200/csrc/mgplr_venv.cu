@@ -365,17 +365,18 @@ __global__ void k_load_levels_at(Dev d, const uint8_t *enc, const int32_t *env_i
   Env s = unpack(d.hot[e]);
   const uint8_t *src = enc + (size_t)k * W * W * 3;
   s.gx = s.gy = s.sx = s.sy = kNone;
+  int enc_dir = 0;
   for (int y = 0; y < W; y++) {
     uint32_t row = 0;
     for (int x = 0; x < W; x++) {
       const uint8_t t = src[((size_t)x * W + y) * 3];
       if (t == 2) row |= 1u << x;
       else if (t == 8) { s.gx = x; s.gy = y; }
-      else if (t == 10) { s.sx = x; s.sy = y; }
+      else if (t == 10) { s.sx = x; s.sy = y; enc_dir = src[((size_t)x * W + y) * 3 + 2] & 3; }
     }
     R.set(y, row);
   }
-  s.sdir = start_dir & 3;
+  s.sdir = (start_dir < 0 ? enc_dir : start_dir) & 3;   // start_dir < 0: the direction stored in the encoding's agent cell
   s.pending = 0;
   s.ep_ret = 0.f; s.ep_len = 0;
   spec_invalidate(d, e);

@@ -5,7 +5,8 @@ env's own `numpy.random.RandomState`, which is the very object the reference dra
 `choice` / `shuffle` / `randint` streams are the reference's by construction; stepping and rendering are the same CUDA
 kernels as every other MultiGrid env, the regenerated levels are uploaded with mgplr_load_levels_at.
 
-PerfectMazeLarge / XL (51 and 101 cells wide) exceed the 32-column bit-plane and raise NotImplementedError.
+PerfectMazeLarge / XL (51 and 101 cells wide) exceed the 32-column bit-plane of the main path: CudaWideMSTMazeVecEnv runs
+them on the wide evaluation kernels (csrc/mgplr_wide.cu: rows of 128 columns, the same view code), same host generator.
 """
 import ctypes as C
 
@@ -120,11 +121,12 @@ class CudaMSTMazeVecEnv(CudaAdversarialVecEnv):
             raise KeyError('No registered env with id: %s' % env_name)
         size = MST_MAZES[env_name]
         if size > 32:
-            raise NotImplementedError('%s is %d cells wide: wider than the 32-column bit-plane' % (env_name, size))
+            raise ValueError('%s is %d cells wide: use CudaWideMSTMazeVecEnv (eval_envs.make_eval_venv picks it)' % (env_name, size))
         spec = dict(n_clutter=0, size=size, choose_goal_last=True, see_through_walls=True, max_steps=2 * size * size,
                     max_episode_steps=32767, resample_n_clutter=False, editor_actions='walls_none_agent_goal',
                     fixed_environment=False)
         super().__init__(env_name, num_envs, device=device, spec=spec, full_obs=full_obs)
+        self.start_dir = 0     # place_agent_at_pos(rand_dir=True) forces direction 0 (multigrid.py:668-672)
         self.hosts = [MSTMazeHost(size) for _ in range(num_envs)]
         self._upload(list(range(num_envs)), [h.first for h in self.hosts])  # the maze built by the constructor's reset()
 
@@ -149,8 +151,8 @@ class CudaMSTMazeVecEnv(CudaAdversarialVecEnv):
         enc = torch.from_numpy(np.ascontiguousarray(np.stack(encs))).to(self.device)
         idx = torch.tensor(envs, dtype=torch.int32, device=self.device)
         o = self._out(obs) if obs is not None else self._out()
-        check(self.L.mgplr_load_levels_at(self.h, ptr(enc), ptr(idx), len(envs), 0, C.byref(o), self._stream()),
-              'mgplr_load_levels_at')
+        check(self.L.mgplr_load_levels_at(self.h, ptr(enc), ptr(idx), len(envs), getattr(self, 'start_dir', 0), C.byref(o),
+                                          self._stream()), 'mgplr_load_levels_at')
         self._raise_errors()
 
     def reset(self):
@@ -179,3 +181,130 @@ class CudaMSTMazeVecEnv(CudaAdversarialVecEnv):
 
     def get_max_episode_steps(self):
         return None
+
+
+class CudaWideMSTMazeVecEnv(object):
+    """PerfectMazeLarge / PerfectMazeXL (51 / 101 cells wide, mst_maze.py:128-136) with the evaluator's API (eval.py:206-329:
+    `reset()`, `step(action)` with the worker's auto-reset, VecMonitor episode infos, preprocessed float32 observations) on the
+    wide evaluation kernels (mgplr_wide_*).  Same host generator as the narrow mazes."""
+
+    def __init__(self, env_name, num_envs, device='cuda:0', full_obs=False):
+        import time
+        from . import _lib
+        from .spaces import Box, Discrete
+        if env_name not in MST_MAZES:
+            raise KeyError('No registered env with id: %s' % env_name)
+        if full_obs:
+            raise NotImplementedError('full_obs (use_global_policy) is not built for the wide mazes')
+        self.env_name, self.num_envs, self.device = env_name, int(num_envs), torch.device(device)
+        if self.device.type != 'cuda' or not torch.cuda.is_available():
+            raise _lib.MgplrError('CudaWideMSTMazeVecEnv needs a CUDA device (no CPU fallback)')
+        self.W = MST_MAZES[env_name]
+        self.max_steps = 2 * self.W * self.W
+        self.L = _lib.load()
+        h = C.c_void_p()
+        torch.cuda.set_device(self.device)
+        check(self.L.mgplr_wide_create(self.W, self.max_steps, self.num_envs, self.device.index or 0, C.byref(h)), 'mgplr_wide_create')
+        self.h, self.closed, self.tstart = h, False, time.time()
+        self.observation_space = {'image': Box(0, 255, (3, 5, 5), 'uint8'), 'direction': Box(0, 3, (1,), 'uint8')}
+        self.action_space = Discrete(7)
+        N = self.num_envs
+        self._flags = torch.zeros(N, dtype=torch.uint8, device=self.device)
+        self._ep_r = torch.zeros(N, dtype=torch.float32, device=self.device)
+        self._ep_l = torch.zeros(N, dtype=torch.int32, device=self.device)
+        self.seed_values = [None] * N
+        self.hosts = [MSTMazeHost(self.W) for _ in range(N)]
+        self._upload(list(range(N)), [h_.first for h_ in self.hosts])
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _new_obs(self):
+        N = self.num_envs
+        return {'image': torch.empty(N, 3, 5, 5, dtype=torch.float32, device=self.device),
+                'direction': torch.empty(N, 1, dtype=torch.float32, device=self.device)}
+
+    def _out(self, obs, **kw):
+        from ._lib import StepOut
+        o = StepOut()
+        if obs is not None:
+            o.image, o.direction = ptr(obs['image']), ptr(obs['direction'])
+        for k, v in kw.items():
+            setattr(o, k, ptr(v))
+        return o
+
+    def set_seed(self, seeds):
+        seeds = list(seeds)
+        assert len(seeds) == self.num_envs
+        for h, s in zip(self.hosts, seeds):
+            h.seed(s)
+        self.seed_values = seeds
+        return [[s] for s in seeds]
+
+    def seed(self, seed, index):
+        self.hosts[index].seed(seed)
+        self.seed_values[index] = seed
+        return [seed]
+
+    def get_seed(self):
+        return list(self.seed_values)
+
+    def _upload(self, envs, encs=None, obs=None):
+        if encs is None:
+            encs = [self.hosts[i].gen() for i in envs]
+        enc = torch.from_numpy(np.ascontiguousarray(np.stack(encs))).to(self.device)
+        idx = torch.tensor(envs, dtype=torch.int32, device=self.device)
+        o = self._out(obs)
+        check(self.L.mgplr_wide_load_levels(self.h, ptr(enc), ptr(idx), len(envs), 0, C.byref(o), self._stream()),
+              'mgplr_wide_load_levels')
+
+    def reset(self):
+        """MultiGridEnv.reset on every env: a NEW maze each time (mst_maze.py:97-99)."""
+        obs = self._new_obs()
+        self._upload(list(range(self.num_envs)), obs=obs)
+        return obs
+
+    def step(self, action):
+        """venv.step(action): transition, VecMonitor episode info; a finished env gets its next maze (the worker's auto-reset,
+        parallel_wrappers.py:20-25) after the respawn draws agent_is_done makes on the old one when the goal was reached."""
+        import time
+        from .vec_env import LazyInfos, _NO_INFO
+        N = self.num_envs
+        a = torch.as_tensor(action).reshape(-1).to(torch.int64).to(self.device).contiguous()
+        obs = self._new_obs()
+        rew = torch.empty(N, 1, dtype=torch.float32, device=self.device)
+        o = self._out(obs, reward=rew, flags=self._flags, ep_return=self._ep_r, ep_length=self._ep_l)
+        check(self.L.mgplr_wide_step(self.h, ptr(a), C.byref(o), self._stream()), 'mgplr_wide_step')
+        flags = self._flags.cpu().numpy()
+        done = (flags & F_DONE) != 0
+        infos = LazyInfos([_NO_INFO] * N)
+        fin = np.nonzero(done)[0].tolist()
+        if fin:
+            ep_r, ep_l = self._ep_r.cpu().numpy(), self._ep_l.cpu().numpy()
+            t_now = round(time.time() - self.tstart, 6)
+            for i in fin:
+                infos[i]['episode'] = {'r': ep_r[i], 'l': ep_l[i], 't': t_now}
+                if flags[i] & F_GOAL:
+                    self.hosts[i].respawn()
+            self._upload(fin, obs=obs)
+        return obs, rew, done, infos
+
+    def get_encodings(self):
+        enc = torch.empty(self.num_envs, self.W, self.W, 3, dtype=torch.uint8, device=self.device)
+        check(self.L.mgplr_wide_get_encodings(self.h, ptr(enc), self._stream()), 'mgplr_wide_get_encodings')
+        return [e for e in enc.cpu().numpy()]
+
+    def get_max_episode_steps(self):
+        return None
+
+    def close(self):
+        if not self.closed and getattr(self, 'h', None):
+            self.L.mgplr_wide_destroy(self.h)
+            self.h = None
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -127,6 +127,9 @@ int mgplr_load_levels(mgplr_venv *v, const uint8_t *enc, int32_t n_levels, const
 int mgplr_load_levels_at(mgplr_venv *v, const uint8_t *enc, const int32_t *env_index, int32_t n, int32_t start_dir,
                          const mgplr_step_out *out, void *stream);
 
+/* (start_dir < 0 in mgplr_load_levels_at: every env starts facing the direction stored in its encoding's agent cell -- envs
+ * whose generator also draws the start direction, envs/multigrid/fourrooms.py:71-78.) */
+
 /* Same, action-string form: locs i32 [n][len] (device), replayed through step_adversary. */
 int mgplr_reset_to_actions(mgplr_venv *v, const int32_t *locs, int32_t len, const int32_t *index, int32_t n,
                            const mgplr_step_out *out, void *stream);
@@ -325,6 +328,23 @@ int mgplr_plr_apply_records(const mgplr_episode *records, const int32_t *n_recor
                             int32_t score_kind, int32_t priority, int32_t score_transform, double temperature, double eps,
                             double staleness_coef, int32_t staleness_transform, double staleness_temperature, double *scratch_f64,
                             int32_t *scratch_i32, void *stream);
+
+/* ---- mazes wider than 32 columns: PerfectMazeLarge (51) / PerfectMazeXL (101), envs/multigrid/mst_maze.py:128-136, part of
+ * eval.py's zero-shot maze benchmark (eval.py:340-349).  Evaluation-only: one thread per env, rows of 128 columns, the same
+ * view code as the main path; MultiGridEnv.step semantics without a TimeLimit (the mazes are registered without one). ---- */
+typedef struct mgplr_wide mgplr_wide;
+int mgplr_wide_create(int32_t width, int32_t max_steps, int32_t num_envs, int32_t device, mgplr_wide **out);
+void mgplr_wide_destroy(mgplr_wide *h);
+/* MultiGridEnv.reset() of n envs with host-generated levels (mst_maze.py:97-115): enc u8 [n][W][W][3] (device), env_index i32
+ * [n] (device) or NULL = envs 0..n-1; start_dir as in mgplr_load_levels_at.  Writes out->image / out->direction rows of the
+ * loaded envs (full-N arrays). */
+int mgplr_wide_load_levels(mgplr_wide *h, const uint8_t *enc, const int32_t *env_index, int32_t n, int32_t start_dir,
+                           const mgplr_step_out *out, void *stream);
+/* venv.step(action) (multigrid.py:943-975 + vec_monitor.py:60-85 + obs_wrappers.py:104-110): action i64 [N] (device); fills
+ * out->image, direction, reward, flags, ep_return, ep_length.  A finished env is put back at its start; the caller then
+ * uploads its next maze (the worker's auto-reset, parallel_wrappers.py:20-25). */
+int mgplr_wide_step(mgplr_wide *h, const int64_t *action, const mgplr_step_out *out, void *stream);
+int mgplr_wide_get_encodings(mgplr_wide *h, uint8_t *enc, void *stream);
 
 #ifdef __cplusplus
 }
