@@ -35,8 +35,31 @@ class EvalEnvRequest(object):
 
 
 def _is_cuda_venv(venv):
+    from .mst_maze import CudaWideMSTMazeVecEnv
     from .vec_env import CudaAdversarialVecEnv
-    return isinstance(venv, CudaAdversarialVecEnv)
+    return isinstance(venv, (CudaAdversarialVecEnv, CudaWideMSTMazeVecEnv, _OnDevice))
+
+
+class _OnDevice(object):
+    """The `device=` argument of VecPreprocessImageWrapper (obs_wrappers.py:77-86,99-100): eval.py's __main__ evaluates on the
+    CPU (eval.py:385), so the CUDA vector env's observation / reward tensors are moved to where the agent lives."""
+
+    def __init__(self, venv, device):
+        import torch
+        self.venv, self._device = venv, torch.device(device)
+
+    def __getattr__(self, name):
+        return getattr(self.venv, name)
+
+    def _move(self, obs):
+        return {k: v.to(self._device) for k, v in obs.items()}
+
+    def reset(self):
+        return self._move(self.venv.reset())
+
+    def step(self, action):
+        obs, rew, done, infos = self.venv.step(action)
+        return self._move(obs), rew.to(self._device), done, infos
 
 
 def install(device='cuda:0', storage=False):
@@ -86,7 +109,13 @@ def install(device='cuda:0', storage=False):
         return venv if _is_cuda_venv(venv) else ref['VecMonitor'](venv, *a, **k)
 
     def vec_preprocess(venv, *a, **k):
-        return venv if _is_cuda_venv(venv) else ref['VecPreprocessImageWrapper'](venv, *a, **k)
+        if not _is_cuda_venv(venv):
+            return ref['VecPreprocessImageWrapper'](venv, *a, **k)
+        import torch
+        want = k.get('device')
+        if want is not None and torch.device(want).type != 'cuda':
+            return _OnDevice(venv, want)
+        return venv
 
     util.create_parallel_env = create_parallel_env
     registration.make = make
