@@ -29,6 +29,9 @@ def _env_and_ref():
     env = dict(os.environ)
     env['PYTHONPATH'] = os.pathsep.join([rh.SHIM, rh.REFERENCE, ROOT, env.get('PYTHONPATH', '')])
     env['OMP_NUM_THREADS'] = '1'
+    # eval.py:435 calls torch.load(path, map_location='cpu') on a checkpoint that pickles the runner's LevelSampler / LevelStore
+    # objects (adversarial_runner.py:214-215); torch >= 2.6 defaults to weights_only=True, which the reference predates
+    env['TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD'] = '1'
     return env, rh.REFERENCE
 
 
