@@ -72,5 +72,5 @@ def test_reference_train_and_eval_scripts_run_on_the_dropin(tmp_path):
     res = glob.glob(os.path.join(res_dir, '*.csv'))
     assert len(res) == 1
     table = {r[0]: r[1:] for r in csv.reader(open(res[0]))}
-    for name in MAZE_BENCHMARK:
-        assert 'solved_rate:' + name in table and 'test_returns:' + name in table, (name, list(table)[:6])
+    for name in MAZE_BENCHMARK:   # (solved_rate rows only come with --accumulator mean, eval.py:331-338)
+        assert 'test_returns:' + name in table and len(table['test_returns:' + name]) == 1, (name, list(table)[:6])
