@@ -54,6 +54,11 @@ struct mgplr_venv {
   int pdl;                 // launch the step kernel with programmatic stream serialization
   int rr_spec;             // DR auto-reset: speculative next-level candidates (MGPLR_RR_SPEC=0 disables)
   int sm_count;
+  cudaStream_t regen_stream;   // DR speculation: the regeneration kernel of step t runs here, next to step t+1
+  cudaEvent_t regen_fork, regen_join;
+  uint32_t rr_calls;       // speculative DR step launches issued: launch k appends its jobs to list k & 1, drains list (k - 1) & 1
+  int rr_dyn, rr_rgrid;    // A/B knobs: dynamic tile tickets, regeneration CTAs per SM
+  int rr_ctas;             // step-kernel CTAs per SM in the speculative DR mode (the rest of the SM is left to the regeneration kernel)
   int steps_since_sweep;   // reset_agent-mode step launches since the last deferred-respawn sweep (kSweepEvery)
 };
 
@@ -590,6 +595,8 @@ struct StepArgs {
   mgplr_done_record *done_list;  // device view of pinned host memory: records cross PCIe as posted writes
   uint8_t *flags_host;           // second flags destination (mapped pinned host memory) or NULL
   int spec;                      // DR auto-reset: speculative next-level candidates enabled (mgplr_env.cuh "SPECULATION")
+  int dyn_tiles;                 // DR variant: tiles handed out by tickets instead of round-robin
+  int spec_list;                 // which of the two job lists this launch appends to (the regeneration kernel drains the other)
 };
 
 // ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
@@ -843,23 +850,21 @@ __device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, 
 // The DR variant (RR) additionally resets finished envs -- by copying a pre-built candidate level, or by rebuilding in
 // the kernel -- and runs the regeneration jobs queued by the previous launch.
 // per warp: obs tile | two row buffers | two mbarriers | (DR variant) batched-RNG scratch [32][32] | job queue
-constexpr int kPendCap = 96;  // DR variant: regeneration jobs a warp collects before it appends them to the global list
+constexpr int kPendCap = 32;  // DR variant: regeneration jobs a warp collects before it appends them to the global list
 __host__ __device__ inline size_t warp_smem_bytes(int W, bool rr) {
-  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + (rr ? 32 * kWarpTile * 4 + kPendCap * 8 : 0) + 127) &
-         ~(size_t)127;
+  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + (rr ? kPendCap * 8 : 0) + 127) & ~(size_t)127;
 }
-// append a warp's collected jobs (one entry per reset env) to the launch's list: ONE atomic per flush, both candidates
+// append a warp's collected jobs (one entry per reset env: the job builds both candidates) to the launch's list: ONE atomic
+// per flush.  A list that is full drops the rest -- candidates are optional, an env without them takes the slow path once.
 __device__ __forceinline__ void flush_pending_jobs(const Dev &d, int rr_par, const uint2 *s_pend, int &pend_n, int lane) {
   __syncwarp();
   if (pend_n) {
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&d.sched[rr_par], 2u * (uint32_t)pend_n);
+    if (lane == 0) base = atomicAdd(&d.sched[rr_par], (uint32_t)pend_n);
     base = __shfl_sync(0xffffffffu, base, 0);
-    uint2 *list = d.rr_list + (size_t)rr_par * 2 * d.N + base;
-    for (int i = lane; i < pend_n; i += 32) {
-      const uint2 jb = s_pend[i];
-      list[2 * i] = jb; list[2 * i + 1] = make_uint2(jb.x | 128u, jb.y);
-    }
+    uint2 *list = d.rr_list + (size_t)rr_par * 2 * d.N;
+    for (int i = lane; i < pend_n; i += 32)
+      if (base + i < 2u * (uint32_t)d.N) list[base + i] = s_pend[i];
     pend_n = 0;
   }
   __syncwarp();
@@ -888,10 +893,49 @@ __device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, 
   }
 }
 
-// reset_agent mode: the shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids; the DR
-// variant carries its in-kernel reset_random, the batched-RNG scratch and the regeneration phase (168 registers, 3 CTAs/SM).
+// Commit of pre-built candidate levels for the finished envs of one tile (`mask`), all lanes together per env: one coalesced
+// W-word read of the rows into the tile's shared-memory image, and the words the record consumed are applied to the env's MT
+// state by copying the NEW state words the record carries (coalesced reads, fire-and-forget stores).  Out of line: ~12 % of the
+// tiles of a launch commit anything, and the hot path should not carry these registers.  Returns the lane's own new MT cursor.
+static __device__ __noinline__ uint32_t rr_commit_records(Dev d, uint32_t *rows, int base, int lane, unsigned mask, int cand_pick,
+                                                          int cand_used, uint32_t sp, uint32_t cand_idx, uint32_t cand_words_used) {
+  const int W = d.c.W;
+  uint32_t new_idx = 0;
+  for (unsigned rest = mask; rest; rest &= rest - 1) {
+    const int le = __ffs(rest) - 1, env = base + le;
+    const int pick = __shfl_sync(0xffffffffu, cand_pick, le), used_w = __shfl_sync(0xffffffffu, cand_used, le);
+    const uint32_t *rec = cand_record(d, env, spec_epoch(__shfl_sync(0xffffffffu, sp, le)), pick);
+    if (lane < W) rows[lane * kWarpTile + le] = __ldcg(rec + lane);
+    uint32_t idx = __shfl_sync(0xffffffffu, cand_idx, le), used = __shfl_sync(0xffffffffu, cand_words_used, le);
+    uint32_t nw[kSpecState / 32];
+#pragma unroll
+    for (int i = 0; i < kSpecState / 32; i++) nw[i] = __ldcg(rec + W + 8 + lane + 32 * i);
+#pragma unroll
+    for (int i = 0; i < kSpecState / 32; i++) {
+      const int j = lane + 32 * i;
+      if (j < used_w) {
+        uint32_t p = idx + j;
+        if (p >= 624) p -= 624;
+        d.mt[mt_at(env, p)] = nw[i];
+      }
+    }
+    idx += used_w;
+    if (idx >= 624) idx -= 624;
+    used += used_w;
+    if (lane == 0) { d.mti[env] = idx; d.words[env] = used; }
+    if (lane == le) new_idx = idx;
+  }
+  return new_idx;
+}
+
+#ifndef MGPLR_RR_MINB
+#define MGPLR_RR_MINB 4
+#endif
+// The shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids, in both modes: the DR variant only
+// carries the COMMIT of pre-built candidate levels in its hot path (regeneration is its own kernel, k_rr_regen); its in-kernel
+// rebuild for envs without a candidate is out of line and may spill.
 template <bool SEE, bool RR, typename EXT>
-__global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int tile0, int n_tiles) {  // tiles [tile0, n_tiles)
+__global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (RR ? MGPLR_RR_MINB : 4)) k_step_env(Dev d, StepArgs A, int tile0, int n_tiles) {  // tiles [tile0, n_tiles)
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = d.c.W, N = d.N;
   const int wpc = blockDim.x >> 5;
@@ -899,8 +943,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   float *s_obs = reinterpret_cast<float *>(wbase);
   uint32_t *s_rows = reinterpret_cast<uint32_t *>(wbase + (size_t)kWarpTile * kObsFloats * 4);
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 2 * W * kWarpTile);
-  uint32_t *s_rng = reinterpret_cast<uint32_t *>(bars + 2);  // only present (and used) when RR
-  uint2 *s_pend = reinterpret_cast<uint2 *>(s_rng + 32 * kWarpTile);  // (RR) jobs collected by this warp
+  uint2 *s_pend = reinterpret_cast<uint2 *>(bars + 2);  // (RR) jobs collected by this warp
   int pend_n = 0;
   unsigned long long prof_start = 0;
   int prof_commits = 0;
@@ -916,48 +959,10 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   if (!RR && tile >= n_tiles) return;  // (the DR variant's idle warps still serve the regeneration phase)
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
   const bool use_spec = RR && A.spec;
-  const int rr_par = use_spec ? (int)(*(volatile uint32_t *)&d.sched[5] & 1u) : 0;  // stable for the whole launch
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
-  if (RR && use_spec) {
-    // ---- regeneration jobs FIRST: the jobs queued by the previous launch (list of the other parity; its length is
-    // final) are the long indivisible items of this launch (~15 us each), so warps take them before any tile; the warps
-    // that find the list empty start on the tiles at once, and because the tiles are handed out dynamically below, the
-    // job warps simply end up with fewer tiles.  Nothing waits on this launch's own progress.
-    const int q = rr_par ^ 1;
-    const uint32_t n_jobs = *(volatile uint32_t *)&d.sched[q];
-    const uint2 *list = d.rr_list + (size_t)q * 2 * N;
-    uint32_t *scr = reinterpret_cast<uint32_t *>(s_obs);  // the observation tile is not in use yet
-    if (n_jobs >= 8u * (uint32_t)total) {
-      // a storm's worth of jobs: 32 candidates per warp side by side (rr_regen_job_lane), tickets in units of 32
-      for (;;) {
-        uint32_t j = 0;
-        if (lane == 0) j = atomicAdd(&d.sched[2 + q], 32u);
-        j = __shfl_sync(0xffffffffu, j, 0);
-        if (j >= n_jobs) break;
-        if (j + lane < n_jobs) rr_regen_job_lane(d, __ldcg(list + j + lane), scr + lane);
-        __syncwarp();
-      }
-    } else
-    for (;;) {
-      uint32_t j = 0;
-      if (lane == 0) j = atomicAdd(&d.sched[2 + q], 1u);
-      j = __shfl_sync(0xffffffffu, j, 0);
-      if (j >= n_jobs) break;
-      const long long c0 = d.prof ? clock64() : 0;
-      rr_regen_job(d, __ldcg(list + j), lane, scr);
-      __syncwarp();
-      if (d.prof && lane == 0) {
-        const unsigned long long dt = (unsigned long long)(clock64() - c0);
-        atomicAdd(&d.prof[3], dt); atomicAdd(&d.prof[4], 1ull); atomicMax(&d.prof[5], dt);
-      }
-    }
-    if (d.prof && lane == 0) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      atomicMax(&d.prof[2], t1);               // end of this warp's job phase
-    }
-    __syncwarp();
-  }
+  const int rr_par = A.spec_list & 1;
+  // (the speculative DR variant is the programmatic dependent of the regeneration kernel and must NOT wait for it, see
+  // launch_step_args; its real predecessor, the previous step launch, completed before that kernel started)
+  if (!(RR && use_spec)) asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
   // the state plane of every observation is all zero: written once here, never touched by emit_packed_f32
 #pragma unroll
   for (int i = 0; i < kV * kV; i++) s_obs[lane * kObsFloats + 2 * kV * kV + i] = 0.0f;
@@ -968,7 +973,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   // counter doubled the reset_agent variant's launch time -- EXCEPT in the speculative DR variant, where warps carry very
   // different loads (jobs, commits): there the next tile is a ticket, requested one tile ahead so that the atomic's
   // round trip hides behind a tile's work.
-  const bool dyn = RR && use_spec;
+  const bool dyn = RR && use_spec && A.dyn_tiles;
   uint32_t ticket = 0;  // (lane 0) ticket of the tile after `next`
   int next;
   if (dyn) {
@@ -1029,11 +1034,31 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     uint32_t cand_idx = 0, cand_words_used = 0, new_idx = 0;  // MT cursor / words drawn before and cursor after the reset
     float fin_ret = 0.f;
     int fin_len = 0;
+    uint32_t sp_now = sp;
     if (valid) {
       const bool want_trunc = A.o.trunc_image || A.o.trunc_direction || A.o.trunc_full_obs;
       // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
       s.step_count++;
       const int fx = s.ax + ((s.adir == 0) - (s.adir == 2)), fy = s.ay + ((s.adir == 1) - (s.adir == 3));
+      if (RR && use_spec) {
+        // The episode ends this step while the regeneration job of its level is still in flight (the level is one step old:
+        // ~1 reset in 300): wait for the job -- it runs next to this launch and takes a few us -- instead of rebuilding the
+        // level here (a ~20 us serial chain that the whole launch would then end on).  Bounded: a job that never reports
+        // (dropped from a full list, regeneration kernel not resident) falls through to the rebuild.
+        const bool will_goal = a == 2 && fx == s.gx && fy == s.gy;
+        const bool will_end = will_goal || s.step_count >= c.max_steps || s.elapsed + 1 >= c.max_episode_steps;
+        const uint32_t want_bit = spec_valid_bit(spec_epoch(sp), will_goal ? 1 : 0);
+        if (will_end && !(sp & want_bit) && (sp & kSpecQueued) && !(sp & spec_built_bit(spec_epoch(sp)))) {
+          unsigned long long t0, t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          do {
+            __nanosleep(256);
+            sp_now = *(volatile uint32_t *)&d.spec[e];
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          } while (!(sp_now & spec_built_bit(spec_epoch(sp))) && t1 - t0 < 30000ull);
+          __threadfence();   // the record was written before the bit was set (the job fences, too)
+        }
+      }
       if (a == 0) s.adir = (s.adir + 3) & 3;
       else if (a == 1) s.adir = (s.adir + 1) & 3;
       else if (a == 2) {
@@ -1042,7 +1067,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
           s.done_flag = 1;
           // DR variant with a valid goal candidate: its record already accounts for the respawn draws (SPECULATION)
           const bool observed = want_trunc && s.elapsed + 1 >= c.max_episode_steps;
-          if (use_spec && (sp & spec_valid_bit(spec_epoch(sp), 1)) && !observed && s.pending == 0) cand_pick = 1;
+          if (use_spec && (sp_now & spec_valid_bit(spec_epoch(sp), 1)) && !observed && s.pending == 0) cand_pick = 1;
           else if (RR || observed || s.pending >= kMaxPending) {
             const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.spec, N, e, rows + lane, kWarpTile, W, s.gx, s.gy, s.pending + 1);
             s.pending = 0; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
@@ -1069,7 +1094,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
         s.ep_ret = 0.f; s.ep_len = 0;
         if (RR) {  // worker.step_env (parallel_wrappers.py:27-37): reset_random
-          if (use_spec && !(flags & MGPLR_F_GOAL) && (sp & spec_valid_bit(spec_epoch(sp), 0)) && s.pending == 0) cand_pick = 0;
+          if (use_spec && !(flags & MGPLR_F_GOAL) && (sp_now & spec_valid_bit(spec_epoch(sp), 0)) && s.pending == 0) cand_pick = 0;
           if (cand_pick >= 0) {
             // take the pre-built successor level: goal / start (rows and the MT advance are done warp-wide below)
             const uint32_t *rec = cand_record(d, e, spec_epoch(sp), cand_pick) + W;  // (L2 loads: written by another SM)
@@ -1092,32 +1117,9 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     if (RR) {
       // committed candidate records, all lanes together per finished env: one coalesced W-word read of the rows, and
       // the words the record consumed are applied to the env's MT state (so regeneration jobs only read env state)
-      for (unsigned rest = __ballot_sync(0xffffffffu, cand_pick >= 0); rest; rest &= rest - 1) {
-        const int le = __ffs(rest) - 1, env = base + le;
-        const int pick = __shfl_sync(0xffffffffu, cand_pick, le), used_w = __shfl_sync(0xffffffffu, cand_used, le);
-        const uint32_t *rec = cand_record(d, env, spec_epoch(__shfl_sync(0xffffffffu, sp, le)), pick);
-        if (lane < W) rows[lane * kWarpTile + le] = __ldcg(rec + lane);
-        uint32_t idx = __shfl_sync(0xffffffffu, cand_idx, le), used = __shfl_sync(0xffffffffu, cand_words_used, le);
-        // the record carries the new MT state words of the span it consumed: coalesced reads, fire-and-forget stores
-        {
-          uint32_t nw[kSpecState / 32];
-#pragma unroll
-          for (int i = 0; i < kSpecState / 32; i++) nw[i] = __ldcg(rec + W + 8 + lane + 32 * i);
-#pragma unroll
-          for (int i = 0; i < kSpecState / 32; i++) {
-            const int j = lane + 32 * i;
-            if (j < used_w) {
-              uint32_t p = idx + j;
-              if (p >= 624) p -= 624;
-              d.mt[mt_at(env, p)] = nw[i];
-            }
-          }
-          idx += used_w;
-          if (idx >= 624) idx -= 624;
-          used += used_w;
-        }
-        if (lane == 0) { d.mti[env] = idx; d.words[env] = used; }
-        if (lane == le) new_idx = idx;
+      {
+        const unsigned commit_mask = __ballot_sync(0xffffffffu, cand_pick >= 0);
+        if (commit_mask) new_idx = rr_commit_records(d, rows, base, lane, commit_mask, cand_pick, cand_used, sp, cand_idx, cand_words_used);
       }
       __syncwarp();
       const long long pc2 = d.prof ? clock64() : 0;
@@ -1134,9 +1136,18 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
       if (m) {
         dirty = dirty || need_rr;
         if (__popc(m) > 10) {
+          // the batched-RNG scratch ([32][32] words) borrows the observation tile: wait for the previous tile's bulk store to
+          // have read it, and put the all-zero state planes back afterwards
+          if (d.use_tma && lane == 0) bulk_wait_read0();
+          __syncwarp();
+          uint32_t *scratch = reinterpret_cast<uint32_t *>(s_obs);
           if (need_rr)
             s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1,
-                                         s_rng + lane, kWarpTile));
+                                         scratch + lane, kWarpTile));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < kV * kV; i++) s_obs[lane * kObsFloats + 2 * kV * kV + i] = 0.0f;
+          __syncwarp();
         } else {
           const uint4 mine = pack(s);
           for (unsigned rest = m; rest; rest &= rest - 1) {
@@ -1190,7 +1201,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
         for (int r = 0; r < W; r++) G.set(r, rows[r * kWarpTile + lane]);
         if (use_spec) {  // new level epoch (drops the old candidates); its two candidates are built during the next launch
           const uint32_t ne = (spec_epoch(sp) + 1u) & 127u;
-          *(volatile uint32_t *)&d.spec[e] = ne << kSpecEpochShift;
+          *(volatile uint32_t *)&d.spec[e] = (ne << kSpecEpochShift) | kSpecQueued;
           if (cand_pick < 0) new_idx = *(volatile uint32_t *)&d.mti[e];  // rebuilt the slow way: cursor as stored by the rebuild
           queue_me = true;
           queue_job = make_uint2(((uint32_t)e << 8) | ne, new_idx);
@@ -1221,15 +1232,57 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     atomicAdd(&d.prof[cls], dur); atomicAdd(&d.prof[cls + 1], 1ull); atomicMax(&d.prof[cls + 2], dur);
   }
   if (RR && use_spec) {
-    // last warp out: the list drained at the start of this launch becomes the next launch's append list
-    const int q = rr_par ^ 1;
     if (lane == 0) {
       __threadfence();
-      if (atomicAdd(&d.sched[4], 1u) == (uint32_t)total - 1u) {  // last warp out: the drained list becomes the next append list
-        d.sched[q] = 0; d.sched[2 + q] = 0; d.sched[4] = 0; d.sched[6] = 0;
-        d.sched[5] = (uint32_t)q;
+      if (atomicAdd(&d.sched[4], 1u) == (uint32_t)total - 1u) { d.sched[4] = 0; d.sched[6] = 0; }  // last warp out: tile tickets
+    }
+  }
+}
+
+// Regeneration kernel of the speculative DR auto-reset: builds the two successor candidates of every env that
+// step launch t reset (job list `q`), while step launch t+1 runs on the main stream.  Warps take job tickets; a storm's worth
+// of jobs (a synchronized time limit resets nearly every env) is built one env per LANE instead of one per warp.  The last warp
+// out empties the list for the launch after next.
+__global__ void __launch_bounds__(128) k_rr_regen(Dev d, int q) {
+  __shared__ __align__(16) uint32_t s_scr[4][1024];
+  asm volatile("griddepcontrol.launch_dependents;");   // the step launch behind this kernel may start right away
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = d.N;
+  const int total = gridDim.x * (blockDim.x >> 5);
+  const uint32_t n_jobs = min(*(volatile uint32_t *)&d.sched[q], 2u * (uint32_t)N);
+  const uint2 *list = d.rr_list + (size_t)q * 2 * N;
+  uint32_t *scr = s_scr[warp];
+  if (n_jobs >= 4u * (uint32_t)total) {
+    for (;;) {
+      uint32_t j = 0;
+      if (lane == 0) j = atomicAdd(&d.sched[2 + q], 32u);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= n_jobs) break;
+      if (j + lane < n_jobs) rr_regen_job_lane(d, __ldcg(list + j + lane), scr + lane);
+      __syncwarp();
+    }
+  } else {
+    for (;;) {
+      uint32_t j = 0;
+      if (lane == 0) j = atomicAdd(&d.sched[2 + q], 1u);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= n_jobs) break;
+      const long long c0 = d.prof ? clock64() : 0;
+      rr_regen_job(d, __ldcg(list + j), lane, scr);
+      __syncwarp();
+      if (d.prof && lane == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - c0);
+        atomicAdd(&d.prof[3], dt); atomicAdd(&d.prof[4], 1ull); atomicMax(&d.prof[5], dt);
       }
     }
+  }
+  if (d.prof && lane == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicMax(&d.prof[2], t1);               // end of the regeneration kernel
+  }
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(&d.sched[7], 1u) == (uint32_t)total - 1u) { d.sched[q] = 0; d.sched[2 + q] = 0; d.sched[7] = 0; }
   }
 }
 
@@ -1359,6 +1412,12 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   v->rr_spec = getenv("MGPLR_RR_SPEC") ? atoi(getenv("MGPLR_RR_SPEC")) : 1;  // DR speculation; 0 = in-kernel rebuild only
   v->host_dma = getenv("MGPLR_HOST_DMA") ? atoi(getenv("MGPLR_HOST_DMA")) : 0;
   CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&v->regen_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&v->regen_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&v->regen_join, cudaEventDisableTiming));
+  v->rr_ctas = getenv("MGPLR_RR_CTAS") ? atoi(getenv("MGPLR_RR_CTAS")) : 3;
+  v->rr_dyn = getenv("MGPLR_RR_DYN") ? atoi(getenv("MGPLR_RR_DYN")) : 1;
+  v->rr_rgrid = getenv("MGPLR_RR_RGRID") ? atoi(getenv("MGPLR_RR_RGRID")) : 2;
   for (int c = 0; c < 8; c++) CK(cudaEventCreateWithFlags(&v->copy_done[c], cudaEventDisableTiming));
   d.prof = nullptr;
   if (getenv("MGPLR_RR_PROF")) {  // debug: phase timestamps / job cycles of the DR step kernel (mgplr_debug_prof)
@@ -1409,6 +1468,9 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
   cudaSetDevice(v->device);
   Dev &d = v->d;
   if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+  if (v->regen_stream) cudaStreamDestroy(v->regen_stream);
+  if (v->regen_fork) cudaEventDestroy(v->regen_fork);
+  if (v->regen_join) cudaEventDestroy(v->regen_join);
   for (int c = 0; c < 8; c++) if (v->copy_done[c]) cudaEventDestroy(v->copy_done[c]);
   cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
   cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(d.spec); cudaFree(d.cand); cudaFree(d.rr_list); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->cnt_dev); cudaFreeHost(v->res_pin);
@@ -1610,14 +1672,31 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   const size_t smem = wpc * warp_smem_bytes(W, reset_random != 0);
   const int all_tiles = (v->d.N + kWarpTile - 1) / kWarpTile;
   const int n_tiles = (tile1 < 0 || tile1 > all_tiles) ? all_tiles : tile1;  // exclusive end of this launch's tile range
-  const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
-  int grid = v->sm_count * per_sm;
+  int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
+  if (per_sm > 4) per_sm = 4;
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
-  // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing job phase
+  // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing regeneration kernel
   // ... and a level with many walls does not fit the 224-word look-ahead window (2-3 words per try): no point in queueing jobs
   A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample && (v->d.N >= 16384 || v->rr_spec > 1) &&
            v->d.c.n_clutter / 2 <= 56;
-  if (A.spec) { if (int rc = rr_spec_alloc(v)) return rc; }
+  if (A.spec) {
+    if (int rc = rr_spec_alloc(v)) return rc;
+    // Regeneration of the levels that the PREVIOUS step launch reset: its own kernel, launched on the caller's stream right
+    // before this step launch, which is then launched as its PROGRAMMATIC DEPENDENT (it may start as soon as every
+    // regeneration CTA has started, griddepcontrol.launch_dependents at the top of k_rr_regen) and never waits for it: the
+    // step does not consume what the regeneration kernel produces in this launch (candidates are optional and validated by
+    // epoch), and everything the step does depend on -- the previous step launch -- had completed before the regeneration
+    // kernel could start.  Both run side by side on one stream: no events, no extra graph edges; the regeneration kernel of
+    // the next call is an ordinary launch and so follows both.  The step kernel leaves room for it (rr_ctas CTAs per SM).
+    A.dyn_tiles = v->rr_dyn;
+    A.spec_list = (int)(v->rr_calls & 1u);
+    const int drain = A.spec_list ^ 1;
+    v->rr_calls++;
+    k_rr_regen<<<v->rr_rgrid * v->sm_count, 128, 0, st>>>(v->d, drain);
+    CK(cudaGetLastError());
+    if (per_sm > v->rr_ctas) per_sm = v->rr_ctas > 0 ? v->rr_ctas : 1;
+  }
+  int grid = v->sm_count * per_sm;
   const int need = (n_tiles - tile0 + wpc - 1) / wpc;
   if (grid > need) grid = need;
   if (grid < 1) return 0;
@@ -1627,7 +1706,7 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = attr; lc.numAttrs = (v->pdl && !A.spec) ? 1 : 0;  // (the DR speculation reads a per-launch parity word)
+  lc.attrs = attr; lc.numAttrs = (v->pdl || A.spec) ? 1 : 0;
 #define LAUNCH(SEE, RR, EXT) CK(cudaLaunchKernelEx(&lc, k_step_env<SEE, RR, EXT>, v->d, A, tile0, n_tiles))
 #define BY_MODE(EXT)                                  \
   do {                                                \
