@@ -46,10 +46,11 @@ struct Dev {
                      //     level epoch of parity p is valid; bits 20-26: level epoch (bumped by every DR reset)
   uint32_t *cand;    // [N][2 epochs][2][W + 8 + 192] candidate records: wall rows, packed goal/start, -, words consumed, error
                      //     bits, and the NEW MT state words of the consumed span (so that a commit copies, never recomputes)
+  uint64_t *fin_list; // [N] finish list of the running speculative DR launch (64-bit self-contained entries, all ones = free)
   uint2 *rr_list;    // [2][2N] regeneration jobs {env << 8 | epoch, MT cursor} (one per reset env: both candidates), two lists
   unsigned long long *prof;  // debug counters (MGPLR_RR_PROF), else NULL
-  uint32_t *sched;   // [8] [0..1] jobs appended to list p, [2..3] next job ticket of list p, [4] step warps exited, [6] next tile
-                     //     ticket of the step kernel, [7] regeneration warps exited
+  uint32_t *sched;   // [16] [0..1] jobs appended to list p, [2..3] next job ticket of list p, [4] step warps exited, [7] regeneration
+                     //      warps exited, [8] finish-list entries, [9] next finish ticket, [10] warps past their tile pass
 };
 // MT19937 state layout: tile-major AND chunked -- the 624 words of 32 consecutive envs form one 78 KB block laid out as
 // [39 chunks][32 envs][16 words]: word i of env e at ((e/32*39 + i/16)*32 + e%32)*16 + i%16.  Both access patterns of this
