@@ -46,11 +46,10 @@ struct Dev {
                      //     level epoch of parity p is valid; bits 20-26: level epoch (bumped by every DR reset)
   uint32_t *cand;    // [N][2 epochs][2][W + 8 + 192] candidate records: wall rows, packed goal/start, -, words consumed, error
                      //     bits, and the NEW MT state words of the consumed span (so that a commit copies, never recomputes)
-  uint64_t *fin_list; // [N] finish list of the running speculative DR launch (64-bit self-contained entries, all ones = free)
-  uint2 *rr_list;    // [2][2N] regeneration jobs {env << 8 | epoch, MT cursor} (one per reset env: both candidates), two lists
+  uint2 *rr_list;    // [2][2N] regeneration jobs {env << 8 | candidate << 7 | epoch, MT cursor}, one list per launch parity
   unsigned long long *prof;  // debug counters (MGPLR_RR_PROF), else NULL
-  uint32_t *sched;   // [16] [0..1] jobs appended to list p, [2..3] next job ticket of list p, [4] step warps exited, [7] regeneration
-                     //      warps exited, [8] finish-list entries, [9] next finish ticket, [10] warps past their tile pass
+  uint32_t *sched;   // [8] regeneration phase: [0..1] jobs appended to list p, [2..3] next ticket of list p, [4] warps exited,
+                     //     [5] parity of the running / next DR launch (device-side so that graph replays stay consistent)
 };
 // MT19937 state layout: tile-major AND chunked -- the 624 words of 32 consecutive envs form one 78 KB block laid out as
 // [39 chunks][32 envs][16 words]: word i of env e at ((e/32*39 + i/16)*32 + e%32)*16 + i%16.  Both access patterns of this
@@ -71,11 +70,6 @@ constexpr int kSpecEpochShift = 20;
 // that may reset the env again) lands on the other parity and is never consulted.
 __host__ __device__ inline uint32_t spec_valid_bit(uint32_t ep, int k) { return 1u << (16 + 2 * (ep & 1u) + k); }
 constexpr uint32_t kSpecEpochMask = 127u << kSpecEpochShift;
-// bit 27: a regeneration job for the current level epoch has been queued (set by the reset that starts the epoch);
-// bits 28 + p: the job of an epoch of parity p has run (whether or not its candidates came out valid).  A step warp whose env
-// finishes while its job is still in flight -- the episode lasted one step -- waits for it instead of rebuilding the level.
-constexpr uint32_t kSpecQueued = 1u << 27;
-__host__ __device__ inline uint32_t spec_built_bit(uint32_t ep) { return 1u << (28 + (ep & 1u)); }
 __host__ __device__ inline uint32_t spec_epoch(uint32_t sp) { return (sp & kSpecEpochMask) >> kSpecEpochShift; }
 constexpr int kSpecWindow = 224;   // MT words one regeneration job can look ahead (< 227: all computable from the present state)
 constexpr int kSpecState = 192;     // new MT state words a candidate record carries (a record that consumed more is not published)
@@ -880,19 +874,16 @@ __device__ __forceinline__ uint32_t *cand_record(const Dev &d, int e, uint32_t e
   return d.cand + (((size_t)e * 2 + (ep & 1u)) * 2 + k) * cand_words(d.c.W);
 }
 
-// One regeneration job = one env, one warp, BOTH candidates (k = 0: the episode ends without a goal, 1: at the goal): the
-// look-ahead window and its tables are shared -- the goal candidate only starts parsing after the respawn's tries -- so the
-// second level costs one more spec_level pass (1.7 us) instead of a second 8.5 us job.
-// Jobs queued by step launch t run in the regeneration kernel that is launched with step t+1 and runs next to it
-// (k_rr_regen), so a job may race with a step warp that resets the very env it is reading.  That is harmless by
-// construction: a job only READS env state (the step kernel applies a committed record's words to the MT state when it
-// commits), every reset bumps the env's level epoch and stores a fresh speculation word, records and validity bits are per
-// epoch parity, and jobs live for one launch -- whatever a job computed from a torn state lands on the parity that is no
-// longer consulted (spec_valid_bit).
+// One regeneration job = ONE candidate (k = 0: the episode ends without a goal, 1: at the goal) of one env, one warp.
+// Jobs queued by launch t run in the tail of launch t+1, next to its tiles, so a job may race with a step warp that
+// resets the very env it is reading.  That is harmless by construction: a job only READS env state (the step kernel
+// applies a committed record's words to the MT state when it commits), every reset bumps the env's level epoch and
+// stores a fresh speculation word, records and validity bits are per epoch parity, and jobs live for one launch --
+// whatever a job computed from a torn state lands on the parity that is no longer consulted (spec_valid_bit).
 static __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint32_t *scr /* 1024 words of shared memory */) {
   const Cfg &c = d.c;
   const uint32_t job = jb.x;
-  const int e = (int)(job >> 8);
+  const int e = (int)(job >> 8), k = (int)((job >> 7) & 1u);
   const uint32_t ep = job & 127u;
   const int W = c.W;
   SpecTables T;
@@ -902,7 +893,7 @@ static __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint
   const uint32_t idx = jb.y % 624u;  // the cursor travels with the job: every load of the job is issued in one go
   const uint32_t sp0 = __ldcg(d.spec + e);
   const uint4 hot = __ldcg(d.hot + e);
-  const uint32_t cur_row = (lane < W) ? __ldcg(env_rows(d, e).p + lane * 32) : 0xffffffffu;
+  const uint32_t cur_row = (k == 1 && lane < W) ? __ldcg(env_rows(d, e).p + lane * 32) : 0xffffffffu;
   // look-ahead window: tempered outputs idx .. idx + kSpecWindow - 1 of the present state (nothing is stored to mt).
   // All 21 loads per lane are issued before the first shared-memory store (which the compiler must order against them).
   uint32_t nst[kSpecState / 32];  // untempered = new state words of positions lane + 32 i
@@ -937,32 +928,28 @@ static __device__ __noinline__ void rr_regen_job(Dev d, uint2 jb, int lane, uint
   const long long c1 = d.prof ? clock64() : 0;
   spec_build_tables(T, W, lane);
   const long long c2 = d.prof ? clock64() : 0;
-  uint32_t valid = 0;
-  for (int k = 0; k < 2; k++) {
-    LevelOut o;
-    int consumed = 0;
-    const bool ok = spec_level(T, cur, s.gx & 31, s.gy & 31, k == 1, lvl, W, c.n_clutter / 2, lane, o, consumed);
-    __syncwarp();
-    if (!ok || consumed > kSpecState) continue;
-    uint32_t *rec = cand_record(d, e, ep, k);
-    if (lane < W) rec[lane] = lvl[lane];
-#pragma unroll
-    for (int i = 0; i < kSpecState / 32; i++) rec[W + 8 + lane + 32 * i] = nst[i];  // coalesced; the commit copies them into mt
-    if (lane == 0) {
-      rec[W] = ((uint32_t)o.gx & 31u) | (((uint32_t)o.gy & 31u) << 5) | (1u << 10) | (((uint32_t)o.sx & 31u) << 11) |
-               (((uint32_t)o.sy & 31u) << 16) | (1u << 21) | ((uint32_t)o.sdir << 22);
-      rec[W + 5] = (uint32_t)consumed;
-      rec[W + 6] = o.err;
-    }
-    valid |= spec_valid_bit(ep, k);
-    __syncwarp();
-  }
+  LevelOut o;
+  int consumed = 0;
+  const bool ok = spec_level(T, cur, s.gx & 31, s.gy & 31, k == 1, lvl, W, c.n_clutter / 2, lane, o, consumed);
+  __syncwarp();
   if (d.prof && lane == 0) {
     atomicAdd(&d.prof[6], (unsigned long long)(c2 - c1)); atomicAdd(&d.prof[7], (unsigned long long)(clock64() - c2));
   }
+  if (!ok || consumed > kSpecState) return;
+  uint32_t *rec = cand_record(d, e, ep, k);
+  if (lane < W) rec[lane] = lvl[lane];
+#pragma unroll
+  for (int i = 0; i < kSpecState / 32; i++) rec[W + 8 + lane + 32 * i] = nst[i];  // coalesced; the commit copies them into mt
+  if (lane == 0) {
+    rec[W] = ((uint32_t)o.gx & 31u) | (((uint32_t)o.gy & 31u) << 5) | (1u << 10) | (((uint32_t)o.sx & 31u) << 11) |
+             (((uint32_t)o.sy & 31u) << 16) | (1u << 21) | ((uint32_t)o.sdir << 22);
+    rec[W + 5] = (uint32_t)consumed;
+    rec[W + 6] = o.err;
+  }
+  __syncwarp();
   if (lane == 0) {
     __threadfence();
-    atomicOr(d.spec + e, valid | spec_built_bit(ep));  // result unused: a reduction, no round trip
+    atomicOr(d.spec + e, spec_valid_bit(ep, k));  // result unused: a reduction, no round trip
   }
 }
 
@@ -1009,51 +996,46 @@ struct FlyRng {
   __device__ __forceinline__ bool ok() const { return !overflow; }
 };
 
-// both candidates of one env per LANE, one after the other; `col` = this lane's column of a [W][32] shared-memory scratch
-// (the level under construction)
+// one candidate per LANE; `col` = this lane's column of a [W][32] shared-memory scratch (the level under construction)
 static __device__ __noinline__ void rr_regen_job_lane(Dev d, uint2 jb, uint32_t *col) {
   const Cfg &c = d.c;
   const uint32_t job = jb.x;
-  const int e = (int)(job >> 8);
+  const int e = (int)(job >> 8), k = (int)((job >> 7) & 1u);
   const uint32_t ep = job & 127u;
   const int W = c.W;
   if (spec_epoch(__ldcg(d.spec + e)) != ep) return;  // the level is gone already
   const Env s = unpack(__ldcg(d.hot + e));
-  uint32_t valid = 0;
-  for (int k = 0; k < 2; k++) {
-    uint32_t *rec = cand_record(d, e, ep, k);
-    FlyRng rng{d.mt, rec + W + 8, e, jb.y % 624u, 0, false};
-    const Rows L{col, 32};
-    int x = 0, y = 0;
-    uint32_t err = 0;
-    if (k == 1) {  // the goal respawn's draws (multigrid.py:821-838) against the current level, agent off the grid
-      Env t{};
-      t.gx = s.gx; t.gy = s.gy; t.has_agent = 0;
-      place_random(env_rows(d, e), t, rng, W, -1, x, y);
-    }
-    Env n{};
-    n.gx = n.gy = n.sx = n.sy = kNone;
-    gen_grid(L, W);
-    if (!place_random(L, n, rng, W, 100, x, y)) err |= kErrRetries;
-    n.gx = x; n.gy = y;
-    n.sdir = rng.randint(0, 4);
-    place_random(L, n, rng, W, -1, x, y);
-    n.sx = x; n.sy = y; n.has_agent = 1; n.ax = x; n.ay = y;
-    const int n_walls = c.n_clutter / 2;
-    for (int i = 0; i < n_walls; i++) {
-      if (!place_random(L, n, rng, W, 100, x, y)) { err |= kErrRetries; break; }
-      L.set(y, L.get(y) | (1u << x));
-    }
-    if (!rng.ok() || rng.pos > kSpecState) continue;
-    for (int r = 0; r < W; r++) rec[r] = L.get(r);
-    rec[W] = ((uint32_t)n.gx & 31u) | (((uint32_t)n.gy & 31u) << 5) | (1u << 10) | (((uint32_t)n.sx & 31u) << 11) |
-             (((uint32_t)n.sy & 31u) << 16) | (1u << 21) | ((uint32_t)n.sdir << 22);
-    rec[W + 5] = (uint32_t)rng.pos;
-    rec[W + 6] = err;
-    valid |= spec_valid_bit(ep, k);
+  uint32_t *rec = cand_record(d, e, ep, k);
+  FlyRng rng{d.mt, rec + W + 8, e, jb.y % 624u, 0, false};
+  const Rows L{col, 32};
+  int x = 0, y = 0;
+  uint32_t err = 0;
+  if (k == 1) {  // the goal respawn's draws (multigrid.py:821-838) against the current level, agent off the grid
+    Env t{};
+    t.gx = s.gx; t.gy = s.gy; t.has_agent = 0;
+    place_random(env_rows(d, e), t, rng, W, -1, x, y);
   }
+  Env n{};
+  n.gx = n.gy = n.sx = n.sy = kNone;
+  gen_grid(L, W);
+  if (!place_random(L, n, rng, W, 100, x, y)) err |= kErrRetries;
+  n.gx = x; n.gy = y;
+  n.sdir = rng.randint(0, 4);
+  place_random(L, n, rng, W, -1, x, y);
+  n.sx = x; n.sy = y; n.has_agent = 1; n.ax = x; n.ay = y;
+  const int n_walls = c.n_clutter / 2;
+  for (int i = 0; i < n_walls; i++) {
+    if (!place_random(L, n, rng, W, 100, x, y)) { err |= kErrRetries; break; }
+    L.set(y, L.get(y) | (1u << x));
+  }
+  if (!rng.ok() || rng.pos > kSpecState) return;
+  for (int r = 0; r < W; r++) rec[r] = L.get(r);
+  rec[W] = ((uint32_t)n.gx & 31u) | (((uint32_t)n.gy & 31u) << 5) | (1u << 10) | (((uint32_t)n.sx & 31u) << 11) |
+           (((uint32_t)n.sy & 31u) << 16) | (1u << 21) | ((uint32_t)n.sdir << 22);
+  rec[W + 5] = (uint32_t)rng.pos;
+  rec[W + 6] = err;
   __threadfence();
-  atomicOr(d.spec + e, valid | spec_built_bit(ep));
+  atomicOr(d.spec + e, spec_valid_bit(ep, k));
 }
 
 // ---------------------------------------------------------------------------------------------

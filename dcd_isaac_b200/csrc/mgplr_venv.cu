@@ -54,12 +54,6 @@ struct mgplr_venv {
   int pdl;                 // launch the step kernel with programmatic stream serialization
   int rr_spec;             // DR auto-reset: speculative next-level candidates (MGPLR_RR_SPEC=0 disables)
   int sm_count;
-  cudaStream_t regen_stream;   // DR speculation: the regeneration kernel of step t runs here, next to step t+1
-  cudaEvent_t regen_fork, regen_join;
-  uint32_t rr_calls;       // speculative DR step launches issued: launch k appends its jobs to list k & 1, drains list (k - 1) & 1
-  int rr_occ;              // resident CTAs per SM of the deferred-finish step kernel (occupancy calculator), 0 = not queried yet
-  int rr_dyn, rr_rgrid, rr_pdl;   // A/B knobs: (unused), regeneration CTAs per SM, step launched as programmatic dependent
-  int rr_ctas;             // step-kernel CTAs per SM in the speculative DR mode (the rest of the SM is left to the regeneration kernel)
   int steps_since_sweep;   // reset_agent-mode step launches since the last deferred-respawn sweep (kSweepEvery)
 };
 
@@ -596,8 +590,6 @@ struct StepArgs {
   mgplr_done_record *done_list;  // device view of pinned host memory: records cross PCIe as posted writes
   uint8_t *flags_host;           // second flags destination (mapped pinned host memory) or NULL
   int spec;                      // DR auto-reset: speculative next-level candidates enabled (mgplr_env.cuh "SPECULATION")
-  int dyn_tiles;                 // DR variant: tiles handed out by tickets instead of round-robin
-  int spec_list;                 // which of the two job lists this launch appends to (the regeneration kernel drains the other)
 };
 
 // ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
@@ -710,7 +702,7 @@ __device__ __forceinline__ uint32_t step_one(const Dev &d, uint32_t *rows, int s
 }
 
 __device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, const Env &s, uint32_t flags, float rew,
-                                                   float ep_ret = 0.f, int ep_len = 0, bool finish_job_writes = false) {
+                                                   float ep_ret = 0.f, int ep_len = 0) {
   const mgplr_step_out &o = A.o;
   if (A.done_count && (flags & MGPLR_F_DONE)) {
     const uint32_t k = atomicAdd(A.done_count, 1u);
@@ -718,12 +710,10 @@ __device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, con
     r.env = e; r.reward = rew; r.ep_return = ep_ret; r.ep_length = ep_len;
     A.done_list[k] = r;
   }
-  if (!finish_job_writes) {   // (deferred-finish DR: the env's finish job writes the new level's direction and the flags)
-    if (o.direction) o.direction[e] = (float)s.adir;
-    if (o.flags) o.flags[e] = (uint8_t)flags;
-    if (A.flags_host) A.flags_host[e] = (uint8_t)flags;
-  }
+  if (o.direction) o.direction[e] = (float)s.adir;
   if (o.reward) o.reward[e] = rew;
+  if (o.flags) o.flags[e] = (uint8_t)flags;
+  if (A.flags_host) A.flags_host[e] = (uint8_t)flags;
   const bool done = flags & MGPLR_F_DONE, last = A.last_step & 1, cliff = last && (A.last_step & 2) && !done;
   if (o.masks) o.masks[e] = (done || last) ? 0.f : 1.f;
   if (o.bad_masks) o.bad_masks[e] = ((flags & MGPLR_F_TRUNC_KEY) || cliff) ? 0.f : 1.f;
@@ -801,9 +791,6 @@ __device__ __forceinline__ void st_hint_f4(float4 *p, const float4 v, uint64_t p
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk stores have finished READING shared memory (the global writes complete before the grid does)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// wait until the bulk stores (all / all but the newest group) have COMPLETED, global writes included
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all_but1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 
 // Stage the wall rows of the CTA's TILE/32 warp-tiles into s_rows[sub][W][32]: one bulk copy of W*128 bytes per
 // sub-tile (one elected thread, completion on `bar`).  The HBM plane is padded to whole tiles, so partial tiles
@@ -856,10 +843,28 @@ __device__ __forceinline__ void store_obs_tile(float *gdst, const float *s_obs, 
 // The DR variant (RR) additionally resets finished envs -- by copying a pre-built candidate level, or by rebuilding in
 // the kernel -- and runs the regeneration jobs queued by the previous launch.
 // per warp: obs tile | two row buffers | two mbarriers | (DR variant) batched-RNG scratch [32][32] | job queue
+constexpr int kPendCap = 96;  // DR variant: regeneration jobs a warp collects before it appends them to the global list
 __host__ __device__ inline size_t warp_smem_bytes(int W, bool rr) {
-  (void)rr;   // every variant: observation tile, two row stages, two mbarriers
-  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + 127) & ~(size_t)127;
+  return ((size_t)kWarpTile * kObsFloats * 4 + 2 * (size_t)W * kWarpTile * 4 + 16 + (rr ? 32 * kWarpTile * 4 + kPendCap * 8 : 0) + 127) &
+         ~(size_t)127;
 }
+// append a warp's collected jobs (one entry per reset env) to the launch's list: ONE atomic per flush, both candidates
+__device__ __forceinline__ void flush_pending_jobs(const Dev &d, int rr_par, const uint2 *s_pend, int &pend_n, int lane) {
+  __syncwarp();
+  if (pend_n) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&d.sched[rr_par], 2u * (uint32_t)pend_n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    uint2 *list = d.rr_list + (size_t)rr_par * 2 * d.N + base;
+    for (int i = lane; i < pend_n; i += 32) {
+      const uint2 jb = s_pend[i];
+      list[2 * i] = jb; list[2 * i + 1] = make_uint2(jb.x | 128u, jb.y);
+    }
+    pend_n = 0;
+  }
+  __syncwarp();
+}
+
 __device__ __noinline__ void rare_emit_u8(uint32_t *rows, int stride, uint4 hot, int W, int see, uint8_t *image_u8, int e) {
   const Env s = unpack(hot);
   const Rows R{rows, stride};
@@ -883,153 +888,23 @@ __device__ __forceinline__ void warp_issue_rows(const Dev &d, uint32_t *s_rows, 
   }
 }
 
-// ---- speculative DR auto-reset, DEFERRED FINISH -----------------------------------------------------
-// In the speculative mode the tile pass is the reset_agent kernel's hot path plus one thing: an env whose episode ends is not
-// reset where it stands -- it is appended to the launch's finish list (env | goal bit | respawn-already-drawn bit) after the
-// tile's observation store has completed -- and the warps that have run out of tiles take finish jobs off that list, one warp
-// per env: commit the pre-built candidate level (record rows -> wall bit-plane, the record's new MT state words -> the env's
-// generator, reset_agent) or, without a candidate, wait for the env's in-flight regeneration job / rebuild the level
-// cooperatively; then start the new level epoch, queue its regeneration job, and write the observation + direction of the NEW
-// level over what the tile pass wrote for this step.  The rebuild code and the commit never touch the hot path's registers, and
-// a launch ends one short job after its last tile instead of on the slowest in-tile reset.
-constexpr uint32_t kFinGoal = 1u << 30, kFinRespawned = 1u << 31, kFinEmpty = 0xffffffffu;
-constexpr uint32_t kFinFromHot = 1u << 11;                // (high word: gx | gy << 5 | has-goal << 10 | from-hot << 11 | flags << 16)
-constexpr uint64_t kFinEmpty64 = ~0ull;
-// Dev::sched words of the finish list, one 128-byte line each: the publish counter is hit by tile warps in the middle of their
-// pass and must not share a line with what the serving warps poll or take tickets from.
-constexpr int kSchedPub = 32, kSchedTicket = 64, kSchedPast = 96, kSchedFinal = 128, kSchedExit = 160, kSchedWords = 192;
-
-template <bool SEE, typename EXT>
-static __device__ __noinline__ void rr_finish_job(Dev d, uint64_t entry64, int lane, uint32_t *col /* [W] words, stride 32 */,
-                                                  int spec_list, float *image, float *direction, uint8_t *image_u8, uint8_t *flags_out,
-                                                  uint8_t *flags_host) {
-  const Cfg &c = d.c;
-  const int W = c.W, N = d.N;
-  const uint32_t entry = (uint32_t)entry64, hi = (uint32_t)(entry64 >> 32);
-  const int e = (int)(entry & 0x3fffffffu);
-  const bool goal = entry & kFinGoal, respawned = entry & kFinRespawned;
-  // What the job needs of the finished episode travels in the entry itself (the goal cell, for a deferred respawn draw against
-  // the old level), so the tile warp publishes it without a fence and leaves the env's hot record, direction and flags to this
-  // job.  The rare env with more to carry (an observed respawn already drawn, leftover pending draws, a u8 image) is flagged
-  // kFinFromHot: its tile wrote the hot record and fenced before publishing.
-  Env s;
-  if (hi & kFinFromHot) s = unpack(__ldcg(&d.hot[e]));
-  else {
-    s.ax = s.ay = s.adir = s.has_agent = s.done_flag = s.step_count = 0;
-    s.sx = s.sy = kNone; s.sdir = 0; s.pending = 0; s.elapsed = s.ep_len = 0; s.ep_ret = 0.f;
-    const bool hg = (hi >> 10) & 1;
-    s.gx = hg ? (int)(hi & 31) : kNone; s.gy = hg ? (int)((hi >> 5) & 31) : kNone;
-  }
-  uint32_t sp = __ldcg(&d.spec[e]);
-  const uint32_t ep = spec_epoch(sp);
-  const uint32_t want = spec_valid_bit(ep, goal ? 1 : 0);
-  if (!respawned && !(sp & want) && (sp & kSpecQueued) && !(sp & spec_built_bit(ep))) {
-    // the level is one step old and its regeneration job is still running next to this launch: wait for it (bounded)
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-      __nanosleep(256);
-      sp = __ldcg(&d.spec[e]);
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    } while (!(sp & spec_built_bit(ep)) && t1 - t0 < 30000ull);
-    __threadfence();
-    if (d.prof && lane == 0) { atomicAdd(&d.prof[19], 1ull); atomicAdd(&d.prof[20], t1 - t0); }
-  }
-  const Rows G = env_rows(d, e);
-  uint32_t new_idx = 0;
-  if (!respawned && (sp & want) && s.pending == 0) {
-    const uint32_t *rec = cand_record(d, e, ep, goal ? 1 : 0);
-    if (lane < W) { const uint32_t row = __ldcg(rec + lane); G.set(lane, row); col[lane * 32] = row; }
-    const uint32_t gs = __ldcg(rec + W), cerr = __ldcg(rec + W + 6);
-    const int used_w = (int)__ldcg(rec + W + 5);
-    uint32_t idx = d.mti[e], used = d.words[e];
-    uint32_t nw[kSpecState / 32];
-#pragma unroll
-    for (int i = 0; i < kSpecState / 32; i++) nw[i] = __ldcg(rec + W + 8 + lane + 32 * i);
-#pragma unroll
-    for (int i = 0; i < kSpecState / 32; i++) {
-      const int j = lane + 32 * i;
-      if (j < used_w) {
-        uint32_t p = idx + j;
-        if (p >= 624) p -= 624;
-        d.mt[mt_at(e, p)] = nw[i];
-      }
-    }
-    idx += used_w;
-    if (idx >= 624) idx -= 624;
-    used += used_w;
-    new_idx = idx;
-    s.gx = gs & 31; s.gy = (gs >> 5) & 31; s.sx = (gs >> 11) & 31; s.sy = (gs >> 16) & 31; s.sdir = (gs >> 22) & 3;
-    if (lane == 0) {
-      d.mti[e] = idx; d.words[e] = used;
-      d.metrics[e] = make_int4(0, 0, kMetricsDirty, 0);  // recomputed on demand by mgplr_get_metrics
-      d.adv[e] &= ~0xfffu;                               // adversary_step_count = 0 (adversarial.py:546)
-      if (cerr) d.err[e] |= cerr;
-      if (d.prof) atomicAdd(&d.prof[8], 1ull);
-    }
-    reset_agent(s);
-  } else {
-    // no candidate: rebuild cooperatively on the env's current rows (the deferred goal respawn is drawn first, against the
-    // old level, exactly as agent_is_done does: multigrid.py:821-838)
-    if (lane < W) col[lane * 32] = G.get(lane);
-    __syncwarp();
-    if (goal && !respawned) s.pending += 1;
-    s = unpack(coop_reset_random(d, col, 32, pack(s), e, -1, lane));
-    __syncwarp();
-    if (lane < W) G.set(lane, col[lane * 32]);
-    new_idx = *(volatile uint32_t *)&d.mti[e];
-    if (d.prof && lane == 0) atomicAdd(&d.prof[9], 1ull);
-  }
-  const uint32_t ne = (ep + 1u) & 127u;
-  if (lane == 0) {
-    *(volatile uint32_t *)&d.spec[e] = (ne << kSpecEpochShift) | kSpecQueued;   // new level epoch: the old candidates are gone
-    d.hot[e] = pack(s);
-    const uint32_t j = atomicAdd(&d.sched[spec_list], 1u);                       // its regeneration job
-    if (j < 2u * (uint32_t)N) d.rr_list[(size_t)spec_list * 2 * N + j] = make_uint2(((uint32_t)e << 8) | ne, new_idx);
-    if (direction) direction[e] = (float)s.adir;
-    const uint8_t fl = (uint8_t)((hi >> 16) & 0xffu) | (d.err[e] ? (uint8_t)MGPLR_F_ERROR : (uint8_t)0);
-    if (flags_out) flags_out[e] = fl;
-    if (flags_host) flags_host[e] = fl;
-  }
-  __syncwarp();
-  if (image) {   // the new level's first observation: lane 0 renders the packed view, 25 lanes write one cell each
-    PackedView v;
-    v.wall = v.vis = 0; v.goal = -1;
-    if (lane == 0) v = render_packed<SEE, EXT>(Rows{col, 32}, s, W);
-    v.wall = __shfl_sync(0xffffffffu, v.wall, 0); v.vis = __shfl_sync(0xffffffffu, v.vis, 0); v.goal = __shfl_sync(0xffffffffu, v.goal, 0);
-    if (lane < kV * kV) {
-      const int vx = lane / kV, vy = lane - vx * kV;
-      const uint32_t bit = 1u << (vy * kV + vx);
-      const bool bw = v.wall & bit;
-      float t = bw ? 0.2f : 0.1f, cl = bw ? 0.5f : 0.0f;
-      if (!SEE) t = (v.vis & bit) ? t : 0.0f;
-      if (v.goal == lane) { t = 0.8f; cl = 0.1f; }
-      float *o = image + (size_t)e * kObsFloats;
-      o[lane] = t; o[kV * kV + lane] = cl; o[2 * kV * kV + lane] = 0.0f;
-    }
-  }
-  if (image_u8 && lane == 0) rare_emit_u8(col, 32, pack(s), W, c.see_through, image_u8, e);
-  __syncwarp();
-}
-
-#ifndef MGPLR_RR_MINB
-#define MGPLR_RR_MINB 4
-#endif
-// The shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids, in both modes: the DR variant only
-// carries the COMMIT of pre-built candidate levels in its hot path (regeneration is its own kernel, k_rr_regen); its in-kernel
-// rebuild for envs without a candidate is out of line and may spill.
-// MODE 0: reset_agent auto-reset (PLR); 1: reset_random rebuilt inside the tile pass (small batches, fixed_environment,
-// resample_n_clutter); 2: reset_random, speculative with deferred finish jobs (rr_finish_job above, k_rr_regen below).
-template <bool SEE, int MODE, typename EXT>
-__global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (MODE == 1 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int tile0, int n_tiles) {  // tiles [tile0, n_tiles)
-  constexpr bool RR = MODE == 1, DEF = MODE == 2;
+// reset_agent mode: the shared-memory bound is 4 CTAs/SM for W <= 24 (<= 128 registers) and 3 for wider grids; the DR
+// variant carries its in-kernel reset_random, the batched-RNG scratch and the regeneration phase (168 registers, 3 CTAs/SM).
+template <bool SEE, bool RR, typename EXT>
+__global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_step_env(Dev d, StepArgs A, int tile0, int n_tiles) {  // tiles [tile0, n_tiles)
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = d.c.W, N = d.N;
   const int wpc = blockDim.x >> 5;
-  uint8_t *wbase = smem + (size_t)warp * warp_smem_bytes(W, MODE != 0);
+  uint8_t *wbase = smem + (size_t)warp * warp_smem_bytes(W, RR);
   float *s_obs = reinterpret_cast<float *>(wbase);
   uint32_t *s_rows = reinterpret_cast<uint32_t *>(wbase + (size_t)kWarpTile * kObsFloats * 4);
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 2 * W * kWarpTile);
+  uint32_t *s_rng = reinterpret_cast<uint32_t *>(bars + 2);  // only present (and used) when RR
+  uint2 *s_pend = reinterpret_cast<uint2 *>(s_rng + 32 * kWarpTile);  // (RR) jobs collected by this warp
+  int pend_n = 0;
+  unsigned long long prof_start = 0;
+  int prof_commits = 0;
+  if (RR && d.prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_start));
   const int total = gridDim.x * wpc;
   // Static round-robin tile assignment (tile = global_warp + k * total_warps).  A dynamic scheduler on one global
   // atomic counter was measured: ~9 k same-address atomics per launch doubled the launch time (10 -> 20 us).
@@ -1038,54 +913,102 @@ __global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (MODE == 1 ? 3 : 4
   // records, so the NEXT launch is allowed to become resident as this one's CTAs retire and to run its on-chip
   // prologue; it blocks at griddepcontrol.wait (below) until this grid has completed and its writes are visible.
   asm volatile("griddepcontrol.launch_dependents;");
-  unsigned long long prof_start = 0;
-  int prof_fin = 0;
-  if (DEF && d.prof) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_start));
-    if (lane == 0) atomicMin(&d.prof[21], prof_start);      // first warp in
-  }
-  if (!DEF && tile >= n_tiles) return;  // (the deferred-finish variant's idle warps still serve the finish jobs)
+  if (!RR && tile >= n_tiles) return;  // (the DR variant's idle warps still serve the regeneration phase)
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_proxy_async_smem(); }
-  // (the speculative DR variant is the programmatic dependent of the regeneration kernel and must NOT wait for it, see
-  // launch_step_args; its real predecessor, the previous step launch, completed before that kernel started)
-  if (!DEF) asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
+  const bool use_spec = RR && A.spec;
+  const int rr_par = use_spec ? (int)(*(volatile uint32_t *)&d.sched[5] & 1u) : 0;  // stable for the whole launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above touched only on-chip state
+  if (RR && use_spec) {
+    // ---- regeneration jobs FIRST: the jobs queued by the previous launch (list of the other parity; its length is
+    // final) are the long indivisible items of this launch (~15 us each), so warps take them before any tile; the warps
+    // that find the list empty start on the tiles at once, and because the tiles are handed out dynamically below, the
+    // job warps simply end up with fewer tiles.  Nothing waits on this launch's own progress.
+    const int q = rr_par ^ 1;
+    const uint32_t n_jobs = *(volatile uint32_t *)&d.sched[q];
+    const uint2 *list = d.rr_list + (size_t)q * 2 * N;
+    uint32_t *scr = reinterpret_cast<uint32_t *>(s_obs);  // the observation tile is not in use yet
+    if (n_jobs >= 8u * (uint32_t)total) {
+      // a storm's worth of jobs: 32 candidates per warp side by side (rr_regen_job_lane), tickets in units of 32
+      for (;;) {
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(&d.sched[2 + q], 32u);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        if (j >= n_jobs) break;
+        if (j + lane < n_jobs) rr_regen_job_lane(d, __ldcg(list + j + lane), scr + lane);
+        __syncwarp();
+      }
+    } else
+    for (;;) {
+      uint32_t j = 0;
+      if (lane == 0) j = atomicAdd(&d.sched[2 + q], 1u);
+      j = __shfl_sync(0xffffffffu, j, 0);
+      if (j >= n_jobs) break;
+      const long long c0 = d.prof ? clock64() : 0;
+      rr_regen_job(d, __ldcg(list + j), lane, scr);
+      __syncwarp();
+      if (d.prof && lane == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - c0);
+        atomicAdd(&d.prof[3], dt); atomicAdd(&d.prof[4], 1ull); atomicMax(&d.prof[5], dt);
+      }
+    }
+    if (d.prof && lane == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicMax(&d.prof[2], t1);               // end of this warp's job phase
+    }
+    __syncwarp();
+  }
   // the state plane of every observation is all zero: written once here, never touched by emit_packed_f32
 #pragma unroll
   for (int i = 0; i < kV * kV; i++) s_obs[lane * kObsFloats + 2 * kV * kV + i] = 0.0f;
   __syncwarp();
   const uint64_t pol_keep = l2_policy(d.l2_hints ? 1 : 0), pol_stream = l2_policy(d.l2_hints ? 2 : 0);
   if (A.done_count_next && blockIdx.x == 0 && threadIdx.x == 0) *A.done_count_next = 0;
-  int next = tile + total;
+  // Tile assignment: static round-robin (tile = global_warp + k * total_warps) -- a dynamic scheduler on one global
+  // counter doubled the reset_agent variant's launch time -- EXCEPT in the speculative DR variant, where warps carry very
+  // different loads (jobs, commits): there the next tile is a ticket, requested one tile ahead so that the atomic's
+  // round trip hides behind a tile's work.
+  const bool dyn = RR && use_spec;
+  uint32_t ticket = 0;  // (lane 0) ticket of the tile after `next`
+  int next;
+  if (dyn) {
+    uint32_t t0 = 0, t1 = 0;
+    if (lane == 0) { t0 = atomicAdd(&d.sched[6], 1u); t1 = atomicAdd(&d.sched[6], 1u); }
+    tile = tile0 + (int)__shfl_sync(0xffffffffu, t0, 0);
+    next = tile0 + (int)__shfl_sync(0xffffffffu, t1, 0);
+  } else {
+    next = tile + total;
+  }
   // prologue: first tile's rows and scalars
   if (tile < n_tiles) warp_issue_rows(d, s_rows, &bars[0], tile, lane, pol_keep);
   uint4 nh = make_uint4(0, 0, 0, 0);
   int na = 6;
+  uint32_t nsp = 0;  // speculation word of the env (DR variant)
   if (tile < n_tiles && tile * kWarpTile + lane < N) {
     nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep);
     na = A.action_u8 ? (int)A.action_u8[tile * kWarpTile + lane] : (int)A.action[tile * kWarpTile + lane];
+    if (use_spec) nsp = d.spec[tile * kWarpTile + lane];
   }
   uint32_t phase = 0;  // bit s = parity to wait for on bars[s]
-  uint32_t held_j0 = 0;               // (DEF) finish-list slots of the previous finish tile: the result of an atomicAdd in flight
-  unsigned held_mask = 0;
-  bool held_plain = false;
-  uint64_t held_entry = kFinEmpty64;
   for (int k = 0; tile < n_tiles; k++) {
     const int st = k & 1, base = tile * kWarpTile, e = base + lane;
     const int n_tile = min(kWarpTile, N - base);
     const bool valid = lane < n_tile;
     const uint4 h = nh;
     const int a = na;
+    const uint32_t sp = nsp;
     uint32_t *rows = s_rows + st * W * kWarpTile;
     // prefetch the next tile into the other stage (its last readers, the previous tile, are done: __syncwarp)
     __syncwarp();
+    if (dyn && lane == 0) ticket = atomicAdd(&d.sched[6], 1u);  // the tile after `next`: consumed at the end of this iteration
     if (next < n_tiles) {
       warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane, pol_keep);
       if (next * kWarpTile + lane < N) {
         nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_keep);
         na = A.action_u8 ? (int)A.action_u8[next * kWarpTile + lane] : (int)A.action[next * kWarpTile + lane];
+        if (use_spec) nsp = d.spec[next * kWarpTile + lane];
       }
     }
-    const long long tile_cw = (DEF && d.prof) ? clock64() : 0;
     if (d.use_tma) {
       mbar_wait(&bars[st], (phase >> st) & 1u);
       phase ^= 1u << st;
@@ -1094,15 +1017,16 @@ __global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (MODE == 1 ? 3 : 4
       __syncwarp();
     }
 
-    const long long tile_c0 = (DEF && d.prof) ? clock64() : 0;
+    const long long pc0 = (RR && d.prof) ? clock64() : 0;
     Env s = unpack(h);
     const Cfg &c = d.c;
     const Rows R{rows + lane, kWarpTile};
     uint32_t flags = 0;
     double rew = 0.0;
     bool dirty = false, need_rr = false;
-    uint32_t fin_entry = kFinEmpty;   // (DEF) this env's entry for the finish list
-    bool fin_from_hot = false;
+    int cand_pick = -1;  // DR variant: candidate record to reset from (0 no goal / 1 goal), -1 = none
+    int cand_used = 0;   // MT words that record consumed
+    uint32_t cand_idx = 0, cand_words_used = 0, new_idx = 0;  // MT cursor / words drawn before and cursor after the reset
     float fin_ret = 0.f;
     int fin_len = 0;
     if (valid) {
@@ -1110,20 +1034,19 @@ __global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (MODE == 1 ? 3 : 4
       // MultiGridEnv.step / step_one_agent (multigrid.py:943-975,866-941)
       s.step_count++;
       const int fx = s.ax + ((s.adir == 0) - (s.adir == 2)), fy = s.ay + ((s.adir == 1) - (s.adir == 3));
-      bool respawned = false;
       if (a == 0) s.adir = (s.adir + 3) & 3;
       else if (a == 1) s.adir = (s.adir + 1) & 3;
       else if (a == 2) {
         if (fx == s.gx && fy == s.gy) {
-          // agent_is_done (multigrid.py:821-838): done; the respawn draw is deferred unless something observes it (reset_agent
-          // mode: Env::pending; deferred-finish mode: the goal candidate's record / the finish job account for it)
+          // agent_is_done (multigrid.py:821-838): done; the respawn draw is deferred unless something observes it
           s.done_flag = 1;
+          // DR variant with a valid goal candidate: its record already accounts for the respawn draws (SPECULATION)
           const bool observed = want_trunc && s.elapsed + 1 >= c.max_episode_steps;
-          if (RR || observed || (!DEF && s.pending >= kMaxPending)) {
+          if (use_spec && (sp & spec_valid_bit(spec_epoch(sp), 1)) && !observed && s.pending == 0) cand_pick = 1;
+          else if (RR || observed || s.pending >= kMaxPending) {
             const uint32_t p = rare_respawn(d.mt, d.mti, d.words, d.spec, N, e, rows + lane, kWarpTile, W, s.gx, s.gy, s.pending + 1);
             s.pending = 0; s.ax = p & 0xff; s.ay = p >> 8; s.adir = 0;
-            respawned = true;
-          } else if (!DEF) s.pending++;
+          } else s.pending++;
           rew = __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)s.step_count, (double)c.max_steps)));  // _reward()
           flags |= MGPLR_F_GOAL;
         } else if (!is_wall(R, fx, fy)) { s.ax = fx; s.ay = fy; }
@@ -1145,59 +1068,75 @@ __global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (MODE == 1 ? 3 : 4
         if (A.o.ep_return) A.o.ep_return[e] = s.ep_ret;
         if (A.o.ep_length) A.o.ep_length[e] = s.ep_len;
         s.ep_ret = 0.f; s.ep_len = 0;
-        // worker.step_env (parallel_wrappers.py:27-37)
-        if (DEF) {
-          fin_entry = (uint32_t)e | ((flags & MGPLR_F_GOAL) ? kFinGoal : 0u) | (respawned ? kFinRespawned : 0u);
-          fin_from_hot = respawned || s.pending != 0 || A.o.image_u8 != nullptr;
-        }
-        else if (RR) need_rr = true;   // reset_random: rebuilt below, warp-converged
-        else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
+        if (RR) {  // worker.step_env (parallel_wrappers.py:27-37): reset_random
+          if (use_spec && !(flags & MGPLR_F_GOAL) && (sp & spec_valid_bit(spec_epoch(sp), 0)) && s.pending == 0) cand_pick = 0;
+          if (cand_pick >= 0) {
+            // take the pre-built successor level: goal / start (rows and the MT advance are done warp-wide below)
+            const uint32_t *rec = cand_record(d, e, spec_epoch(sp), cand_pick) + W;  // (L2 loads: written by another SM)
+            const uint32_t gs = __ldcg(rec), cerr = __ldcg(rec + 6);
+            cand_used = (int)__ldcg(rec + 5);
+            cand_idx = d.mti[e]; cand_words_used = d.words[e];  // (same round trip as the record fields)
+            s.gx = gs & 31; s.gy = (gs >> 5) & 31; s.sx = (gs >> 11) & 31; s.sy = (gs >> 16) & 31; s.sdir = (gs >> 22) & 3;
+            d.metrics[e] = make_int4(0, 0, kMetricsDirty, 0);  // recomputed on demand by mgplr_get_metrics
+            d.adv[e] &= ~0xfffu;  // adversary_step_count = 0 (adversarial.py:546)
+            if (cerr) d.err[e] |= cerr;
+            reset_agent(s);
+            dirty = true;
+          } else need_rr = true;  // no candidate: rebuilt below, warp-converged
+        } else if (!reset_agent(s)) d.err[e] |= kErrNoStart;
       } else if ((A.last_step & 3) == 3 && want_trunc) {
         rare_emit_trunc(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.trunc_image, A.o.trunc_direction, e, A.o.trunc_full_obs);
       }
     }
-    if (DEF) {
-      // A synchronized time-limit storm finishes (nearly) every env of the tile at once: one warp-wide finish job per env
-      // would serialise 32 of them, so such a tile rebuilds its envs right here, one per lane, with the plain lane-serial
-      // generator (the code path of MODE 1; the candidates are ignored -- the new levels are the same either way).
-      const unsigned fm0 = __ballot_sync(0xffffffffu, fin_entry != kFinEmpty);
-      if (__popc(fm0) > 10) {
-        need_rr = fin_entry != kFinEmpty;
-        if (need_rr && (fin_entry & kFinGoal) && !(fin_entry & kFinRespawned)) s.pending += 1;   // reset_random flushes it first
-        fin_entry = kFinEmpty;
-        fin_from_hot = false;
+    const long long pc1 = (RR && d.prof) ? clock64() : 0;
+    if (RR) {
+      // committed candidate records, all lanes together per finished env: one coalesced W-word read of the rows, and
+      // the words the record consumed are applied to the env's MT state (so regeneration jobs only read env state)
+      for (unsigned rest = __ballot_sync(0xffffffffu, cand_pick >= 0); rest; rest &= rest - 1) {
+        const int le = __ffs(rest) - 1, env = base + le;
+        const int pick = __shfl_sync(0xffffffffu, cand_pick, le), used_w = __shfl_sync(0xffffffffu, cand_used, le);
+        const uint32_t *rec = cand_record(d, env, spec_epoch(__shfl_sync(0xffffffffu, sp, le)), pick);
+        if (lane < W) rows[lane * kWarpTile + le] = __ldcg(rec + lane);
+        uint32_t idx = __shfl_sync(0xffffffffu, cand_idx, le), used = __shfl_sync(0xffffffffu, cand_words_used, le);
+        // the record carries the new MT state words of the span it consumed: coalesced reads, fire-and-forget stores
+        {
+          uint32_t nw[kSpecState / 32];
+#pragma unroll
+          for (int i = 0; i < kSpecState / 32; i++) nw[i] = __ldcg(rec + W + 8 + lane + 32 * i);
+#pragma unroll
+          for (int i = 0; i < kSpecState / 32; i++) {
+            const int j = lane + 32 * i;
+            if (j < used_w) {
+              uint32_t p = idx + j;
+              if (p >= 624) p -= 624;
+              d.mt[mt_at(env, p)] = nw[i];
+            }
+          }
+          idx += used_w;
+          if (idx >= 624) idx -= 624;
+          used += used_w;
+        }
+        if (lane == 0) { d.mti[env] = idx; d.words[env] = used; }
+        if (lane == le) new_idx = idx;
       }
-    }
-    // (DEF) the tile's slots in the finish list: one atomicAdd, issued here so that its round trip (~3 us under this kernel's
-    // memory load) runs behind the render / emit / store work below; the result is first read at the end of the tile.
-    // ptxas rewrites an atomic add on a warp-uniform address into its warp-aggregated form, whose shuffle consumes the result
-    // on the spot: a formally lane-dependent address keeps it one plain predicated ATOMG.
-    const unsigned fin_mask = DEF ? __ballot_sync(0xffffffffu, fin_entry != kFinEmpty) : 0u;
-    uint32_t cur_j0 = 0;
-    if (DEF && fin_mask) {
-      uint32_t *ctr = d.sched + kSchedPub + (lane << 5);
-      asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %1, 0;\n@p atom.global.add.u32 %0, [%2], %3;\n}"
-                   : "+r"(cur_j0) : "r"(lane), "l"(ctr), "r"((uint32_t)__popc(fin_mask)) : "memory");
-    }
-    if (MODE != 0) {
-      // Finished envs get a fresh random level.  Few per tile: the warp rebuilds them one at a time cooperatively; many (a
-      // synchronized time-limit storm): every lane rebuilds its own.
+      __syncwarp();
+      const long long pc2 = d.prof ? clock64() : 0;
+      if (d.prof) {
+        const unsigned cm = __ballot_sync(0xffffffffu, cand_pick >= 0);
+        if (cm && lane == 0) { atomicAdd(&d.prof[16], (unsigned long long)(pc1 - pc0)); atomicAdd(&d.prof[17], (unsigned long long)(pc2 - pc1)); atomicAdd(&d.prof[18], 1ull); }
+      }
+      // Finished envs without a candidate get a fresh random level the slow way.  Few per tile: the warp rebuilds them
+      // one at a time cooperatively; many (a synchronized time-limit storm): every lane rebuilds its own.
       const unsigned m = __ballot_sync(0xffffffffu, need_rr);
+      if (d.prof && need_rr) atomicAdd(&d.prof[9], 1ull);
+      if (d.prof && cand_pick >= 0) atomicAdd(&d.prof[8], 1ull);
+      if (d.prof) prof_commits += __popc(__ballot_sync(0xffffffffu, cand_pick >= 0 || need_rr));
       if (m) {
-        dirty = need_rr;
+        dirty = dirty || need_rr;
         if (__popc(m) > 10) {
-          // the batched-RNG scratch ([32][32] words) borrows the observation tile: wait for the previous tile's bulk store to
-          // have read it, and put the all-zero state planes back afterwards
-          if (d.use_tma && lane == 0) bulk_wait_read0();
-          __syncwarp();
-          uint32_t *scratch = reinterpret_cast<uint32_t *>(s_obs);
           if (need_rr)
             s = unpack(rare_reset_random(d, rows + lane, kWarpTile, pack(s), e, (c.resample && A.n_walls) ? A.n_walls[e] : -1,
-                                         scratch + lane, kWarpTile));
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < kV * kV; i++) s_obs[lane * kObsFloats + 2 * kV * kV + i] = 0.0f;
-          __syncwarp();
+                                         s_rng + lane, kWarpTile));
         } else {
           const uint4 mine = pack(s);
           for (unsigned rest = m; rest; rest &= rest - 1) {
@@ -1218,7 +1157,6 @@ __global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (MODE == 1 ? 3 : 4
     if (d.use_tma && lane == 0) bulk_wait_read0();
     __syncwarp();
     emit_packed_f32<SEE, false>(v, s_obs + lane * kObsFloats);
-    const long long tile_c1 = (DEF && d.prof) ? clock64() : 0;
     if (A.o.image) {
       float *gdst = A.o.image + (size_t)base * kObsFloats;
       if (n_tile == kWarpTile && (((uintptr_t)gdst) & 15u) == 0 && !d.use_tma) {
@@ -1239,187 +1177,59 @@ __global__ void __launch_bounds__(128, sizeof(EXT) == 8 ? 3 : (MODE == 1 ? 3 : 4
         __syncwarp();
       }
     }
-    const long long tile_c2 = (DEF && d.prof) ? clock64() : 0;
+    bool queue_me = false;
+    uint2 queue_job = make_uint2(0, 0);
+    const long long pc3 = (RR && d.prof) ? clock64() : 0;
     if (valid) {
-      const bool job_writes = DEF && fin_entry != kFinEmpty;   // hot record / direction / flags of the NEW level: the finish job's
-      if (!job_writes || fin_from_hot) st_hint_u4(&d.hot[e], pack(s), pol_keep);
-      if ((!DEF || dirty) && (flags & MGPLR_F_DONE) && d.err[e]) flags |= MGPLR_F_ERROR;  // an auto-reset failed: the host raises (mgplr_get_errors)
-      write_step_scalars(A, e, s, flags, (float)rew, fin_ret, fin_len, job_writes);
+      st_hint_u4(&d.hot[e], pack(s), pol_keep);
+      if ((flags & MGPLR_F_DONE) && d.err[e]) flags |= MGPLR_F_ERROR;  // an auto-reset failed: the host raises (mgplr_get_errors)
+      write_step_scalars(A, e, s, flags, (float)rew, fin_ret, fin_len);
       if (A.o.image_u8) rare_emit_u8(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.image_u8, e);
-      if (MODE != 0 && dirty) {
+      if (RR && dirty) {
         const Rows G = env_rows(d, e);
         for (int r = 0; r < W; r++) G.set(r, rows[r * kWarpTile + lane]);
+        if (use_spec) {  // new level epoch (drops the old candidates); its two candidates are built during the next launch
+          const uint32_t ne = (spec_epoch(sp) + 1u) & 127u;
+          *(volatile uint32_t *)&d.spec[e] = ne << kSpecEpochShift;
+          if (cand_pick < 0) new_idx = *(volatile uint32_t *)&d.mti[e];  // rebuilt the slow way: cursor as stored by the rebuild
+          queue_me = true;
+          queue_job = make_uint2(((uint32_t)e << 8) | ne, new_idx);
+        }
       }
     }
-    if (DEF) {
-      // (storm tile) the rebuilt envs start a new level epoch and queue their regeneration jobs: one atomic per warp
-      const unsigned qm = __ballot_sync(0xffffffffu, valid && dirty);
+    if (RR && use_spec) {
+      const unsigned qm = __ballot_sync(0xffffffffu, queue_me);
+      if (d.prof && qm && lane == 0) { atomicAdd(&d.prof[19], (unsigned long long)(pc3 - pc1)); atomicAdd(&d.prof[20], (unsigned long long)(clock64() - pc3)); }
       if (qm) {
-        uint32_t j0 = 0;
-        if (lane == 0) j0 = atomicAdd(&d.sched[A.spec_list & 1], (uint32_t)__popc(qm));
-        j0 = __shfl_sync(0xffffffffu, j0, 0);
-        if (valid && dirty) {
-          const uint32_t ne = (spec_epoch(d.spec[e]) + 1u) & 127u;
-          *(volatile uint32_t *)&d.spec[e] = (ne << kSpecEpochShift) | kSpecQueued;
-          const uint32_t j = j0 + __popc(qm & ((1u << lane) - 1u));
-          if (j < 2u * (uint32_t)N) d.rr_list[(size_t)(A.spec_list & 1) * 2 * N + j] = make_uint2(((uint32_t)e << 8) | ne, *(volatile uint32_t *)&d.mti[e]);
-        }
-      }
-    }
-    const long long tile_c3 = (DEF && d.prof) ? clock64() : 0;
-    if (DEF) {
-      // Finished envs -> the launch's finish list.  An entry is self-contained (see rr_finish_job) and, the observation apart,
-      // nothing the tile wrote for these envs is touched by the job, so there is no fence -- except for the rare from-hot
-      // entries.  The entries are stored one tile later (or after the loop): by then the tile's observation store has completed.
-      if (held_mask) {
-        // (the finish job writes the env's NEW observation over the one in this warp's bulk store of the finish tile: that
-        // store -- the older of at most two groups in flight, issued a tile ago -- must have completed)
-        if (held_plain) __threadfence();   // (partial tile / no TMA: the observation went out with plain stores)
-        else if (lane == 0) bulk_wait_all_but1();
-        __syncwarp();
-        const uint32_t j0 = __shfl_sync(0xffffffffu, held_j0, 0);
-        if (held_entry != kFinEmpty64) *(volatile uint64_t *)&d.fin_list[j0 + __popc(held_mask & ((1u << lane) - 1u))] = held_entry;
-        held_mask = 0;
-      }
-      const long long tile_c4 = d.prof ? clock64() : 0;
-      long long tile_c5 = tile_c4, tile_c6 = tile_c4;
-      if (fin_mask) {
-        if (__any_sync(0xffffffffu, fin_from_hot)) { __threadfence(); if (d.prof && lane == 0) atomicAdd(&d.prof[43], 1ull); }
-        __syncwarp();
-        tile_c5 = d.prof ? clock64() : 0;
-        held_j0 = cur_j0;
-        if (d.prof) { asm volatile("" :: "r"(held_j0) : "memory"); tile_c6 = clock64(); }
-        held_mask = fin_mask;
-        held_plain = !(d.use_tma && n_tile == kWarpTile && ((((uintptr_t)(A.o.image + (size_t)base * kObsFloats)) & 15u) == 0));
-        held_entry = kFinEmpty64;
-        if (fin_entry != kFinEmpty) {
-          const uint32_t hg = s.gx != kNone;
-          const uint32_t hi = ((uint32_t)s.gx & 31u) | (((uint32_t)s.gy & 31u) << 5) | (hg << 10) | (fin_from_hot ? kFinFromHot : 0u) |
-                              ((flags & 0xffu) << 16);
-          held_entry = ((uint64_t)hi << 32) | fin_entry;
-        }
-        if (d.prof) prof_fin += __popc(fin_mask);
-      }
-      if (d.prof && lane == 0) {
-        const unsigned long long dt = (unsigned long long)(clock64() - tile_c0);
-        if (fin_mask) { atomicAdd(&d.prof[3], dt); atomicAdd(&d.prof[4], 1ull); atomicMax(&d.prof[5], dt); }
-        else { atomicAdd(&d.prof[7], dt); atomicAdd(&d.prof[23], 1ull); atomicMax(&d.prof[6], dt); }
-        const int o = fin_mask ? 24 : 32;
-        atomicAdd(&d.prof[o + 0], (unsigned long long)(tile_c1 - tile_c0)); atomicAdd(&d.prof[o + 1], (unsigned long long)(tile_c2 - tile_c1));
-        atomicAdd(&d.prof[o + 2], (unsigned long long)(tile_c3 - tile_c2)); atomicAdd(&d.prof[o + 3], (unsigned long long)(clock64() - tile_c3));
-        atomicAdd(&d.prof[o + 4], (unsigned long long)(tile_c0 - tile_cw));
-        if (fin_mask) {
-          atomicAdd(&d.prof[40], (unsigned long long)(tile_c4 - tile_c3)); atomicAdd(&d.prof[41], (unsigned long long)(tile_c5 - tile_c4));
-          atomicAdd(&d.prof[42], (unsigned long long)(tile_c6 - tile_c5));
-        }
+        if (pend_n + __popc(qm) > kPendCap) flush_pending_jobs(d, rr_par, s_pend, pend_n, lane);
+        if (queue_me) s_pend[pend_n + __popc(qm & ((1u << lane) - 1u))] = queue_job;
+        pend_n += __popc(qm);
       }
     }
     tile = next;
-    next += total;
+    next = dyn ? tile0 + (int)__shfl_sync(0xffffffffu, ticket, 0) : next + total;
   }
-  if (DEF && held_mask) {   // the entries of the last finish tile
-    if (held_plain) __threadfence();
-    else if (lane == 0) bulk_wait_all0();
-    __syncwarp();
-    const uint32_t j0 = __shfl_sync(0xffffffffu, held_j0, 0);
-    if (held_entry != kFinEmpty64) *(volatile uint64_t *)&d.fin_list[j0 + __popc(held_mask & ((1u << lane) - 1u))] = held_entry;
-  }
+  if (RR && use_spec) flush_pending_jobs(d, rr_par, s_pend, pend_n, lane);
   if (lane == 0) bulk_wait_read0();
-  if (DEF && d.prof && lane == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    atomicMin(&d.prof[0], t); atomicMax(&d.prof[1], t);   // first / last warp past its tile pass
-    const unsigned long long dur = t - prof_start;
-    const int cls = prof_fin ? 13 : 10;                    // tile-pass time of warps with / without finished envs
+  unsigned long long prof_t0 = 0;
+  if (RR && d.prof && lane == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t0));
+    atomicMax(&d.prof[1], prof_t0);            // end of the last warp's tiles
+    atomicMin(&d.prof[0], prof_t0);            // end of the first warp's tiles
+    const unsigned long long dur = prof_t0 - prof_start;
+    const int cls = prof_commits ? 13 : 10;
     atomicAdd(&d.prof[cls], dur); atomicAdd(&d.prof[cls + 1], 1ull); atomicMax(&d.prof[cls + 2], dur);
   }
-  if (DEF) {
-    // ---- finish jobs: warps that are past their tiles serve the list as it fills
-    __syncwarp();
-    // Who serves the list: one warp in eight (warp 0 of every other CTA; global warp 0 always exists).  All warps polling one
-    // L2 sector delayed the very atomics they were waiting for by ~15 us, and claiming entries with compare-and-swap from a
-    // couple of hundred warps ran at ~1 claim per us.  So a serving warp takes a TICKET with one atomicAdd -- its own slot of the
-    // list, nobody else's -- and waits for that slot to be published, or for the list to be final (every warp has reported the
-    // end of its tile pass, sched[10]) and shorter than its ticket.  A ticket is never abandoned, so no entry can be lost;
-    // the wait is on the rest of this grid only, which is resident (the grid is sized by the occupancy calculator).
+  if (RR && use_spec) {
+    // last warp out: the list drained at the start of this launch becomes the next launch's append list
+    const int q = rr_par ^ 1;
     if (lane == 0) {
       __threadfence();
-      if (atomicAdd(&d.sched[kSchedPast], 1u) == (uint32_t)total - 1u)   // the list is final: tell the servers how long it is
-        *(volatile uint32_t *)&d.sched[kSchedFinal] = *(volatile uint32_t *)&d.sched[kSchedPub] | 0x80000000u;
-    }
-    const bool server = ((blockIdx.x * wpc + warp) & 7) == 0;
-    uint32_t *col = s_rows;   // the tile rows are no longer needed: scratch for one level
-    while (server) {
-      uint64_t entry = kFinEmpty64;
-      if (lane == 0) {
-        const uint32_t tk = atomicAdd(&d.sched[kSchedTicket], 1u);
-        unsigned backoff = 100;
-        for (;;) {
-          entry = *(volatile uint64_t *)&d.fin_list[tk];
-          if (entry != kFinEmpty64) { d.fin_list[tk] = kFinEmpty64; break; }
-          const uint32_t fin = *(volatile uint32_t *)&d.sched[kSchedFinal];
-          if ((fin & 0x80000000u) && tk >= (fin & 0x7fffffffu)) break;   // the list is final and ends before this ticket
-          __nanosleep(backoff);
-          if (backoff < 1600) backoff *= 2;
-        }
-      }
-      entry = __shfl_sync(0xffffffffu, entry, 0);
-      if (entry == kFinEmpty64) break;
-      const long long fc0 = d.prof ? clock64() : 0;
-      rr_finish_job<SEE, EXT>(d, entry, lane, col, A.spec_list & 1, A.o.image, A.o.direction, A.o.image_u8, A.o.flags, A.flags_host);
-      if (d.prof && lane == 0) {
-        const unsigned long long dt = (unsigned long long)(clock64() - fc0);
-        atomicAdd(&d.prof[16], dt); atomicAdd(&d.prof[18], 1ull); atomicMax(&d.prof[17], dt);
+      if (atomicAdd(&d.sched[4], 1u) == (uint32_t)total - 1u) {  // last warp out: the drained list becomes the next append list
+        d.sched[q] = 0; d.sched[2 + q] = 0; d.sched[4] = 0; d.sched[6] = 0;
+        d.sched[5] = (uint32_t)q;
       }
     }
-    if (d.prof && lane == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      atomicMax(&d.prof[22], t);                            // last warp out of the finish phase
-    }
-    if (lane == 0) {
-      __threadfence();
-      if (atomicAdd(&d.sched[kSchedExit], 1u) == (uint32_t)total - 1u) {
-        d.sched[kSchedExit] = 0; d.sched[kSchedPub] = 0; d.sched[kSchedTicket] = 0; d.sched[kSchedPast] = 0; d.sched[kSchedFinal] = 0;
-      }
-    }
-  }
-}
-
-// Regeneration kernel of the speculative DR auto-reset: builds the two successor candidates of every env that
-// step launch t reset (job list `q`), while step launch t+1 runs on the main stream.  Warps take job tickets; a storm's worth
-// of jobs (a synchronized time limit resets nearly every env) is built one env per LANE instead of one per warp.  The last warp
-// out empties the list for the launch after next.
-__global__ void __launch_bounds__(128) k_rr_regen(Dev d, int q) {
-  __shared__ __align__(16) uint32_t s_scr[4][1024];
-  asm volatile("griddepcontrol.launch_dependents;");   // the step launch behind this kernel may start right away
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, N = d.N;
-  const uint32_t total = gridDim.x * (blockDim.x >> 5), me = blockIdx.x * (blockDim.x >> 5) + warp;
-  const uint32_t n_jobs = min(*(volatile uint32_t *)&d.sched[q], 2u * (uint32_t)N);
-  const uint2 *list = d.rr_list + (size_t)q * 2 * N;
-  uint32_t *scr = s_scr[warp];
-  // Static assignment (no ticket traffic: the grid is sized for a storm, 7 CTAs per SM, and on an ordinary step all but the
-  // first hundred CTAs find nothing and leave).  A list longer than the grid has warps is built one env per LANE.
-  if (n_jobs > total) {
-    for (uint32_t j = 32u * me; j < n_jobs; j += 32u * total) {
-      if (j + lane < n_jobs) rr_regen_job_lane(d, __ldcg(list + j + lane), scr + lane);
-      __syncwarp();
-    }
-  } else {
-    for (uint32_t j = me; j < n_jobs; j += total) {
-      rr_regen_job(d, __ldcg(list + j), lane, scr);
-      __syncwarp();
-    }
-  }
-  if (d.prof && lane == 0) {
-    unsigned long long t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    atomicMax(&d.prof[2], t1);               // end of the regeneration kernel
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {   // last CTA out empties the list for the launch after next
-    __threadfence();
-    if (atomicAdd(&d.sched[7], 1u) == gridDim.x - 1u) { d.sched[q] = 0; d.sched[2 + q] = 0; d.sched[7] = 0; }
   }
 }
 
@@ -1541,26 +1351,19 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(dalloc(&d.limbs, 3 * N, total));
   CK(dalloc(&d.words, N, total));
   CK(dalloc(&d.err, N, total));
-  CK(dalloc(&d.sched, kSchedWords, total));
-  CK(cudaMemset(d.sched, 0, kSchedWords * sizeof(uint32_t)));
+  CK(dalloc(&d.sched, 8, total));
+  CK(cudaMemset(d.sched, 0, 8 * sizeof(uint32_t)));
   CK(dalloc(&d.spec, N, total));
   CK(cudaMemset(d.spec, 0, N * sizeof(uint32_t)));
-  d.cand = nullptr; d.rr_list = nullptr; d.fin_list = nullptr;  // DR speculation buffers: allocated by the first DR step launch (rr_spec_alloc)
+  d.cand = nullptr; d.rr_list = nullptr;  // DR speculation buffers: allocated by the first DR step launch (rr_spec_alloc)
   v->rr_spec = getenv("MGPLR_RR_SPEC") ? atoi(getenv("MGPLR_RR_SPEC")) : 1;  // DR speculation; 0 = in-kernel rebuild only
   v->host_dma = getenv("MGPLR_HOST_DMA") ? atoi(getenv("MGPLR_HOST_DMA")) : 0;
   CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&v->regen_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&v->regen_fork, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&v->regen_join, cudaEventDisableTiming));
-  v->rr_ctas = getenv("MGPLR_RR_CTAS") ? atoi(getenv("MGPLR_RR_CTAS")) : 4;
-  v->rr_dyn = getenv("MGPLR_RR_DYN") ? atoi(getenv("MGPLR_RR_DYN")) : 1;
-  v->rr_rgrid = getenv("MGPLR_RR_RGRID") ? atoi(getenv("MGPLR_RR_RGRID")) : 7;
-  v->rr_pdl = getenv("MGPLR_RR_PDL") ? atoi(getenv("MGPLR_RR_PDL")) : 1;
   for (int c = 0; c < 8; c++) CK(cudaEventCreateWithFlags(&v->copy_done[c], cudaEventDisableTiming));
   d.prof = nullptr;
   if (getenv("MGPLR_RR_PROF")) {  // debug: phase timestamps / job cycles of the DR step kernel (mgplr_debug_prof)
-    CK(cudaMalloc((void **)&d.prof, 48 * sizeof(unsigned long long)));
-    CK(cudaMemset(d.prof, 0, 48 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&d.prof, 24 * sizeof(unsigned long long)));
+    CK(cudaMemset(d.prof, 0, 24 * sizeof(unsigned long long)));
   }
   CK(dalloc(&v->seed_scratch, 4 * N, total));
   CK(dalloc(&v->act_dev, N, total));
@@ -1573,13 +1376,13 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   CK(cudaDeviceGetAttribute(&v->sm_count, cudaDevAttrMultiProcessorCount, device));
   {
     const int W = cfg->width;
-#define SET_STEP(SEE, MODE, EXT)                                                                        \
-  CK(cudaFuncSetAttribute(k_step_env<SEE, MODE, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                          (int)(4 * warp_smem_bytes(W, MODE != 0))));
+#define SET_STEP(SEE, RR, EXT)                                                                          \
+  CK(cudaFuncSetAttribute(k_step_env<SEE, RR, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                          (int)(4 * warp_smem_bytes(W, RR))));
 #define SET_ROLL(SEE, RR, TL, EXT) \
   CK(cudaFuncSetAttribute(k_rollout<SEE, RR, TL, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes(W, TL, 2)));
 #define SET_ALL(EXT)                                                                                  \
-  SET_STEP(true, 0, EXT) SET_STEP(true, 1, EXT) SET_STEP(true, 2, EXT) SET_STEP(false, 0, EXT) SET_STEP(false, 1, EXT) SET_STEP(false, 2, EXT) \
+  SET_STEP(true, false, EXT) SET_STEP(true, true, EXT) SET_STEP(false, false, EXT) SET_STEP(false, true, EXT) \
   SET_ROLL(true, false, 64, EXT) SET_ROLL(true, true, 64, EXT) SET_ROLL(false, false, 64, EXT) SET_ROLL(false, true, 64, EXT)
     if (W <= 24) { SET_ALL(uint32_t) } else { SET_ALL(uint64_t) }
 #undef SET_ALL
@@ -1606,12 +1409,9 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
   cudaSetDevice(v->device);
   Dev &d = v->d;
   if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
-  if (v->regen_stream) cudaStreamDestroy(v->regen_stream);
-  if (v->regen_fork) cudaEventDestroy(v->regen_fork);
-  if (v->regen_join) cudaEventDestroy(v->regen_join);
   for (int c = 0; c < 8; c++) if (v->copy_done[c]) cudaEventDestroy(v->copy_done[c]);
   cudaFree(d.wall); cudaFree(d.hot); cudaFree(d.adv); cudaFree(d.metrics); cudaFree(d.mt); cudaFree(d.mti);
-  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(d.spec); cudaFree(d.cand); cudaFree(d.rr_list); cudaFree(d.fin_list); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->cnt_dev); cudaFreeHost(v->res_pin);
+  cudaFree(d.limbs); cudaFree(d.words); cudaFree(d.err); cudaFree(d.sched); cudaFree(d.spec); cudaFree(d.cand); cudaFree(d.rr_list); cudaFree(v->seed_scratch); cudaFree(v->act_dev); cudaFree(v->cnt_dev); cudaFreeHost(v->res_pin);
   delete v;
 }
 
@@ -1620,9 +1420,8 @@ extern "C" void mgplr_venv_destroy(mgplr_venv *v) {
 extern "C" int mgplr_debug_prof(mgplr_venv *v, unsigned long long *out) {
   if (!v || !v->d.prof) return fail(MGPLR_E_BADARG, "profiling is off (MGPLR_RR_PROF)");
   CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, v->d.prof, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  unsigned long long init[48] = {~0ull};
-  init[21] = ~0ull;
+  CK(cudaMemcpy(out, v->d.prof, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long init[24] = {~0ull};
   CK(cudaMemcpy(v->d.prof, init, sizeof(init), cudaMemcpyHostToDevice));
   return 0;
 }
@@ -1785,8 +1584,6 @@ static int rr_spec_alloc(mgplr_venv *v) {
   const size_t N = (size_t)v->d.N;
   cudaError_t e = dalloc(&v->d.cand, N * 4 * (size_t)cand_words(v->d.c.W), v->bytes);
   if (e == cudaSuccess) e = dalloc(&v->d.rr_list, 4 * N, v->bytes);  // uint2 entries
-  if (e == cudaSuccess) e = dalloc(&v->d.fin_list, N + 8192, v->bytes);   // (+ one unpublished slot per serving warp's last ticket)
-  if (e == cudaSuccess) e = cudaMemset(v->d.fin_list, 0xff, (N + 8192) * sizeof(uint64_t));   // kFinEmpty everywhere
   if (e != cudaSuccess) {
     cudaGetLastError();
     v->d.cand = nullptr;
@@ -1813,44 +1610,14 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   const size_t smem = wpc * warp_smem_bytes(W, reset_random != 0);
   const int all_tiles = (v->d.N + kWarpTile - 1) / kWarpTile;
   const int n_tiles = (tile1 < 0 || tile1 > all_tiles) ? all_tiles : tile1;  // exclusive end of this launch's tile range
-  int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
-  if (per_sm > 4) per_sm = 4;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
+  int grid = v->sm_count * per_sm;
   const bool see = v->d.c.see_through, rr = reset_random != 0, narrow = W <= 24;
-  // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing regeneration kernel
+  // small batches finish less than one env per launch: the in-kernel rebuild is cheaper than a standing job phase
   // ... and a level with many walls does not fit the 224-word look-ahead window (2-3 words per try): no point in queueing jobs
   A.spec = rr && v->rr_spec && !v->d.c.fixed_env && !v->d.c.resample && (v->d.N >= 16384 || v->rr_spec > 1) &&
            v->d.c.n_clutter / 2 <= 56;
-  if (A.spec) {
-    if (int rc = rr_spec_alloc(v)) return rc;
-    // Regeneration of the levels that the PREVIOUS step launch reset: its own kernel, launched on the caller's stream right
-    // before this step launch, which is then launched as its PROGRAMMATIC DEPENDENT (it may start as soon as every
-    // regeneration CTA has started, griddepcontrol.launch_dependents at the top of k_rr_regen) and never waits for it: the
-    // step does not consume what the regeneration kernel produces in this launch (candidates are optional and validated by
-    // epoch), and everything the step does depend on -- the previous step launch -- had completed before the regeneration
-    // kernel could start.  Both run side by side on one stream: no events, no extra graph edges; the regeneration kernel of
-    // the next call is an ordinary launch and so follows both.  The step kernel leaves room for it (rr_ctas CTAs per SM).
-    A.spec_list = (int)(v->rr_calls & 1u);
-    const int drain = A.spec_list ^ 1;
-    v->rr_calls++;
-    if (v->rr_rgrid > 0) {   // (0: A/B knob -- no regeneration at all, every reset rebuilds its level in a finish job)
-      k_rr_regen<<<v->rr_rgrid * v->sm_count, 128, 0, st>>>(v->d, drain);
-      CK(cudaGetLastError());
-    }
-    if (per_sm > v->rr_ctas) per_sm = v->rr_ctas > 0 ? v->rr_ctas : 1;
-    // the finish phase waits on the other warps of the grid: never launch more CTAs than can be resident at once
-    if (v->rr_occ == 0) {
-      int occ = 0;
-      cudaError_t oe;
-      if (narrow) oe = see ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_env<true, 2, uint32_t>, wpc * 32, smem)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_env<false, 2, uint32_t>, wpc * 32, smem);
-      else oe = see ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_env<true, 2, uint64_t>, wpc * 32, smem)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_env<false, 2, uint64_t>, wpc * 32, smem);
-      if (oe != cudaSuccess) return cuda_fail(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-      v->rr_occ = occ > 0 ? occ : 1;
-    }
-    if (per_sm > v->rr_occ) per_sm = v->rr_occ;
-  }
-  int grid = v->sm_count * per_sm;
+  if (A.spec) { if (int rc = rr_spec_alloc(v)) return rc; }
   const int need = (n_tiles - tile0 + wpc - 1) / wpc;
   if (grid > need) grid = need;
   if (grid < 1) return 0;
@@ -1860,16 +1627,14 @@ static int launch_step_args(mgplr_venv *v, StepArgs &A, int32_t reset_random, cu
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = attr; lc.numAttrs = (v->pdl || (A.spec && v->rr_rgrid > 0 && v->rr_pdl)) ? 1 : 0;
-#define LAUNCH(SEE, MODE, EXT) CK(cudaLaunchKernelEx(&lc, k_step_env<SEE, MODE, EXT>, v->d, A, tile0, n_tiles))
+  lc.attrs = attr; lc.numAttrs = (v->pdl && !A.spec) ? 1 : 0;  // (the DR speculation reads a per-launch parity word)
+#define LAUNCH(SEE, RR, EXT) CK(cudaLaunchKernelEx(&lc, k_step_env<SEE, RR, EXT>, v->d, A, tile0, n_tiles))
 #define BY_MODE(EXT)                                  \
   do {                                                \
-    if (see && A.spec) LAUNCH(true, 2, EXT);          \
-    else if (see && rr) LAUNCH(true, 1, EXT);         \
-    else if (see) LAUNCH(true, 0, EXT);               \
-    else if (A.spec) LAUNCH(false, 2, EXT);           \
-    else if (rr) LAUNCH(false, 1, EXT);               \
-    else LAUNCH(false, 0, EXT);                       \
+    if (see && rr) LAUNCH(true, true, EXT);           \
+    else if (see) LAUNCH(true, false, EXT);           \
+    else if (rr) LAUNCH(false, true, EXT);            \
+    else LAUNCH(false, false, EXT);                   \
   } while (0)
   if (narrow) BY_MODE(uint32_t); else BY_MODE(uint64_t);
 #undef BY_MODE
@@ -2001,12 +1766,10 @@ extern "C" int mgplr_rollout_ex(mgplr_venv *v, const uint8_t *actions, int32_t T
 #define LAUNCH(SEE, RR, EXT) k_rollout<SEE, RR, 64, EXT><<<grid, 64, smem, st>>>(v->d, actions, T, A)
 #define BY_MODE(EXT)                                  \
   do {                                                \
-    if (see && A.spec) LAUNCH(true, 2, EXT);          \
-    else if (see && rr) LAUNCH(true, 1, EXT);         \
-    else if (see) LAUNCH(true, 0, EXT);               \
-    else if (A.spec) LAUNCH(false, 2, EXT);           \
-    else if (rr) LAUNCH(false, 1, EXT);               \
-    else LAUNCH(false, 0, EXT);                       \
+    if (see && rr) LAUNCH(true, true, EXT);           \
+    else if (see) LAUNCH(true, false, EXT);           \
+    else if (rr) LAUNCH(false, true, EXT);            \
+    else LAUNCH(false, false, EXT);                   \
   } while (0)
   if (narrow) BY_MODE(uint32_t); else BY_MODE(uint64_t);
 #undef BY_MODE

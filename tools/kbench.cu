@@ -72,7 +72,7 @@ int main(int argc, char **argv) {
     }
   }
   if (getenv("MGPLR_RR_PROF")) {  // phase timing of single DR launches
-    unsigned long long pr[48];
+    unsigned long long pr[24];
     mgplr_debug_prof(v, pr);
     for (int t = 0; t < 6; t++) {
       mgplr_step_out o = {};
@@ -80,25 +80,11 @@ int main(int argc, char **argv) {
       CKM(mgplr_step_env(v, act + (size_t)t * N, rr, nullptr, 0, &o, st));
       CKC(cudaStreamSynchronize(st));
       mgplr_debug_prof(v, pr);
-      printf("prof step %d: kernel start -> first warp past tiles %.1f us -> last %.1f us -> last warp out %.1f us\n", t,
-             (pr[0] - pr[21]) * 1e-3, (pr[1] - pr[21]) * 1e-3, (pr[22] - pr[21]) * 1e-3);
-      printf("   finish jobs %llu: avg %.1f us, max %.1f us; waits for an in-flight regeneration job %llu (avg %.1f us)\n", pr[18],
-             pr[18] ? pr[16] / (double)pr[18] / 1965.0 : 0.0, pr[17] / 1965.0, pr[19], pr[19] ? pr[20] / (double)pr[19] * 1e-3 : 0.0);
-      if (0) printf("prof step %d: tiles first->last %.1f us, regen phase %.1f us, jobs %llu, avg %.1f us (tables %.1f, level %.1f), max %.1f us\n", t,
+      printf("prof step %d: tiles first->last %.1f us, regen phase %.1f us, jobs %llu, avg %.1f us (tables %.1f, level %.1f), max %.1f us\n", t,
              (pr[1] - pr[0]) * 1e-3, pr[2] > pr[1] ? (pr[2] - pr[1]) * 1e-3 : 0.0, pr[4], pr[4] ? pr[3] / (double)pr[4] / 1965.0 : 0.0,
              pr[4] ? pr[6] / (double)pr[4] / 1965.0 : 0.0, pr[4] ? pr[7] / (double)pr[4] / 1965.0 : 0.0, pr[5] / 1965.0);
-      if (0) printf("   tiles with a commit (%llu): step block %.2f us, commit loop %.2f us, rebuild+render+emit %.2f us, write-back %.2f us\n", pr[18],
+      if (pr[18]) printf("   tiles with a commit (%llu): step block %.2f us, commit loop %.2f us, rebuild+render+emit %.2f us, write-back %.2f us\n", pr[18],
              pr[16] / (double)pr[18] / 1965.0, pr[17] / (double)pr[18] / 1965.0, pr[19] / (double)pr[18] / 1965.0, pr[20] / (double)pr[18] / 1965.0);
-      printf("   tiles with finished envs %llu: avg %.2f us, max %.2f us; other tiles %llu: avg %.2f us, max %.2f us\n", pr[4],
-             pr[4] ? pr[3] / (double)pr[4] / 1965.0 : 0.0, pr[5] / 1965.0, pr[23],
-             pr[23] ? pr[7] / (double)pr[23] / 1965.0 : 0.0, pr[6] / 1965.0);
-      for (int o = 24; o <= 32; o += 8) {
-        const double n = (o == 24 ? pr[4] : pr[23]) * 1965.0;
-        if (n > 0) printf("   %s tiles: wait rows %.2f, step+render %.2f, obs store %.2f, scalars %.2f, publish %.2f us\n", o == 24 ? "finish" : "other ",
-               pr[o + 4] / n, pr[o] / n, pr[o + 1] / n, pr[o + 2] / n, pr[o + 3] / n);
-      }
-      if (pr[4]) printf("   finish tiles, publish: held entries %.2f, fence %.2f (%llu fenced), slot wait %.2f us\n", pr[40] / (pr[4] * 1965.0),
-                        pr[41] / (pr[4] * 1965.0), pr[43], pr[42] / (pr[4] * 1965.0));
       printf("   resets from candidates %llu, rebuilt in the kernel %llu; tile phase per warp: no reset avg %.1f max %.1f us (%llu warps), with resets avg %.1f max %.1f us (%llu warps)\n", pr[8], pr[9],
              pr[11] ? pr[10] / (double)pr[11] * 1e-3 : 0.0, pr[12] * 1e-3, pr[11], pr[14] ? pr[13] / (double)pr[14] * 1e-3 : 0.0, pr[15] * 1e-3, pr[14]);
     }
