@@ -1333,6 +1333,15 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   Dev &d = v->d;
   d.N = num_envs;
   d.l2_hints = getenv("MGPLR_L2_HINTS") ? atoi(getenv("MGPLR_L2_HINTS")) : 1;
+  if (getenv("MGPLR_L2_PERSIST_MB")) {
+    // A/B knob: an L2 set-aside for persisting (evict_last) lines, cudaLimitPersistingL2CacheSize -- device-wide
+    int max_persist = 0;
+    CK(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device));
+    size_t want = (size_t)atoi(getenv("MGPLR_L2_PERSIST_MB")) << 20;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    if (getenv("MGPLR_VERBOSE")) fprintf(stderr, "mgplr: persisting L2 set-aside %zu MB (device max %d MB)\n", want >> 20, max_persist >> 20);
+  }
   d.use_tma = getenv("MGPLR_TMA") ? atoi(getenv("MGPLR_TMA")) : 1;
   v->pdl = getenv("MGPLR_PDL") ? atoi(getenv("MGPLR_PDL")) : 0;  // measured: no gain at 131 072 envs, slower at 4 096
   d.c = Cfg{cfg->width, cfg->max_steps, cfg->max_episode_steps, cfg->see_through_walls != 0, cfg->n_clutter,
