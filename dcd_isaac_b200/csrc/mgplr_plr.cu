@@ -576,19 +576,26 @@ __device__ double block_sum2(double v, double w2, double *red, double &out2) {
   return r;
 }
 
-// _score_transform (level_sampler.py:752-785) for the transforms the shipped configs use:
-//   1 rank:     w = 1 / rank^(1/T), rank 1 = highest value, ties by index (see before())
-//   2 power:    w = (clip(v, 0) + eps)^(1/T)
-//   0 constant: w = 1
+// _score_transform (level_sampler.py:752-785):
+//   1 rank:       w = 1 / rank^(1/T), rank 1 = highest value, ties by index (see before())
+//   2 power:      w = (clip(v, 0) + eps)^(1/T)
+//   0 constant:   w = 1
+//   3 softmax:    w = exp(v / T)
+//   4 match:      w = ((1 - v) v)^(1/T)
+//   5 match_rank: rank transform of (1 - v) v
+//   6 eps_greedy: w = eps / n everywhere, + (1 - eps) at argmax(v) (first index of the maximum: numpy argmax); `eps` is the
+//                 sampler's eps here, not the power transform's offset
+// ('max' draws its argmax tie-break from np.random inside the transform: not built.)
 // out[i] receives the raw transform of vals[i]; `keys` is dynamic shared memory for the sort.
 __device__ void transform_vals(int transform, const double *vals, int n, double temperature, double eps, double *out, Key *keys) {
   const double inv_t = 1.0 / temperature;
-  if (transform == 1) {
+  if (transform == 1 || transform == 5) {
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
       Key k;
-      k.s = (i < n) ? vals[i] : -INFINITY; k.i = (i < n) ? i : -1 - i;
+      const double v = (i < n) ? vals[i] : 0.0;
+      k.s = (i < n) ? (transform == 5 ? __dmul_rn(__dsub_rn(1.0, v), v) : v) : -INFINITY; k.i = (i < n) ? i : -1 - i;
       keys[i] = k;
     }
     __syncthreads();
@@ -599,6 +606,37 @@ __device__ void transform_vals(int transform, const double *vals, int n, double 
     // an admission mostly consisted of with the default staleness temperature 1 (10.7 us per draw at 4 000 slots)
     if (inv_t == 1.0) { for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = fmax(vals[i], 0.0) + eps; }
     else for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = pow(fmax(vals[i], 0.0) + eps, inv_t);
+  } else if (transform == 3) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = exp(vals[i] / temperature);
+  } else if (transform == 4) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double m = __dmul_rn(__dsub_rn(1.0, vals[i]), vals[i]);
+      out[i] = inv_t == 1.0 ? m : pow(m, inv_t);
+    }
+  } else if (transform == 6) {
+    // first index of the maximum: pack (value, -index) comparisons through one shared slot per warp, then thread 0
+    __shared__ double s_best_v[32];
+    __shared__ int s_best_i[32];
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (vals[i] > bv || (vals[i] == bv && i < bi)) { bv = vals[i]; bi = i; }
+    for (int o = 16; o; o >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_best_v[threadIdx.x >> 5] = bv; s_best_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < (int)((blockDim.x + 31) >> 5); w++)
+        if (s_best_v[w] > bv || (s_best_v[w] == bv && s_best_i[w] < bi)) { bv = s_best_v[w]; bi = s_best_i[w]; }
+      s_best_i[0] = bi;
+    }
+    __syncthreads();
+    const int am = s_best_i[0];
+    const double base = eps / (double)n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = (i == am) ? __dadd_rn(__dsub_rn(1.0, eps), base) : base;
   } else {
     for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = 1.0;
   }
@@ -703,7 +741,9 @@ extern "C" int mgplr_plr_score_weights(const double *scores, const double *unsee
   return 0;
 }
 
-static int check_transform(int t) { return (t >= 0 && t <= 2) ? 0 : pfail(MGPLR_E_UNSUPPORTED, "transform must be 0 constant, 1 rank or 2 power"); }
+static int check_transform(int t) {
+  return (t >= 0 && t <= 6) ? 0 : pfail(MGPLR_E_UNSUPPORTED, "transform must be 0 constant, 1 rank, 2 power, 3 softmax, 4 match, 5 match_rank or 6 eps_greedy");
+}
 
 extern "C" int mgplr_plr_sample_weights(const double *scores, const double *staleness, const double *unseen, int32_t n,
                                         int32_t score_transform, double temperature, double eps, double staleness_coef,
@@ -745,7 +785,7 @@ __global__ void __launch_bounds__(1024) k_sample_replay(const double *scores, do
   if (staged) {   // layout: [keys scratch (only used by a rank STALENESS transform) | w_rank | weights | staleness | unseen]
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
-    double *base = reinterpret_cast<double *>(sm + (a.stale_transform == 1 ? (size_t)n2 * sizeof(Key) : 0));
+    double *base = reinterpret_cast<double *>(sm + ((a.stale_transform == 1 || a.stale_transform == 5) ? (size_t)n2 * sizeof(Key) : 0));
     double *s_w = base, *s_wt = base + n, *s_st = base + 2 * (size_t)n, *s_un = base + 3 * (size_t)n;
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) { s_w[i] = w_rank[i]; s_st[i] = staleness_g[i]; s_un[i] = unseen_g[i]; }
@@ -809,7 +849,7 @@ extern "C" int mgplr_plr_sample_replay(const double *scores, double *staleness, 
   if (int rc = ensure_dscratch(2 * (size_t)kMaxBuf)) return rc;
   const int staged = n <= kStageMax;
   size_t smem = sort_smem(n);
-  if (staged) smem = (staleness_transform == 1 ? smem : 0) + 4 * (size_t)n * sizeof(double);
+  if (staged) smem = ((staleness_transform == 1 || staleness_transform == 5) ? smem : 0) + 4 * (size_t)n * sizeof(double);
   if (!score_weights_in && smem < sort_smem(n)) smem = sort_smem(n);
   PCK(cudaFuncSetAttribute(k_sample_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const WeightArgs a{score_transform, staleness_transform, temperature, eps, staleness_coef, staleness_temperature};
@@ -1101,7 +1141,7 @@ extern "C" int mgplr_plr_apply_records(const mgplr_episode *records, const int32
     k_record_uid<<<(upper + 255) / 256, 256, 0, st>>>(a);
     PCK(cudaGetLastError());
   }
-  const int staged = n_buf <= kStageMax && staleness_transform != 1;  // (a rank STALENESS transform sorts in the aliased key region)
+  const int staged = n_buf <= kStageMax && staleness_transform != 1 && staleness_transform != 5 && score_transform != 5;  // (those sort in the aliased key region)
   const size_t smem = sort_smem(n_buf) + (staged ? (size_t)n_buf * (3 * sizeof(double) + sizeof(int32_t)) : 0);
   PCK(cudaFuncSetAttribute(k_apply_records, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_apply_records<<<1, 1024, smem, st>>>(a, staged);

@@ -19,7 +19,7 @@ the staging set) brings up to date.  Random decisions consume the GLOBAL np.rand
 (level_sampler.py:611,616,674): one random_sample() per replay decision (only when the fill test passes) and one per draw.
 
 Deviations: ties in the rank transform are broken by index (the reference inherits numpy's unspecified
-quicksort order); only the constant / rank / power transforms and the strategies in _KERNEL_STRATEGY are built; a rollout
+quicksort order); every transform but `max` and the strategies in _KERNEL_STRATEGY are built; a rollout
 whose last step is not `done` (never produced by the reference runner) is scored on [start, T) instead of the reference's
 off-by-one slices, and such tails are carried per (actor, seed) instead of per (actor, buffer slot).
 """
@@ -28,7 +28,7 @@ import numpy as np
 INT32_MAX = 2147483647
 MAX_BUFFER = 8192     # one CTA sorts / scans the buffer in shared memory (mgplr_plr.cu kMaxBuf)
 
-_TRANSFORMS = {'constant': 0, 'rank': 1, 'power': 2}
+_TRANSFORMS = {'constant': 0, 'rank': 1, 'power': 2, 'softmax': 3, 'match': 4, 'match_rank': 5, 'eps_greedy': 6}
 _KERNEL_STRATEGY = {  # -> (MGPLR_SCORE_* code)
     'positive_value_loss': 0, 'signed_value_loss': 1, 'gae': 1, 'value_l1': 2,
     'grounded_signed_value_loss': 3, 'uniform': 3,
@@ -154,11 +154,13 @@ class LevelSampler(object):
 
     def _transform_code(self, name):
         if name not in _TRANSFORMS:
-            raise NotImplementedError('transform %r is not part of the B200 build (constant, rank, power are)' % name)
+            raise NotImplementedError('transform %r is not part of the B200 build (%s are)' % (name, ', '.join(sorted(_TRANSFORMS))))
         return _TRANSFORMS[name]
 
     def _weight_args(self):
         eps = 0.0 if self.staleness_coef > 0 else 1e-3  # level_sampler.py:771
+        if self.score_transform == 'eps_greedy':
+            eps = float(self.eps)                        # level_sampler.py:762-764
         return (self._transform_code(self.score_transform), float(self.temperature), eps, float(self.staleness_coef),
                 self._transform_code(self.staleness_transform), float(self.staleness_temperature))
 

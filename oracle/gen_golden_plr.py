@@ -209,6 +209,40 @@ def gen_weights():
     print('weights fixtures ok')
 
 
+def gen_transforms():
+    """sample_weights + 30 sequential replay draws under the score transforms beyond the shipped configs' constant / rank /
+    power: softmax, match, match_rank, eps_greedy (level_sampler.py:752-785), with and without the staleness mix."""
+    import numpy as np
+    from level_replay import LevelSampler
+    from gym import spaces
+    rs = np.random.RandomState(11)
+    out = {}
+    for transform in ('softmax', 'match', 'match_rank', 'eps_greedy'):
+        for tag, n, temp, sc in (('a', 600, 0.3, 0.3), ('b', 37, 1.0, 0.0), ('c', 4000, 0.5, 0.1)):
+            s = LevelSampler([], {'image': spaces.Box(0, 255, (3, 5, 5), 'uint8')}, spaces.Discrete(7), num_actors=4,
+                             strategy='positive_value_loss', score_transform=transform, temperature=temp, eps=0.07, rho=0.5,
+                             replay_prob=0.5, staleness_coef=sc, staleness_transform='power', staleness_temperature=1.0,
+                             sample_full_distribution=True, seed_buffer_size=n)
+            scores = rs.rand(n)
+            unseen = (rs.rand(n) < 0.2).astype(np.float64)
+            stale = np.floor(rs.rand(n) * 50)
+            s.seed_scores[:] = scores
+            s.unseen_seed_weights[:] = unseen
+            s.seed_staleness[:] = stale
+            s.seeds[:] = np.arange(1, n + 1)
+            s.working_seed_buffer_size = n
+            k = transform + '_' + tag
+            out['scores_' + k], out['unseen_' + k], out['stale_' + k] = scores, unseen, stale
+            out['weights_' + k] = s.sample_weights()
+            out['params_' + k] = np.array([temp, sc, 0.07])
+            np.random.seed(321)
+            picks = [s.sample_replay_level() for _ in range(30)]
+            out['picks_' + k] = np.array(picks, dtype=np.int64) - 1
+            out['stale_after_' + k] = s.seed_staleness.copy()
+    np.savez_compressed(os.path.join(GOLDEN, 'plr_transforms.npz'), **out)
+    print('transform fixtures ok')
+
+
 class _StubPopart(object):
     def denormalize(self, x):
         return x
@@ -350,8 +384,13 @@ def gen_plr():
     gen_score_functions()
     gen_storage()
     gen_weights()
+    gen_transforms()
     gen_sampler()
 
 
 if __name__ == '__main__':
-    gen_plr()
+    if len(sys.argv) > 1 and sys.argv[1] == 'transforms':   # only the (round-2) transform fixtures
+        rh.activate()
+        gen_transforms()
+    else:
+        gen_plr()

@@ -122,12 +122,24 @@ def _transform(name, temperature, vals, eps):
         return 1 / ranks ** (1. / temperature)
     if name == 'power':
         return (np.array(vals).clip(0) + eps) ** (1. / temperature)
+    if name == 'softmax':
+        return np.exp(np.array(vals) / temperature)
+    if name == 'match':
+        return ((1 - np.array(vals)) * np.array(vals)) ** (1. / temperature)
+    if name == 'match_rank':
+        return _transform('rank', temperature, (1 - np.array(vals)) * np.array(vals), eps)
+    if name == 'eps_greedy':          # (eps is the sampler's eps here: level_sampler.py:762-764)
+        w = np.zeros_like(vals)
+        w[np.argmax(vals)] = 1. - eps
+        return w + eps / len(vals)
     raise NotImplementedError(name)
 
 
 def sample_weights(scores, staleness, unseen, score_transform='rank', temperature=0.3, staleness_coef=0.3,
-                   staleness_transform='power', staleness_temperature=1.0):
+                   staleness_transform='power', staleness_temperature=1.0, sampler_eps=0.05):
     eps = 0 if staleness_coef > 0 else 1e-3
+    if score_transform == 'eps_greedy':
+        eps = sampler_eps
     w = _transform(score_transform, temperature, scores, eps) * (1 - unseen)
     z = np.sum(w)
     if z > 0:

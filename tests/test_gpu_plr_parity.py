@@ -147,7 +147,9 @@ def _rec_array(recs):
 @pytest.mark.parametrize('strategy,alpha,coef,priority,transform', [
     ('positive_value_loss', 1.0, 0.0, 'replay_support', 'rank'), ('positive_value_loss', 0.7, 0.3, 'replay_support', 'rank'),
     ('grounded_signed_value_loss', 1.0, 0.0, 'replay_support', 'rank'), ('value_l1', 0.5, 0.0, 'score', 'rank'),
-    ('value_l1', 1.0, 0.0, 'replay_support', 'power'), ('uniform', 1.0, 0.0, 'replay_support', 'rank')])
+    ('value_l1', 1.0, 0.0, 'replay_support', 'power'), ('uniform', 1.0, 0.0, 'replay_support', 'rank'),
+    ('positive_value_loss', 1.0, 0.0, 'replay_support', 'softmax'), ('positive_value_loss', 0.7, 0.0, 'replay_support', 'match_rank'),
+    ('value_l1', 1.0, 0.0, 'replay_support', 'match'), ('positive_value_loss', 1.0, 0.0, 'replay_support', 'eps_greedy')])
 def test_device_record_walk_vs_oracle(strategy, alpha, coef, priority, transform):
     """mgplr_plr_apply_records (the single-CTA walk over the episode records: EWA updates, staging -> working admission with
     eviction by argmin of sample_weights, incremental ranks) against the sequential oracle that is pinned by the recorded
@@ -290,6 +292,31 @@ def test_sample_weights_and_replay_golden():
         picks += s.sample_replay_levels(20)
         assert np.array_equal(np.array(picks) - 1, g['picks_' + tag])
         assert np.array_equal(s.seed_staleness, g['stale_after_' + tag])
+
+
+@pytest.mark.parametrize('transform', ['softmax', 'match', 'match_rank', 'eps_greedy'])
+def test_extra_score_transforms_golden(transform):
+    """The transforms beyond constant / rank / power against the reference's own sample_weights() and replay draws
+    (tests/golden/plr_transforms.npz), through the device kernels."""
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    g = golden('plr_transforms.npz')
+    for tag in 'abc':
+        k = transform + '_' + tag
+        temp, sc, eps = g['params_' + k]
+        n = len(g['scores_' + k])
+        s = LevelSampler([], None, None, num_actors=4, strategy='positive_value_loss', score_transform=transform,
+                         temperature=float(temp), eps=float(eps), staleness_coef=float(sc), staleness_transform='power',
+                         staleness_temperature=1.0, sample_full_distribution=True, seed_buffer_size=n)
+        s.seed_scores[:] = g['scores_' + k]
+        s.unseen_seed_weights[:] = g['unseen_' + k]
+        s.seed_staleness[:] = g['stale_' + k]
+        s.seeds[:] = np.arange(1, n + 1)
+        s.working_seed_buffer_size = n
+        assert np.allclose(s.sample_weights(), g['weights_' + k], rtol=1e-9, atol=1e-300), k
+        np.random.seed(321)
+        picks = [s.sample_replay_level() for _ in range(10)] + s.sample_replay_levels(20)
+        assert np.array_equal(np.array(picks) - 1, g['picks_' + k]), k
+        assert np.array_equal(s.seed_staleness, g['stale_after_' + k]), k
 
 
 def _assert_weights_match(w, ref, s, cyc):

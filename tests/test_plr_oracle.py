@@ -31,6 +31,24 @@ def test_sample_weights_and_draws():
         assert np.array_equal(stale, g['stale_after_' + tag])
 
 
+def test_extra_score_transforms():
+    """softmax / match / match_rank / eps_greedy (level_sampler.py:752-785) against the reference's sample_weights and 30 replay
+    draws (oracle/gen_golden_plr.py::gen_transforms); the uniforms are re-drawn from the same np.random seed."""
+    g = golden('plr_transforms.npz')
+    for transform in ('softmax', 'match', 'match_rank', 'eps_greedy'):
+        for tag in 'abc':
+            k = transform + '_' + tag
+            temp, sc, eps = g['params_' + k]
+            kw = dict(score_transform=transform, temperature=temp, staleness_coef=sc, staleness_temperature=1.0, sampler_eps=eps)
+            w = po.sample_weights(g['scores_' + k], g['stale_' + k], g['unseen_' + k], **kw)
+            assert np.allclose(w, g['weights_' + k], rtol=1e-12, atol=0), k
+            np.random.seed(321)
+            u = np.array([np.random.random_sample() for _ in range(30)])
+            idx, stale = po.sample_replay(g['scores_' + k], g['stale_' + k], g['unseen_' + k], u, **kw)
+            assert np.array_equal(idx, g['picks_' + k]), k
+            assert np.array_equal(stale, g['stale_after_' + k]), k
+
+
 def test_storage_returns_and_value_loss():
     """discounted returns bit-exact, batched value loss to 1e-6 against the executed reference RolloutStorage."""
     g = golden('plr_storage.npz')
