@@ -12,7 +12,7 @@ between them, so `roofline.avg_launch_us` is the step kernel's launch time INSID
 (avg_launch_us * T <= ms_per_step by construction).  `variants` repeats the measurement for the other configurations
 north_star names (25x25 / 50 blocks with occlusion, 15x15 with occlusion, DR auto-reset) at the same envs/GPU, each
 with its own roofline fraction.  `e2e` drives the same rollout through the host-buffer C-ABI call
-(mgplr_step_env_host_u8 every vector step: the kernel reads the pinned uint8 actions over PCIe and writes flags + done
+(mgplr_step_env_host_u8 every vector step: the kernel reads the pinned uint8 actions over PCIe and appends the done
 records back to pinned host memory).  `cpu_baseline` = the C port of the reference algorithm on all host threads;
 `cpu_baseline_python` = the reference's OWN vectorised Python path (util.create_parallel_env -> step_env loop from the
 staged copy baseline/_ref/reference) on the same host cores.
@@ -477,12 +477,12 @@ def run_ours(a):
     if not a.no_e2e:
         stream = torch.cuda.current_stream(dev).cuda_stream
         h_act = B.actions_u8.cpu().pin_memory()
-        h_flg = torch.zeros(N, dtype=torch.uint8).pin_memory()
         h_done = torch.zeros(N * 16, dtype=torch.uint8).pin_memory()
         h_nd = torch.zeros(1, dtype=torch.int32).pin_memory()
         hp = [ptr(h_act[t]) for t in range(T)]
         nd_np = h_nd.numpy()  # (reading the count through numpy: no tensor indexing in the per-step loop)
-        p_flg, p_done, p_nd = ptr(h_flg), ptr(h_done), ptr(h_nd)
+        # (no flags array: since ABI v4 the done records carry each finished env's flags, and only finished envs have any)
+        p_flg, p_done, p_nd = None, ptr(h_done), ptr(h_nd)
         step_host = L.mgplr_step_env_host_u8
         out_refs = [C.byref(o) for o in outs]
         done_seen = [0]
@@ -516,9 +516,9 @@ def run_ours(a):
             ems = float(tt.item())
         dones_per_rollout = done_seen[0] // (ksteps + 1)
         e2e = {'value': N * T * ksteps * world / (ems * 1e-3), 'unit': 'env-steps/s',
-               'h2d_bytes_per_step': T * N, 'd2h_bytes_per_step': T * N + 16 * dones_per_rollout + 4,
+               'h2d_bytes_per_step': T * N, 'd2h_bytes_per_step': 16 * dones_per_rollout + 4 * T + 4,
                'api': 'mgplr_step_env_host_u8 every vector step (T calls per rollout): the kernel reads the pinned uint8 actions over PCIe '
-                      '(zero-copy), writes flags u8[N] and the done records into pinned host memory, one stream sync per vector step; '
+                      '(zero-copy) and appends the done records (env, reward, episode return, length | flags) to pinned host memory, one stream sync per vector step; '
                       'observations / rewards / masks stay in rollout storage'}
     venv.close()
 

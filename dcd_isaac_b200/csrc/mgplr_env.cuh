@@ -30,7 +30,7 @@ struct Cfg {
 struct Dev {
   int N;
   int use_tma;       // 1: TMA bulk copies for the tile rows / observation tile; 0: cp.async + vector stores (A/B knob)
-  int l2_hints;      // 1: L2 eviction-priority hints in the step kernel (level + hot records evict_last, observations evict_first)
+  int l2_hints;      // bit mask of the step kernel's L2 hints (mgplr_venv_create): 5 = eviction priorities + streaming scalar stores
   Cfg c;
   uint32_t *wall;    // [ceil(N/32)][W][32] wall bit-plane rows (bit x of row y), tile-major: see env_rows()
   uint4 *hot;        // [N] x: ax6|ay6|adir2|has1|done1|step16  y: gx5|gy5|hasgoal1|sx5|sy5|hasstart1|sdir2|pending8  z: elapsed16|eplen16  w: ep_ret bits

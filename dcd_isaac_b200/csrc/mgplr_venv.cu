@@ -590,6 +590,7 @@ struct StepArgs {
   mgplr_done_record *done_list;  // device view of pinned host memory: records cross PCIe as posted writes
   uint8_t *flags_host;           // second flags destination (mapped pinned host memory) or NULL
   int spec;                      // DR auto-reset: speculative next-level candidates enabled (mgplr_env.cuh "SPECULATION")
+  int stream_scalars;            // A/B (MGPLR_L2_HINTS bit 2): streaming stores for the per-env scalars, streaming action loads
 };
 
 // ---- rare paths, kept out of line with by-value arguments so the common path stays in registers ----
@@ -707,14 +708,24 @@ __device__ __forceinline__ void write_step_scalars(const StepArgs &A, int e, con
   if (A.done_count && (flags & MGPLR_F_DONE)) {
     const uint32_t k = atomicAdd(A.done_count, 1u);
     mgplr_done_record r;
-    r.env = e; r.reward = rew; r.ep_return = ep_ret; r.ep_length = ep_len;
+    r.env = e; r.reward = rew; r.ep_return = ep_ret; r.ep_length = (int32_t)((uint32_t)ep_len | (flags << 24));
     A.done_list[k] = r;
+  }
+  const bool done = flags & MGPLR_F_DONE, last = A.last_step & 1, cliff = last && (A.last_step & 2) && !done;
+  if (A.stream_scalars) {   // (A/B, MGPLR_L2_HINTS bit 2) written once, read much later: streaming stores
+    if (o.direction) __stcs(&o.direction[e], (float)s.adir);
+    if (o.reward) __stcs(&o.reward[e], rew);
+    if (o.flags) __stcs(reinterpret_cast<unsigned char *>(&o.flags[e]), (unsigned char)flags);
+    if (A.flags_host) A.flags_host[e] = (uint8_t)flags;
+    if (o.masks) __stcs(&o.masks[e], (done || last) ? 0.f : 1.f);
+    if (o.bad_masks) __stcs(&o.bad_masks[e], ((flags & MGPLR_F_TRUNC_KEY) || cliff) ? 0.f : 1.f);
+    if (o.cliffhanger_masks) __stcs(&o.cliffhanger_masks[e], cliff ? 0.f : 1.f);
+    return;
   }
   if (o.direction) o.direction[e] = (float)s.adir;
   if (o.reward) o.reward[e] = rew;
   if (o.flags) o.flags[e] = (uint8_t)flags;
   if (A.flags_host) A.flags_host[e] = (uint8_t)flags;
-  const bool done = flags & MGPLR_F_DONE, last = A.last_step & 1, cliff = last && (A.last_step & 2) && !done;
   if (o.masks) o.masks[e] = (done || last) ? 0.f : 1.f;
   if (o.bad_masks) o.bad_masks[e] = ((flags & MGPLR_F_TRUNC_KEY) || cliff) ? 0.f : 1.f;
   if (o.cliffhanger_masks) o.cliffhanger_masks[e] = cliff ? 0.f : 1.f;
@@ -962,7 +973,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
 #pragma unroll
   for (int i = 0; i < kV * kV; i++) s_obs[lane * kObsFloats + 2 * kV * kV + i] = 0.0f;
   __syncwarp();
-  const uint64_t pol_keep = l2_policy(d.l2_hints ? 1 : 0), pol_stream = l2_policy(d.l2_hints ? 2 : 0);
+  const uint64_t pol_keep = l2_policy((d.l2_hints & 16) ? 2 : ((d.l2_hints & 1) && !(d.l2_hints & 32)) ? 1 : 0), pol_stream = l2_policy((d.l2_hints & 1) && !(d.l2_hints & 8) ? 2 : 0);
+  const uint64_t pol_hot = (d.l2_hints & 64) ? l2_policy(2) : (d.l2_hints & 128) ? l2_policy(0) : pol_keep;
   if (A.done_count_next && blockIdx.x == 0 && threadIdx.x == 0) *A.done_count_next = 0;
   // Tile assignment: static round-robin (tile = global_warp + k * total_warps) -- a dynamic scheduler on one global
   // counter doubled the reset_agent variant's launch time -- EXCEPT in the speculative DR variant, where warps carry very
@@ -985,8 +997,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
   int na = 6;
   uint32_t nsp = 0;  // speculation word of the env (DR variant)
   if (tile < n_tiles && tile * kWarpTile + lane < N) {
-    nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_keep);
-    na = A.action_u8 ? (int)A.action_u8[tile * kWarpTile + lane] : (int)A.action[tile * kWarpTile + lane];
+    nh = ld_hint_u4(&d.hot[tile * kWarpTile + lane], pol_hot);
+    na = A.action_u8 ? (int)A.action_u8[tile * kWarpTile + lane] : (int)(A.stream_scalars ? __ldcs(&A.action[tile * kWarpTile + lane]) : A.action[tile * kWarpTile + lane]);
     if (use_spec) nsp = d.spec[tile * kWarpTile + lane];
   }
   uint32_t phase = 0;  // bit s = parity to wait for on bars[s]
@@ -1004,8 +1016,8 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     if (next < n_tiles) {
       warp_issue_rows(d, s_rows + (st ^ 1) * W * kWarpTile, &bars[st ^ 1], next, lane, pol_keep);
       if (next * kWarpTile + lane < N) {
-        nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_keep);
-        na = A.action_u8 ? (int)A.action_u8[next * kWarpTile + lane] : (int)A.action[next * kWarpTile + lane];
+        nh = ld_hint_u4(&d.hot[next * kWarpTile + lane], pol_hot);
+        na = A.action_u8 ? (int)A.action_u8[next * kWarpTile + lane] : (int)(A.stream_scalars ? __ldcs(&A.action[next * kWarpTile + lane]) : A.action[next * kWarpTile + lane]);
         if (use_spec) nsp = d.spec[next * kWarpTile + lane];
       }
     }
@@ -1181,7 +1193,7 @@ __global__ void __launch_bounds__(128, RR ? 3 : (sizeof(EXT) == 8 ? 3 : 4)) k_st
     uint2 queue_job = make_uint2(0, 0);
     const long long pc3 = (RR && d.prof) ? clock64() : 0;
     if (valid) {
-      st_hint_u4(&d.hot[e], pack(s), pol_keep);
+      st_hint_u4(&d.hot[e], pack(s), pol_hot);
       if ((flags & MGPLR_F_DONE) && d.err[e]) flags |= MGPLR_F_ERROR;  // an auto-reset failed: the host raises (mgplr_get_errors)
       write_step_scalars(A, e, s, flags, (float)rew, fin_ret, fin_len);
       if (A.o.image_u8) rare_emit_u8(rows + lane, kWarpTile, pack(s), W, c.see_through, A.o.image_u8, e);
@@ -1332,7 +1344,11 @@ extern "C" int mgplr_venv_create(const mgplr_env_config *cfg, int32_t num_envs, 
   v->device = device;
   Dev &d = v->d;
   d.N = num_envs;
-  d.l2_hints = getenv("MGPLR_L2_HINTS") ? atoi(getenv("MGPLR_L2_HINTS")) : 1;
+  // bit 0: evict_last on level rows + hot records, evict_first on the observation bulk stores; bit 2: streaming (.cs) stores for
+  // the per-env scalars and streaming action loads; A/B only: bit 3 = no evict_first on the observations, bit 4 = evict_first
+  // on rows + hot records, bit 5 = no evict_last on them, bit 6 = evict_first on the hot records; bit 7: hot records evict_normal
+  // (default 133 = bits 0, 2, 7)
+  d.l2_hints = getenv("MGPLR_L2_HINTS") ? atoi(getenv("MGPLR_L2_HINTS")) : 133;
   if (getenv("MGPLR_L2_PERSIST_MB")) {
     // A/B knob: an L2 set-aside for persisting (evict_last) lines, cudaLimitPersistingL2CacheSize -- device-wide
     int max_persist = 0;
@@ -1583,6 +1599,7 @@ static int launch_step(mgplr_venv *v, const int64_t *action, int32_t reset_rando
                        const mgplr_step_out *out, cudaStream_t st) {
   StepArgs A;
   memset(&A, 0, sizeof(A));
+  A.stream_scalars = (v->d.l2_hints & 4) != 0;
   A.action = action; A.n_walls = n_walls; A.last_step = last_step;
   if (out) A.o = *out;
   return launch_step_args(v, A, reset_random, st);
@@ -1665,6 +1682,7 @@ extern "C" int mgplr_step_env_u8(mgplr_venv *v, const uint8_t *action, int32_t r
   if (!action) return fail(MGPLR_E_BADARG, "action is NULL");
   StepArgs A;
   memset(&A, 0, sizeof(A));
+  A.stream_scalars = (v->d.l2_hints & 4) != 0;
   A.action_u8 = action; A.n_walls = n_walls; A.last_step = last_step;
   if (out) A.o = *out;
   return launch_step_args(v, A, reset_random, st);
@@ -1712,6 +1730,7 @@ static int step_env_host_impl(mgplr_venv *v, const void *action_host_any, size_t
   const bool stage_flags = flags_host && !flags_map;
   StepArgs A;
   memset(&A, 0, sizeof(A));
+  A.stream_scalars = (v->d.l2_hints & 4) != 0;
   if (out_dev) A.o = *out_dev;
   if (narrow) A.action_u8 = (const uint8_t *)act; else A.action = act;
   A.last_step = last_step;
@@ -1766,6 +1785,7 @@ extern "C" int mgplr_rollout_ex(mgplr_venv *v, const uint8_t *actions, int32_t T
   if (!actions || T < 1) return fail(MGPLR_E_BADARG, "mgplr_rollout: bad arguments");
   StepArgs A;
   memset(&A, 0, sizeof(A));
+  A.stream_scalars = (v->d.l2_hints & 4) != 0;
   if (out_t0) A.o = *out_t0;
   A.last_step = last_step;  // applied to step T-1 only (k_rollout)
   const int tile = 64;

@@ -456,7 +456,7 @@ class CudaAdversarialVecEnv(object):
             ep_r = ep_l = None
             if nd:   # the finished episodes arrive as compact records: scatter them by env
                 rec = self._h_done_np[:nd * 16].view(self._done_dtype)
-                ep_r, ep_l = dict(zip(rec['env'].tolist(), rec['ep_return'])), dict(zip(rec['env'].tolist(), rec['ep_length']))
+                ep_r, ep_l = dict(zip(rec['env'].tolist(), rec['ep_return'])), dict(zip(rec['env'].tolist(), rec['ep_length'] & 0xffffff))   # (top byte: the env's flags)
         done = (flags & F_DONE) != 0
         infos = LazyInfos([_NO_INFO] * N)
         if ep_r is not None or flags.any():

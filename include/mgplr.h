@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MGPLR_ABI_VERSION 3
+#define MGPLR_ABI_VERSION 4
 
 #define MGPLR_E_BADARG (-1)
 #define MGPLR_E_UNSUPPORTED (-2)
@@ -163,14 +163,19 @@ typedef struct mgplr_done_record {
   int32_t env;        /* env index */
   float reward;       /* reward of the terminating step */
   float ep_return;    /* info['episode']['r'] */
-  int32_t ep_length;  /* info['episode']['l'] */
+  int32_t ep_length;  /* info['episode']['l'] in the low 24 bits, the step's MGPLR_F_* flags of this env in the top byte (ABI v4):
+                       * the record list alone tells the host everything the flags array does -- every env with a non-zero flag
+                       * is DONE -- so flags_host may be NULL and 1 byte per env less crosses PCIe per step */
 } mgplr_done_record;
+#define MGPLR_DONE_LENGTH(rec_ep_length) ((rec_ep_length) & 0xffffff)
+#define MGPLR_DONE_FLAGS(rec_ep_length) (((uint32_t)(rec_ep_length)) >> 24)
 
 /* The same transition driven from HOST buffers (the reference's calling convention: actions arrive as a CPU
  * tensor, adversarial_runner.py:512-517; done / infos go back to the host).  Observations, rewards and masks stay
  * in HBM at the `out_dev` destinations (rollout storage).  With PINNED host buffers (cudaHostAlloc /
  * cudaHostRegister / torch pin_memory) the call is one kernel launch + one stream synchronisation: the kernel reads
- * action i64 [N] straight from the caller's memory over PCIe, writes flags u8 [N] straight into flags_host and appends
+ * action i64 [N] straight from the caller's memory over PCIe, writes flags u8 [N] straight into flags_host (optional: NULL skips
+ * it -- the done records carry the flags of every env that has any) and appends
  * the (few) done records to a device-mapped pinned list owned by the handle.  Pageable buffers work too (staged
  * copies).  done_host receives min(*n_done_host, done_capacity) records in unspecified order.  Use one stream per
  * handle for these calls. */

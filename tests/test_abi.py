@@ -17,7 +17,7 @@ def test_library_exports_header_symbols():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for sym in declared:
         assert hasattr(L, sym), 'libmgplr.so does not export %s' % sym
-    assert L.mgplr_abi_version() == 3
+    assert L.mgplr_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_device():
