@@ -319,6 +319,36 @@ def test_extra_score_transforms_golden(transform):
         assert np.array_equal(s.seed_staleness, g['stale_after_' + k]), k
 
 
+@pytest.mark.parametrize('n,coef,n_unseen,n_draws', [(4000, 0.3, 800, 600), (37, 0.3, 5, 300), (4096, 0.1, 0, 4096), (500, 0.0, 100, 200),
+                                                    (64, 0.5, 62, 50), (64, 0.5, 63, 20), (300, 0.3, 30, 100)])
+def test_fast_sequential_draws_equal_the_general_path(monkeypatch, n, coef, n_unseen, n_draws):
+    """mgplr_plr_sample_replay's Fenwick-tree path (closed-form staleness between the draws of one call) against
+    the general block-wide path: same picks, same staleness afterwards -- long calls, repeated picks of the same slot (few seen
+    slots), unseen slots, no staleness mix, a single seen slot and all-zero staleness (preconditions fail -> general path)."""
+    from dcd_isaac_b200.level_sampler import LevelSampler
+    rs = np.random.RandomState(n + n_draws)
+    scores = rs.rand(n)
+    unseen = np.zeros(n)
+    unseen[rs.permutation(n)[:n_unseen]] = 1.0
+    stale = np.floor(rs.rand(n) * 40) if n != 300 else np.zeros(n)
+    res = []
+    for knob in ('0', '2'):
+        monkeypatch.setenv('MGPLR_REPLAY_FAST', knob)
+        s = LevelSampler([], None, None, num_actors=4, strategy='positive_value_loss', score_transform='rank', temperature=0.3,
+                         staleness_coef=coef, staleness_transform='power', staleness_temperature=1.0,
+                         sample_full_distribution=True, seed_buffer_size=n)
+        s.seed_scores[:] = scores
+        s.unseen_seed_weights[:] = unseen
+        s.seed_staleness[:] = stale
+        s.seeds[:] = np.arange(1, n + 1)
+        s.working_seed_buffer_size = n
+        np.random.seed(9)
+        res.append((np.array(s.sample_replay_levels(n_draws)), s.seed_staleness.copy()))
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])
+    assert len(np.unique(res[0][0])) < n_draws or n >= 4000   # (small buffers: slots are picked repeatedly)
+
+
 def _assert_weights_match(w, ref, s, cyc):
     """Weights equal the reference's up to the order INSIDE groups of exactly equal scores: the reference ranks with
     numpy's default unstable argsort (level_sampler.py:766), so which member of a tie group gets which rank is
