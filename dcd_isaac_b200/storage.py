@@ -192,11 +192,13 @@ class RolloutStorage(object):
             return {k: self.obs[k][idx] for k in self.obs.keys()}
         return self.obs[idx]
 
+    def _obs_buffers(self):
+        return list(self.obs.values()) if self.is_dict_obs else [self.obs]
+
     def copy_obs_to_index(self, obs, index):
-        if self.is_dict_obs:
-            [self.obs[k][index].copy_(obs[k]) for k in self.obs.keys()]
-        else:
-            self.obs[index].copy_(obs)
+        src = [obs[k] for k in self.obs] if self.is_dict_obs else [obs]
+        for buf, o in zip(self._obs_buffers(), src):
+            buf[index].copy_(o)
 
     def insert(self, obs, recurrent_hidden_states, actions, action_log_probs, action_log_dist, value_preds, rewards, masks,
                bad_masks, level_seeds=None, cliffhanger_masks=None):
@@ -245,14 +247,9 @@ class RolloutStorage(object):
             self.truncated_obs[self.step + 1][index].copy_(as_t(obs))
 
     def after_update(self):
-        if self.is_dict_obs:
-            [self.obs[k][0].copy_(self.obs[k][-1]) for k in self.obs.keys()]
-        else:
-            self.obs[0].copy_(self.obs[-1])
-        self.recurrent_hidden_states[0].copy_(self.recurrent_hidden_states[-1])
-        self.masks[0].copy_(self.masks[-1])
-        self.bad_masks[0].copy_(self.bad_masks[-1])
-        self.cliffhanger_masks[0].copy_(self.cliffhanger_masks[-1])
+        """The last slot of every [T+1] buffer becomes slot 0 of the next rollout (algos/storage.py:195-204)."""
+        for buf in self._obs_buffers() + [self.recurrent_hidden_states, self.masks, self.bad_masks, self.cliffhanger_masks]:
+            buf[0].copy_(buf[-1])
 
     def replace_final_return(self, returns):
         self.rewards[-1] = returns
@@ -282,29 +279,26 @@ class RolloutStorage(object):
                 self.truncated_value_preds[steps, proc] = self.model.get_value(obs, rnn_hxs, masks)
         return self.truncated_value_preds
 
-    def _value_preds_for_returns(self, next_value):
+    def _bootstrap_values(self, next_value):
+        """-> (values the returns bootstrap from, their PopArt-denormalised form or None): the truncated-value buffer under
+        use_proper_time_limits, else value_preds (algos/storage.py:238-249,260-270)."""
         self.value_preds[-1] = next_value
-        value_preds = self.value_preds
-        if self.use_proper_time_limits:
-            self._compute_truncated_value_preds()
-            value_preds = self.truncated_value_preds
+        v = self._compute_truncated_value_preds() if self.use_proper_time_limits else self.value_preds
+        denorm = None
         if self.use_popart:
-            self.denorm_value_preds = self.model.popart.denormalize(value_preds)
-            value_preds = self.denorm_value_preds
-        return value_preds.contiguous()
+            denorm = self.denorm_value_preds = self.model.popart.denormalize(v)
+        return v, denorm
+
+    def _value_preds_for_returns(self, next_value):
+        v, denorm = self._bootstrap_values(next_value)
+        return (v if denorm is None else denorm).contiguous()
 
     def compute_gae_returns(self, returns_buffer, next_value, gamma, gae_lambda):
         gae_returns(self.rewards, self._value_preds_for_returns(next_value), self.masks, returns_buffer, gamma, gae_lambda)
 
     def compute_discounted_returns(self, returns_buffer, next_value, gamma):
-        self.value_preds[-1] = next_value
-        value_preds = self.value_preds
-        if self.use_proper_time_limits:
-            self._compute_truncated_value_preds()
-            value_preds = self.truncated_value_preds
-        if self.use_popart:
-            self.denorm_value_preds = self.model.popart.denormalize(value_preds)
-        self.returns[-1] = value_preds[-1]  # (the reference bootstraps from the un-denormalised buffer, `:272`)
+        v, _ = self._bootstrap_values(next_value)
+        self.returns[-1] = v[-1]  # (the reference bootstraps from the un-denormalised buffer, `:272`)
         discounted_returns(self.rewards, self.masks, returns_buffer, gamma)
 
     def compute_returns(self, next_value, use_gae, gamma, gae_lambda):
