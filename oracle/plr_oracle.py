@@ -173,6 +173,45 @@ def sample_replay(scores, staleness, unseen, u, **kw):
     return np.array(idx), staleness
 
 
+def sample_replay_closed_form(scores, staleness, unseen, u, **kw):
+    """The same sequential draws WITHOUT recomputing the weights: the algebra behind the Fenwick-tree path of k_sample_replay
+    (DESIGN.md 4.4), restated with plain prefix sums so that the CPU suite checks it against sample_replay above.
+    Valid for staleness transform `power` with temperature 1 and S_0 > 0, >= 2 seen slots (or no staleness mix)."""
+    coef = kw.get('staleness_coef', 0.3)
+    assert kw.get('staleness_transform', 'power') == 'power' and kw.get('staleness_temperature', 1.0) == 1.0
+    seen = 1.0 - unseen
+    # normalised, masked score weights: constant during the call (the power transform's eps depends on the REAL coef)
+    eps = 0 if coef > 0 else 1e-3
+    if kw.get('score_transform', 'rank') == 'eps_greedy':
+        eps = kw.get('sampler_eps', 0.05)
+    a = _transform(kw.get('score_transform', 'rank'), kw.get('temperature', 0.3), scores, eps) * seen
+    a = a / a.sum() if a.sum() > 0 else seen / max(1.0, seen.sum())
+    PA, PS, PN = np.cumsum(a), np.cumsum(staleness * seen), np.cumsum(seen)
+    S0, n_seen, n = PS[-1], PN[-1], len(scores)
+    assert coef == 0 or (S0 > 0 and n_seen >= 2)
+    corr = np.zeros(n)            # s0_j + k_j + 1 for picked slots
+    lastk = np.full(n, -1)
+    idx = []
+    for t, uu in enumerate(u):
+        if coef > 0:
+            St = S0 + t * n_seen - corr.sum()
+            cdf = (1 - coef) * PA + coef / St * (PS + t * PN - np.cumsum(corr))
+        else:
+            cdf = PA.copy()
+        cdf = cdf / cdf[-1]
+        i = min(int(np.searchsorted(cdf, uu, side='right')), n - 1)
+        idx.append(i)
+        if coef > 0:
+            if seen[i] > 0:
+                corr[i] = staleness[i] + t + 1
+            lastk[i] = t
+    T = len(u)
+    final = staleness.copy()
+    if coef > 0:
+        final = np.where(lastk >= 0, T - 1 - lastk, staleness + T).astype(staleness.dtype)
+    return np.array(idx), final
+
+
 class BufferOracle(object):
     """Sequential restatement of the sampler's buffer bookkeeping for the full-distribution (robust PLR / ACCEL) mode:
     observe_external_unseen_sample (level_sampler.py:645-659), the per-record score update with staging -> working

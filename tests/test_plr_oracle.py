@@ -49,6 +49,29 @@ def test_extra_score_transforms():
             assert np.array_equal(stale, g['stale_after_' + k]), k
 
 
+def test_closed_form_sequential_draws():
+    """The algebra of the Fenwick-tree draw path (staleness in closed form between the draws of one call):
+    same picks and final staleness as recomputing sample_weights() before every draw -- on the recorded reference
+    fixtures and on random cases with repeated picks, unseen slots and no staleness mix."""
+    g = golden('plr_weights.npz')
+    for tag in ('n4000', 'n4000_t01', 'n37_nostale'):
+        temp, sc, st = g['params_' + tag]
+        kw = dict(score_transform='rank', temperature=temp, staleness_coef=sc, staleness_temperature=st)
+        idx, stale = po.sample_replay_closed_form(g['scores_' + tag], g['stale_' + tag], g['unseen_' + tag], g['u_' + tag], **kw)
+        assert np.array_equal(idx, g['picks_' + tag]) and np.array_equal(stale, g['stale_after_' + tag]), tag
+    rs = np.random.RandomState(0)
+    for n, coef, n_unseen, n_draws, tr in [(4000, 0.3, 800, 400, 'rank'), (37, 0.3, 5, 300, 'rank'), (500, 0.0, 100, 200, 'rank'),
+                                           (64, 0.5, 60, 80, 'power'), (300, 0.1, 0, 300, 'softmax')]:
+        scores, unseen = rs.rand(n), np.zeros(n)
+        unseen[rs.permutation(n)[:n_unseen]] = 1.0
+        stale, u = np.floor(rs.rand(n) * 40), rs.rand(n_draws)
+        kw = dict(score_transform=tr, temperature=0.3, staleness_coef=coef, staleness_temperature=1.0)
+        i1, s1 = po.sample_replay(scores, stale, unseen, u, **kw)
+        i2, s2 = po.sample_replay_closed_form(scores, stale, unseen, u, **kw)
+        assert np.array_equal(i1, i2) and np.array_equal(s1, s2), (n, coef, tr)
+        assert n >= 4000 or len(np.unique(i1)) < n_draws   # small buffers: slots are picked repeatedly
+
+
 def test_storage_returns_and_value_loss():
     """discounted returns bit-exact, batched value loss to 1e-6 against the executed reference RolloutStorage."""
     g = golden('plr_storage.npz')
